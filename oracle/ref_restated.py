@@ -1,0 +1,380 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's retrieval hot path.
+
+This file is the *checker*.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
+`--impl reference` legs may import it; the product (rag_docvqa_b200/) never does.
+
+Parity status: PINNED.  The reference (Pikurrot/RAG-DocVQA) has no tests or golden vectors of its
+own, so the pins were manufactured: oracle/make_golden.py imports the unmodified
+reference in the build container (oracle/ref_import.py), runs it on seeded inputs and freezes its
+outputs under tests/golden/; tests/test_oracle_golden.py checks every function below against those
+files (bit-exact: same torch CPU ops in the same order), and -- when /root/reference is present --
+against the live reference as well.
+
+Each function cites the reference lines it restates.  Floating-point work uses the same torch CPU
+operators the reference calls (torch.norm / matmul / topk / F.normalize / bmm), so results are
+bit-identical to the reference on the same torch build; integer / list work is plain Python.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------
+# a4: cosine score          reference: src/_modules.py:1978-1997 (Retriever._get_similarities)
+# --------------------------------------------------------------------------------------
+def score(text_embeddings: Sequence[torch.Tensor], question_embeddings: torch.Tensor) -> List[torch.Tensor]:
+    out = []
+    for b, emb in enumerate(text_embeddings):
+        q = question_embeddings[b]
+        chunk_norms = torch.norm(emb, dim=-1)            # :1990
+        q_norm = torch.norm(q)                            # :1991
+        dots = torch.matmul(emb, q)                       # :1992
+        out.append(dots / (chunk_norms * q_norm + 1e-8))  # :1993  eps on the *product* of norms
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a6: per-document top-k    reference: src/_modules.py:2015-2016, :2408 (torch.topk)
+# --------------------------------------------------------------------------------------
+def topk_reference(sim: torch.Tensor, k: int) -> torch.Tensor:
+    """Exactly what the reference calls; tie order is whatever torch.topk gives."""
+    k_min = min(k, len(sim))                              # :2015
+    return torch.topk(sim, k=k_min, dim=-1).indices       # :2016
+
+
+def order_key(values: np.ndarray) -> np.ndarray:
+    """fp32 -> uint32 key whose unsigned order is the float order with torch.topk's conventions:
+    NaN (either sign) greatest, -0.0 == +0.0."""
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    u = v.view(np.uint32).copy()
+    u[u == np.uint32(0x80000000)] = 0                     # -0.0 -> +0.0
+    neg = (u >> 31).astype(bool)
+    key = np.where(neg, ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+    key[np.isnan(v)] = np.uint32(0xFFFFFFFF)
+    return key
+
+
+def topk_lowest_index(sim: Union[torch.Tensor, np.ndarray], k: int) -> np.ndarray:
+    """The contract north_star mandates: descending score, ties broken by LOWEST index.
+    Equal to torch.topk wherever scores are distinct."""
+    v = sim.detach().cpu().numpy() if isinstance(sim, torch.Tensor) else np.asarray(sim)
+    n = v.shape[0]
+    k_min = min(k, n)
+    if k_min == 0:
+        return np.zeros(0, dtype=np.int64)
+    packed = (order_key(v).astype(np.uint64) << np.uint64(32)) | \
+        (np.uint64(0xFFFFFFFF) - np.arange(n, dtype=np.uint64))
+    order = np.argsort(packed, kind="stable")[::-1]
+    return order[:k_min].astype(np.int64)
+
+
+# --------------------------------------------------------------------------------------
+# a8: compact chunks        reference: src/_modules.py:1102-1132 (Chunker.compact_chunks)
+# --------------------------------------------------------------------------------------
+def compact_chunks(words_text_chunks, words_boxes_chunks):
+    texts, bboxes = [], []
+    for doc_words, doc_boxes in zip(words_text_chunks, words_boxes_chunks):
+        doc_texts, doc_bboxes = [], []
+        for chunk_words, chunk_boxes in zip(doc_words, doc_boxes):
+            doc_texts.append(" ".join(chunk_words))
+            if len(chunk_boxes):
+                bbox = [min(bx[0] for bx in chunk_boxes), min(bx[1] for bx in chunk_boxes),
+                        max(bx[2] for bx in chunk_boxes), max(bx[3] for bx in chunk_boxes)]
+            else:
+                bbox = [0, 0, 1, 1]                       # :1126-1127
+            doc_bboxes.append(bbox)
+        texts.append(doc_texts)
+        bboxes.append(doc_bboxes)
+    return texts, bboxes
+
+
+# --------------------------------------------------------------------------------------
+# a9: crop rectangle        reference: src/_modules.py:2102-2121
+# --------------------------------------------------------------------------------------
+def crop_rectangle(bbox, page_width: int, page_height: int):
+    x0 = int(bbox[0] * page_width)                        # int() truncates toward zero  :2110-2113
+    y0 = int(bbox[1] * page_height)
+    x1 = int(bbox[2] * page_width)
+    y1 = int(bbox[3] * page_height)
+    return [min(x0, x1), min(y0, y1), max(x0, x1), max(y0, y1)]  # :2115-2118
+
+
+# --------------------------------------------------------------------------------------
+# a7: gather of the hits    reference: src/_modules.py:1999-2153 (Retriever._get_top_k)
+# --------------------------------------------------------------------------------------
+def gather_hits(topk_indices: Sequence[Sequence[int]], words_text_chunks, words_box_chunks,
+                layout_labels_chunks, images, page_indices, include_surroundings: int = 0,
+                reorder_chunks: bool = False, crop: bool = True):
+    """Given per-document hit indices in rank order, rebuild the eight list outputs.
+    With crop=False the 7th output holds crop rectangles instead of PIL images."""
+    B = len(topk_indices)
+    s = include_surroundings
+    out_words, out_boxes, out_labels, out_pages = [], [], [], []
+    for b in range(B):
+        hits = [int(i) for i in topk_indices[b]]
+        out_labels.append([layout_labels_chunks[b][i] for i in hits])   # :2019
+        out_pages.append([page_indices[b][i] for i in hits])            # :2020
+        # per-page concatenation of ALL chunks in chunk order  (:2032-2050)
+        page_words, page_boxes, span, seen = {}, {}, {}, {}
+        for c in range(len(words_text_chunks[b])):
+            p = page_indices[b][c]
+            if p not in page_words:
+                page_words[p], page_boxes[p], seen[p] = [], [], set()
+            start = len(page_words[p])
+            page_words[p].extend(words_text_chunks[b][c])
+            page_boxes[p].extend(words_box_chunks[b][c])
+            span[c] = (start, start + len(words_text_chunks[b][c]))
+        doc_words, doc_boxes = [], []
+        for i in hits:                                                  # :2056-2087
+            p = page_indices[b][i]
+            start, end = span[i]
+            lo = max(0, start - s)
+            hi = min(len(page_words[p]), end + s)
+            fresh = [j for j in range(lo, hi) if j not in seen[p]]     # dedup vs higher-ranked hits
+            seen[p].update(fresh)
+            doc_words.append([page_words[p][j] for j in fresh])
+            doc_boxes.append([page_boxes[p][j] for j in fresh])
+        out_words.append(doc_words)
+        out_boxes.append(doc_boxes)
+    out_text, out_bbox = compact_chunks(out_words, out_boxes)           # :2093
+    out_word_labels = [[[out_labels[b][i]] * len(out_words[b][i]) for i in range(len(out_words[b]))]
+                       for b in range(B)]                               # :2094-2100
+    out_patches = []
+    for b in range(B):                                                  # :2102-2121
+        doc_patches = []
+        for i, p in enumerate(out_pages[b]):
+            page = images[b][p]
+            rect = crop_rectangle(out_bbox[b][i], page.width, page.height)
+            doc_patches.append(page.crop(rect) if crop else rect)
+        out_patches.append(doc_patches)
+    if reorder_chunks:                                                  # :2129-2142
+        for b in range(B):
+            order = sorted(range(len(out_pages[b])),
+                           key=lambda i: (out_pages[b][i], out_bbox[b][i][1], out_bbox[b][i][0]))
+            for lst in (out_text, out_bbox, out_labels, out_words, out_boxes, out_word_labels,
+                        out_patches, out_pages):
+                lst[b] = [lst[b][i] for i in order]
+    return (out_text, out_bbox, out_labels, out_words, out_boxes, out_word_labels, out_patches, out_pages)
+
+
+# --------------------------------------------------------------------------------------
+# a11: Retriever.retrieve   reference: src/_modules.py:2155-2180
+# --------------------------------------------------------------------------------------
+def retrieve(text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
+             layout_labels_chunks, images, page_indices, k: int = 10, include_surroundings: int = 0,
+             reorder_chunks: bool = False, deterministic_ties: bool = False, crop: bool = True):
+    sims = score(text_embeddings, question_embeddings)
+    if deterministic_ties:
+        hits = [topk_lowest_index(s_b, k) for s_b in sims]
+    else:
+        hits = [topk_reference(s_b, k).tolist() for s_b in sims]
+    lists = gather_hits(hits, words_text_chunks, words_box_chunks, layout_labels_chunks, images,
+                        page_indices, include_surroundings, reorder_chunks, crop=crop)
+    return (*lists, sims)
+
+
+# --------------------------------------------------------------------------------------
+# a1: masked mean pooling   reference: src/_model_utils.py:49-61
+# --------------------------------------------------------------------------------------
+def mean_pooling(embs: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+    expanded = attention_mask.unsqueeze(-1).expand(embs.size())         # :56
+    summed = (embs * expanded).sum(dim=1)                               # :57-58
+    counts = attention_mask.sum(dim=1).unsqueeze(-1).clamp(min=1e-9)    # :59
+    return summed / counts                                              # :60
+
+
+# --------------------------------------------------------------------------------------
+# a5: MaxSim late interaction   reference: src/utils.py:442-458, src/_modules.py:2191-2205
+# --------------------------------------------------------------------------------------
+def late_interaction(query: torch.Tensor, patches: torch.Tensor) -> torch.Tensor:
+    qn = F.normalize(query, p=2, dim=-1)                                # :445
+    pn = F.normalize(patches, p=2, dim=-1)                              # :446
+    S = torch.bmm(qn.expand(pn.size(0), -1, -1), pn.transpose(1, 2))    # :448-451
+    return S.max(dim=-1).values.sum(dim=-1)                             # :454-457
+
+
+def late_interaction_f64(query: torch.Tensor, patches: torch.Tensor) -> torch.Tensor:
+    """Same math in float64 -- the yardstick for the fp32 GPU kernel's summation-order error."""
+    return late_interaction(query.double(), patches.double())
+
+
+def visual_scores(patch_embeddings, question_embeddings):
+    return [late_interaction(question_embeddings[b].unsqueeze(0), patch_embeddings[b])
+            for b in range(len(patch_embeddings))]
+
+
+# --------------------------------------------------------------------------------------
+# a10: visual top-k decode  reference: src/_modules.py:2207-2282, 2284-2384, 2386-2450
+# --------------------------------------------------------------------------------------
+def surrounding_cells(row: int, col: int, n_rows: int, n_cols: int, include_surroundings):
+    cells = set()
+    if isinstance(include_surroundings, tuple) and len(include_surroundings) == 2:   # :2237-2244
+        rx, ry = include_surroundings
+        for r in range(row - ry, row + ry + 1):
+            for c in range(col - rx, col + rx + 1):
+                cells.add((r, c))
+    else:                                                                            # :2246-2274
+        level, phase = include_surroundings // 3, include_surroundings % 3
+        for r in range(row - level, row + level + 1):
+            for c in range(col - level, col + level + 1):
+                cells.add((r, c))
+        if phase > 0:
+            for r in range(row - level, row + level + 1):
+                cells.add((r, col - level - 1))
+                cells.add((r, col + level + 1))
+        if phase > 1:
+            for c in range(col - level, col + level + 1):
+                cells.add((row - level - 1, c))
+                cells.add((row + level + 1, c))
+    return {(r, c) for r, c in cells if 0 <= r < n_rows and 0 <= c < n_cols}
+
+
+def rectangles_overlap(a, b) -> bool:                                                 # src/utils.py:460-463
+    return a[0] < b[2] and a[2] > b[0] and a[1] < b[3] and a[3] > b[1]
+
+
+def merged_rectangles(cells, matrix_shapes, patches_xyxy):
+    """cells: iterable of (group, row, col).  Returns {group: sorted list of merged rectangles}
+    (bounding box per connected component of the strict-overlap graph; :2331-2382)."""
+    by_group = {}
+    for g, r, c in cells:
+        n_rows, n_cols = matrix_shapes[g]
+        if 0 <= r < n_rows and 0 <= c < n_cols:
+            by_group.setdefault(g, []).append(list(patches_xyxy[g][r]))
+    out = {}
+    for g, rects in by_group.items():
+        parent = list(range(len(rects)))
+
+        def find(i):
+            while parent[i] != i:
+                parent[i] = parent[parent[i]]
+                i = parent[i]
+            return i
+        for i in range(len(rects)):
+            for j in range(i + 1, len(rects)):
+                if rectangles_overlap(rects[i], rects[j]):
+                    parent[find(i)] = find(j)
+        comps = {}
+        for i, rc in enumerate(rects):
+            comps.setdefault(find(i), []).append(rc)
+        out[g] = sorted([min(x[0] for x in comp), min(x[1] for x in comp),
+                         max(x[2] for x in comp), max(x[3] for x in comp)] for comp in comps.values())
+    return out
+
+
+def visual_decode(topk_indices, patches_flatten_indices, matrix_shapes, patches_xyxy,
+                  include_surroundings=0, mode: str = "horizontal"):
+    """Per document: hit strip index -> (group,row,0) -> neighbourhood -> merged crop rectangles.
+    Returns (rects_per_doc: {group: [rect...]}, groups_per_doc: sorted list).  The reference returns
+    PIL crops and page ids in Python-set iteration order (:2428, :2445); compare as multisets."""
+    rects_all, groups_all = [], []
+    for b, hits in enumerate(topk_indices):
+        flat = np.asarray(patches_flatten_indices[b])
+        if len(flat) == 0:                                                            # :2403-2406
+            rects_all.append({})
+            groups_all.append([])
+            continue
+        cells = set()
+        for idx in hits:
+            idx = int(idx)
+            group = int(flat[idx])                                                    # :2411
+            row = idx - int(np.count_nonzero(flat < group))                           # :2412
+            if mode == "square":
+                raise NotImplementedError()                                           # :2413-2414
+            n_rows, n_cols = matrix_shapes[b][group]
+            for r, c in surrounding_cells(row, 0, n_rows, n_cols, include_surroundings):
+                cells.add((group, r, c))
+        rects_all.append(merged_rectangles(cells, matrix_shapes[b], patches_xyxy[b]))
+        groups_all.append(sorted({g for g, _, _ in cells}))
+    return rects_all, groups_all
+
+
+# --------------------------------------------------------------------------------------
+# a12: generator-input assembly   reference: src/utils.py:233-253 (flatten),
+#                                  src/VT5.py:141-192 (prepare_inputs_for_vqa, ids/boxes/mask part)
+# --------------------------------------------------------------------------------------
+def flatten(lst, add_sep_token: Optional[str] = None):
+    if add_sep_token is None:
+        return [item for sub in lst for item in sub]
+    flat = []
+    for i, sub in enumerate(lst):
+        if len(sub) == 0:
+            continue
+        if i > 0:
+            if isinstance(sub[0], str):
+                flat.append(add_sep_token)
+            elif isinstance(sub[0], list):
+                flat.append([0, 0, 0, 0])
+            elif isinstance(sub[0], int):
+                flat.append(0)
+        flat.extend(sub)
+    return flat
+
+
+def vt5_pack(prompt_token_ids: Sequence[Sequence[int]], words, boxes, word_tokens,
+             layout_labels=None, max_source_length: int = 512, eos_id: int = 1, pad_id: int = 0):
+    """Packed generator tensors from already-flattened per-document word/box lists.
+    `prompt_token_ids[b]` are the prompt ids WITHOUT the trailing EOS (src/VT5.py:147-148);
+    `word_tokens(word)` returns the word's ids without EOS (:160)."""
+    B = len(words)
+    ids_all, boxes_all, lab_all = [], [], []
+    longest = 0
+    for b in range(B):
+        ids = list(prompt_token_ids[b])
+        bxs = [[0, 0, 1000, 1000]] * len(ids)                                         # :133, :151
+        labs = [4] * len(ids)                                                         # :136, :149
+        for i, word in enumerate(words[b]):
+            toks = word_tokens(word)
+            ids.extend(toks)
+            bxs.extend((np.array([boxes[b][i]] * len(toks)) * 1000).tolist())         # :162 (float64)
+            if layout_labels is not None:
+                labs.extend([layout_labels[b][i]] * len(toks))
+        ids_all.append(ids[:max_source_length - 1] + [eos_id])                        # :166
+        if len(bxs[:max_source_length - 1]):
+            boxes_all.append(np.concatenate([np.array(bxs[:max_source_length - 1], dtype=np.float64),
+                                             np.zeros((1, 4))]))                      # :167
+        else:
+            boxes_all.append(np.zeros((1, 4)))
+        lab_all.append(labs[:max_source_length - 1] + [4])                            # :169
+        longest = min(max(longest, len(ids) + 1), max_source_length)                  # :170
+    t_ids = torch.full([B, longest], pad_id, dtype=torch.long)                        # :173
+    t_boxes = torch.zeros([B, longest, 4], dtype=torch.long)                          # :174
+    t_labs = torch.full([B, longest], 4, dtype=torch.long)                            # :176
+    t_mask = torch.zeros([B, longest], dtype=torch.long)                              # :177
+    for b in range(B):
+        n = len(ids_all[b])
+        t_ids[b, :n] = torch.LongTensor(ids_all[b])
+        t_boxes[b, :n] = torch.from_numpy(boxes_all[b][:n])                           # float64 -> int64 truncates
+        if layout_labels is not None:
+            t_labs[b, :n] = torch.LongTensor(lab_all[b])
+        t_mask[b, :n] = 1
+    return t_ids, t_boxes, t_mask, (t_labs if layout_labels is not None else None)
+
+
+# --------------------------------------------------------------------------------------
+# corpus mode (C5): sharded top-k + merge   (no reference counterpart: north_star config 5;
+#                   the scoring formula is a4's, applied to Q questions x N chunks)
+# --------------------------------------------------------------------------------------
+def corpus_scores(E: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
+    """(Q, N) cosine with a4's eps convention, in float32 math on float32 copies of E, Q."""
+    E32, Q32 = E.float(), Q.float()
+    return (Q32 @ E32.T) / (Q32.norm(dim=-1)[:, None] * E32.norm(dim=-1)[None, :] + 1e-8)
+
+
+def merge_topk(cand_scores: np.ndarray, cand_idx: np.ndarray, k: int):
+    """cand_*: (Q, m) candidates (idx < 0 = empty slot) -> (Q, k) by (score desc, idx asc)."""
+    Qn = cand_scores.shape[0]
+    out_s = np.full((Qn, k), -np.inf, dtype=np.float32)
+    out_i = np.full((Qn, k), -1, dtype=np.int64)
+    for q in range(Qn):
+        valid = cand_idx[q] >= 0
+        s, i = cand_scores[q][valid], cand_idx[q][valid].astype(np.int64)
+        key = (order_key(s).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - i.astype(np.uint64))
+        order = np.argsort(key, kind="stable")[::-1][:k]
+        out_s[q, :len(order)] = s[order]
+        out_i[q, :len(order)] = i[order]
+    return out_s, out_i

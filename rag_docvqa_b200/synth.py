@@ -1,0 +1,204 @@
+"""Seeded synthetic inputs shaped like the workloads BASELINE.json names.
+
+Nothing here is reference code: the reference ships no data generator.  The shapes follow
+the batch dict the reference's retrieval stage consumes (src/RAGVT5.py:208-252):
+
+  text_embeddings        List[B] of (n_b, d) fp32      BiEncoder.batch_forward  (src/_modules.py:1415)
+  question_embeddings    (B, d) fp32                   BiEncoder.forward        (src/_modules.py:1457)
+  words_text_chunks      [B][n_b][w] str               Chunker.get_chunks       (src/_modules.py:1095)
+  words_box_chunks       [B][n_b][w][4] float 0..1
+  layout_labels_chunks   [B][n_b] int
+  page_indices           [B][n_b] int
+  images                 [B][pages] PIL.Image
+
+Workload ids: C1..C5 are BASELINE.json `configs[0..4]`.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+SEED_BASE = 1234
+
+
+@dataclasses.dataclass(frozen=True)
+class Workload:
+    name: str
+    config_id: int
+    docs: int            # B: one question per document
+    min_pages: int
+    max_pages: int
+    chunks_per_page: int
+    dim: int
+    k: int
+
+
+WORKLOADS: Dict[str, Workload] = {
+    # configs[0]: SP-DocVQA-shaped, the reference's own CPU-runnable case
+    "C1": Workload("C1", 1, 1, 1, 1, 30, 384, 5),
+    # configs[1]: MP-DocVQA-shaped batch (the bench headline)
+    "C2": Workload("C2", 2, 64, 1, 20, 30, 384, 5),
+    # configs[2]: DUDE / MMLongBenchDoc-shaped long documents
+    "C3": Workload("C3", 3, 256, 20, 200, 50, 768, 10),
+}
+
+
+def _gen(seed: int, device="cpu") -> torch.Generator:
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return g
+
+
+def doc_sizes(w: Workload, seed: Optional[int] = None, ragged_edge_cases: bool = True,
+              full: bool = False) -> List[int]:
+    """Number of chunks per document.  `full=True` gives every doc max_pages pages (the
+    algorithmic-bytes figure in BASELINE.md assumes this)."""
+    seed = SEED_BASE + w.config_id if seed is None else seed
+    rng = np.random.RandomState(seed)
+    if full:
+        pages = np.full(w.docs, w.max_pages)
+    else:
+        pages = rng.randint(w.min_pages, w.max_pages + 1, size=w.docs)
+    sizes = (pages * w.chunks_per_page).astype(np.int64)
+    if ragged_edge_cases and w.docs >= 8 and not full:
+        sizes[3] = 0            # an empty document  (src/_modules.py:1463-1464)
+        sizes[5] = max(1, w.k - 2)  # fewer chunks than k  (src/_modules.py:2015)
+    return [int(s) for s in sizes]
+
+
+def make_embeddings(sizes: List[int], dim: int, seed: int, device="cpu", normalised: bool = True,
+                    dup_frac: float = 0.01, dtype=torch.float32):
+    """Chunk and question embeddings with a shared mean direction (cosines cluster ~0.2-0.6,
+    like real sentence embedders) and `dup_frac` exact duplicate rows per document (repeated
+    headers/footers), which exercise the lowest-index tie-break."""
+    g = _gen(seed, device)
+    B = len(sizes)
+    u = torch.randn(dim, generator=g, device=device)
+    u = u / u.norm()
+    docs = []
+    for n in sizes:
+        e = torch.randn(n, dim, generator=g, device=device) / (dim ** 0.5) + 0.5 * u
+        if normalised and n:
+            e = e / e.norm(dim=-1, keepdim=True)
+        n_dup = int(n * dup_frac)
+        if n_dup:
+            src = torch.randint(0, n, (n_dup,), generator=g, device=device)
+            dst = torch.randint(0, n, (n_dup,), generator=g, device=device)
+            e[dst] = e[src].clone()
+        docs.append(e.to(dtype).contiguous())
+    q = torch.randn(B, dim, generator=g, device=device) / (dim ** 0.5) + 0.5 * u
+    if normalised:
+        q = q / q.norm(dim=-1, keepdim=True)
+    return docs, q.to(dtype).contiguous()
+
+
+def make_page_indices(sizes: List[int], chunks_per_page: int) -> List[List[int]]:
+    return [[i // chunks_per_page for i in range(n)] for n in sizes]
+
+
+def make_words(sizes: List[int], seed: int, min_words: int = 40, max_words: int = 72,
+               vocab: int = 5000, empty_chunk_every: int = 0):
+    """Per-chunk word strings and boxes (plain Python lists, the reference's format).
+    Returns (words_text_chunks, words_box_chunks, layout_labels_chunks)."""
+    rng = np.random.RandomState(seed)
+    words_all, boxes_all, labels_all = [], [], []
+    for n in sizes:
+        words_doc, boxes_doc = [], []
+        for c in range(n):
+            w = int(rng.randint(min_words, max_words + 1))
+            if empty_chunk_every and c % empty_chunk_every == empty_chunk_every - 1:
+                w = 0
+            ids = rng.randint(0, vocab, size=w)
+            x0 = rng.uniform(0.0, 0.9, size=w)
+            y0 = rng.uniform(0.0, 0.95, size=w)
+            x1 = x0 + rng.uniform(0.005, 0.1, size=w)
+            y1 = y0 + rng.uniform(0.005, 0.05, size=w)
+            words_doc.append(["w%d" % i for i in ids])
+            boxes_doc.append(np.stack([x0, y0, x1, y1], axis=1).tolist() if w else [])
+        words_all.append(words_doc)
+        boxes_all.append(boxes_doc)
+        labels_all.append([1 + (c % 3 == 0) * 2 for c in range(n)])  # labels in {1, 3}
+    return words_all, boxes_all, labels_all
+
+
+def make_images(sizes: List[int], chunks_per_page: int, width: int = 850, height: int = 1100,
+                ragged_sizes: bool = False):
+    """One blank-ish RGB page per page index (PIL).  Content is a cheap gradient so crops differ."""
+    from PIL import Image
+    out = []
+    for b, n in enumerate(sizes):
+        n_pages = max(1, -(-n // chunks_per_page))
+        pages = []
+        for p in range(n_pages):
+            w = width + (17 * p if ragged_sizes else 0)
+            h = height - (13 * p if ragged_sizes else 0)
+            arr = np.empty((h, w, 3), dtype=np.uint8)
+            arr[..., 0] = (np.arange(w, dtype=np.uint32) * 255 // max(1, w - 1)).astype(np.uint8)[None, :]
+            arr[..., 1] = (np.arange(h, dtype=np.uint32) * 255 // max(1, h - 1)).astype(np.uint8)[:, None]
+            arr[..., 2] = (b * 37 + p * 11) % 256
+            pages.append(Image.fromarray(arr, "RGB"))
+        out.append(pages)
+    return out
+
+
+def make_text_batch(name: str, with_lists: bool = False, device="cpu", normalised: bool = True,
+                    seed: Optional[int] = None, docs: Optional[int] = None, full: bool = False,
+                    dup_frac: float = 0.01, ragged_edge_cases: bool = True, with_images: bool = True):
+    """One batch of workload `name` (C1/C2/C3).  `docs` overrides B (for slices)."""
+    w = WORKLOADS[name]
+    if docs is not None:
+        w = dataclasses.replace(w, docs=docs)
+    seed = SEED_BASE + w.config_id if seed is None else seed
+    sizes = doc_sizes(w, seed, ragged_edge_cases=ragged_edge_cases, full=full)
+    emb, q = make_embeddings(sizes, w.dim, seed, device=device, normalised=normalised, dup_frac=dup_frac)
+    batch = dict(workload=w, sizes=sizes, text_embeddings=emb, question_embeddings=q,
+                 page_indices=make_page_indices(sizes, w.chunks_per_page))
+    if with_lists:
+        words, boxes, labels = make_words(sizes, seed + 7)
+        batch.update(words_text_chunks=words, words_box_chunks=boxes, layout_labels_chunks=labels)
+        if with_images:
+            batch["images"] = make_images(sizes, w.chunks_per_page)
+    return batch
+
+
+def make_token_batch(n: int, dim: int, seed: int, device="cpu", mean_len: float = 96.0,
+                     std_len: float = 24.0, min_len: int = 8, max_len: int = 512,
+                     all_pad_rows: int = 0):
+    """Token embeddings + int64 right-padded attention mask, the inputs of mean_pooling
+    (src/_model_utils.py:49; produced at src/_modules.py:1466-1473)."""
+    g = _gen(seed, device)
+    lens = torch.clamp(torch.round(torch.randn(n, generator=g, device=device) * std_len + mean_len),
+                       min_len, max_len).to(torch.int64)
+    if all_pad_rows:
+        lens[:all_pad_rows] = 0
+    L = int(lens.max().item()) if n else 0
+    L = max(L, 1)
+    embs = torch.randn(n, L, dim, generator=g, device=device)
+    mask = (torch.arange(L, device=device)[None, :] < lens[:, None]).to(torch.int64)
+    return embs, mask
+
+
+def make_strip_batch(docs: int, strips: List[int], tokens: int, dim: int, seed: int, device="cpu"):
+    """Un-pooled encoder token matrices for the visual path: List[B] of (n_b, tokens, dim) and
+    questions (B, tokens, dim)  (src/_modules.py:1627-1666 produces (n, 2048, 768))."""
+    g = _gen(seed, device)
+    patches = [torch.randn(n, tokens, dim, generator=g, device=device) for n in strips]
+    q = torch.randn(docs, tokens, dim, generator=g, device=device)
+    return patches, q
+
+
+def make_tokens_for_words(words_text_chunks, seed: int = 0, vocab: int = 32000):
+    """Deterministic stand-in for the T5 tokenizer (no tokenizer files exist offline): each
+    distinct word maps to 1-3 ids (p = .6/.3/.1), ids in [3, vocab).  Returns a dict word->list."""
+    table = {}
+    rng = np.random.RandomState(seed)
+    for doc in words_text_chunks:
+        for chunk in doc:
+            for w in chunk:
+                if w not in table:
+                    n_tok = int(rng.choice([1, 2, 3], p=[0.6, 0.3, 0.1]))
+                    table[w] = [int(t) for t in rng.randint(3, vocab, size=n_tok)]
+    return table
