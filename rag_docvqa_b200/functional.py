@@ -1,0 +1,151 @@
+"""Tensor-level entry points of the B200 retrieval path (thin host code over librdv.so).
+
+Every function here launches hand-written sm_100a kernels through the C ABI in include/rdv.h on
+torch's current CUDA stream.  PyTorch is used for device memory and streams only.  Inputs must live on
+a CUDA device: there is no CPU path (use oracle/ for a CPU checker).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, NamedTuple, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_lib_fn = _lib.lib
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: rag_docvqa_b200 has no CPU fallback "
+                           "(got device %s)" % (what, t.device))
+
+
+def _f32_contig_aligned(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+class _Workspace:
+    """Per (device, stream) zero-initialised int32 scratch that the kernels leave zeroed."""
+    _cache = {}
+
+    @classmethod
+    def zeros_i32(cls, device, n: int) -> torch.Tensor:
+        key = (device.index, _stream_ptr(device))
+        buf = cls._cache.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.zeros(max(n, 1024), dtype=torch.int32, device=device)
+            cls._cache[key] = buf
+        return buf
+
+
+class ScoreTopK(NamedTuple):
+    similarities: List[torch.Tensor]   # List[B] of (n_b,) fp32 views into `sims`
+    sims: torch.Tensor                 # (N,) fp32, all documents back to back
+    topk_idx: torch.Tensor             # (B, k) int32, -1 padded, rank order
+    topk_val: torch.Tensor             # (B, k) fp32, -inf padded
+    topk_cnt: torch.Tensor             # (B,) int32 = min(k, n_b)
+    sizes: List[int]
+
+
+class DocTable(NamedTuple):
+    """Device-side description of a ragged batch of documents (see rdv_score_topk_f32)."""
+    desc: torch.Tensor     # uint8 blob on device: ptr[B] u64 | row_off[B+1] i64 | tile_off[B+1] i32
+    keepalive: tuple       # tensors whose storage the pointer table references
+    B: int
+    d: int
+    sizes: List[int]
+    total_rows: int
+    total_tiles: int
+    tile_rows: int
+    max_rows: int
+
+    def pointers(self):
+        base = self.desc.data_ptr()
+        return base, base + 8 * self.B, base + 8 * self.B + 8 * (self.B + 1)
+
+
+def build_doc_table(docs: Sequence[torch.Tensor], d: int, device, tile_rows: int = 0) -> DocTable:
+    """Uploads the pointer / offset table of a ragged batch in ONE pinned H2D copy."""
+    B = len(docs)
+    keep = []
+    sizes = np.empty(B, dtype=np.int64)
+    ptrs = np.empty(B, dtype=np.uint64)
+    for b, t in enumerate(docs):
+        if t.dim() != 2 or (t.shape[0] and t.shape[1] != d):
+            raise ValueError("document %d: expected (n, %d) embeddings, got %s" % (b, d, tuple(t.shape)))
+        if t.shape[0]:
+            _require_cuda(t, "text_embeddings[%d]" % b)
+            t = _f32_contig_aligned(t)
+        keep.append(t)
+        sizes[b] = t.shape[0]
+        ptrs[b] = t.data_ptr() if t.shape[0] else 0
+    total_rows = int(sizes.sum()) if B else 0
+    if tile_rows <= 0:
+        tile_rows = int(_lib_fn.rdv_score_tile_rows(total_rows, d))
+    row_off = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(sizes, out=row_off[1:])
+    tile_off = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum((sizes + tile_rows - 1) // tile_rows, out=tile_off[1:])
+    if tile_off[-1] >= 2 ** 31 - 1:
+        raise ValueError("too many tiles for one launch")
+    nbytes = 8 * B + 8 * (B + 1) + 4 * (B + 1)
+    nbytes = (nbytes + 15) // 16 * 16
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    raw = host.numpy()
+    raw[:8 * B].view(np.uint64)[:] = ptrs
+    raw[8 * B:8 * B + 8 * (B + 1)].view(np.int64)[:] = row_off
+    raw[16 * B + 8:16 * B + 8 + 4 * (B + 1)].view(np.int32)[:] = tile_off.astype(np.int32)
+    desc = host.to(device, non_blocking=True)
+    return DocTable(desc, tuple(keep), B, d, [int(s) for s in sizes], total_rows, int(tile_off[-1]),
+                    tile_rows, int(sizes.max()) if B else 0)
+
+
+def score_topk_table(table: DocTable, questions: torch.Tensor, k: int) -> ScoreTopK:
+    """Launches the fused score + top-k kernel on an uploaded DocTable."""
+    device = questions.device
+    B, d = table.B, table.d
+    q = _f32_contig_aligned(questions)
+    sims = torch.empty(table.total_rows, dtype=torch.float32, device=device)
+    topk_idx = torch.empty((B, k), dtype=torch.int32, device=device)
+    topk_val = torch.empty((B, k), dtype=torch.float32, device=device)
+    topk_cnt = torch.empty((B,), dtype=torch.int32, device=device)
+    if B:
+        done = _Workspace.zeros_i32(device, B)
+        p_ptr, p_row, p_tile = table.pointers()
+        _lib.check(_lib_fn.rdv_score_topk_f32(
+            p_ptr, p_row, p_tile, q.data_ptr(), B, d, k, table.tile_rows, table.total_tiles,
+            table.max_rows, sims.data_ptr(), topk_idx.data_ptr(), topk_val.data_ptr(),
+            topk_cnt.data_ptr(), done.data_ptr(), _stream_ptr(device)))
+    views = list(torch.split(sims, table.sizes)) if B else []
+    return ScoreTopK(views, sims, topk_idx, topk_val, topk_cnt, table.sizes)
+
+
+def score_topk(text_embeddings: Sequence[torch.Tensor], question_embeddings: torch.Tensor, k: int,
+               tile_rows: int = 0) -> ScoreTopK:
+    """Cosine score of question b against every chunk of document b + per-document top-k.
+
+    Replaces Retriever._get_similarities + torch.topk (reference src/_modules.py:1978-1997, 2015-2016).
+    text_embeddings: List[B] of (n_b, d) CUDA fp32 tensors (n_b may be 0); question_embeddings: (B, d).
+    """
+    _require_cuda(question_embeddings, "question_embeddings")
+    if question_embeddings.dim() != 2 or question_embeddings.shape[0] != len(text_embeddings):
+        raise ValueError("question_embeddings must be (B, d) with B == len(text_embeddings)")
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    d = question_embeddings.shape[1]
+    with torch.cuda.device(question_embeddings.device):
+        table = build_doc_table(text_embeddings, d, question_embeddings.device, tile_rows)
+        return score_topk_table(table, question_embeddings, k)

@@ -1,0 +1,45 @@
+"""CPU-side checks of the C-ABI boundary: librdv.so builds, loads, and exports exactly the
+symbols include/rdv.h declares (no compute is launched here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rdv.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"RDV_API\s+[\w\s\*]+?\b(rdv_\w+)\s*\(", text)))
+
+
+def test_header_declares_something():
+    syms = declared_symbols()
+    assert "rdv_score_topk_f32" in syms and "rdv_last_error" in syms
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from rag_docvqa_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), "librdv.so does not export %s" % name
+    out = subprocess.run(["nm", "-D", "--defined-only", path], stdout=subprocess.PIPE, text=True).stdout
+    exported = sorted(set(re.findall(r"\bT (rdv_\w+)", out)))
+    assert exported == declared_symbols(), "exported %s != declared %s" % (exported, declared_symbols())
+
+
+def test_binding_table_matches_header():
+    from rag_docvqa_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    assert _lib.lib.rdv_abi_version() == _lib.ABI_VERSION
+    assert _lib.lib.rdv_last_error() == b""
+
+
+def test_sass_is_sm100a_only():
+    from rag_docvqa_b200 import build
+    out = subprocess.run(["cuobjdump", "--list-elf", build.LIB], stdout=subprocess.PIPE, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
