@@ -77,9 +77,138 @@ RDV_API int rdv_score_topk_f32(const void* const* d_doc_ptr, const int64_t* d_ro
                                float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
                                int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
 
+/* Stand-alone segmented top-k over an existing score vector (same ordering rules as above); used
+ * for the visual path, where the scores come from MaxSim (torch.topk at src/_modules.py:2408).
+ * d_scores [N] fp32, d_row_off [B+1] int64; outputs / workspace as in rdv_score_topk_f32. */
+RDV_API int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_off, int32_t B, int32_t k,
+                                  int32_t max_rows, int32_t* d_topk_idx, float* d_topk_val,
+                                  int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
+
 /* Launch heuristic for tile_rows given the batch's total row count (keeps >= ~8 tiles per SM for
  * small batches so the hardware scheduler can balance ragged documents). */
 RDV_API int32_t rdv_score_tile_rows(int64_t total_rows, int32_t d);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Masked mean pooling of encoder token outputs (+ optional fused L2 normalisation / bf16 copy).
+ *
+ * Replaces mean_pooling (src/_model_utils.py:49-61; call site src/_modules.py:1474):
+ *     out[i,:] = sum_t embs[i,t,:] * mask[i,t] / max(sum_t mask[i,t], 1e-9)
+ *   d_embs (n,L,d) fp32 contiguous, 16-byte aligned;  d_mask (n,L) int64 (HF tokenizer attention mask)
+ *   normalise != 0: out row is divided by max(||row||, 1e-12) (F.normalize, as src/utils.py:445 does for
+ *                   the visual path; sentence-transformers' Normalize module for BGE)
+ *   d_out (n,d) fp32 or NULL; d_out_bf16 (n,d) bf16 or NULL (corpus shards); d_out_norm (n,) or NULL:
+ *   L2 norm of the pooled row before normalisation.
+ * Tokens with mask == 0 are not read.  Requirements: d % 4 == 0, d <= 8192, L <= 4096.
+ * ------------------------------------------------------------------------------------------- */
+RDV_API int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int32_t n, int32_t L, int32_t d,
+                              int32_t normalise, float* d_out, void* d_out_bf16, float* d_out_norm,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaxSim late interaction, fp32 parity mode.
+ *
+ * Replaces late_interaction (src/utils.py:442-458; call site src/_modules.py:2202):
+ *     score[n] = sum_i max_j < Q[i]/max(||Q[i]||,1e-12) , P[n][j]/max(||P[n][j]||,1e-12) >
+ *   rdv_row_inv_norm_f32: inv[r] = 1 / max(||x[r]||, 1e-12) for a (rows, d) fp32 matrix (F.normalize's
+ *                         denominator, src/utils.py:445-446); run it on Q and on P first.
+ *   rdv_maxsim_f32: d_q (Lq,d), d_p (n,Lp,d) fp32 16-byte aligned; d_partial (n * rdv_maxsim_tiles_i(Lq))
+ *                   fp32 workspace; d_counter (n) int32 workspace, zero on entry, left zero; d_out (n).
+ * The (Lq x Lp) similarity matrix is never materialised.  Requirements: d % 4 == 0, Lp >= 1, n <= 65535.
+ * ------------------------------------------------------------------------------------------- */
+RDV_API int rdv_row_inv_norm_f32(const float* d_x, int64_t rows, int32_t d, float* d_inv, void* stream);
+RDV_API int rdv_maxsim_f32(const float* d_q, const float* d_p, const float* d_inv_q, const float* d_inv_p,
+                           int32_t n, int32_t Lq, int32_t Lp, int32_t d, float* d_partial,
+                           int32_t* d_counter, float* d_out, void* stream);
+RDV_API int32_t rdv_maxsim_tiles_i(int32_t Lq);
+
+/* ---------------------------------------------------------------------------------------------
+ * Merge of per-shard top-k candidates (corpus mode, BASELINE.json configs[4]; no reference
+ * counterpart -- the reference is single-GPU).  (Q, m) candidates with GLOBAL ids (id < 0 = empty)
+ * -> (Q, k) by (score desc, id asc), NaN greatest: the ordering of rdv_score_topk_f32, so a sharded
+ * search returns exactly what an unsharded one would.
+ * ------------------------------------------------------------------------------------------- */
+RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, int32_t Q, int32_t m, int32_t k,
+                           float* d_out_val, int64_t* d_out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gather of the retrieved chunks into the VT5 generator's input tensors.
+ *
+ * Replaces, for a pre-tokenised batch of documents, everything between torch.topk and the generator's
+ * embedding lookup: Retriever._get_top_k (src/_modules.py:2014-2100: page-list range of each hit
+ * +- include_surroundings, minus words already emitted by better hits), Chunker.compact_chunks
+ * (src/_modules.py:1102-1132: bbox), the crop rectangle (src/_modules.py:2108-2119), reorder_chunks
+ * (src/_modules.py:2129-2142), flatten with separator (src/utils.py:233-253) and the id/box/mask/label
+ * packing of VT5.prepare_inputs_for_vqa (src/VT5.py:141-185).
+ *
+ * rdv_docstore: CSR view of B documents, all arrays in DEVICE memory (N chunks, W words, T tokens):
+ *   chunk_off[B+1] i64      first global chunk of each document (== d_row_off of the score kernel)
+ *   chunk_word_off[N+1]     first global word of each chunk        word_tok_off[W+1]  first token of each word
+ *   tok_ids[T]              token ids (the tokenizer's ids without EOS, src/VT5.py:160)
+ *   word_box[W*4] f64       word boxes, 0..1, as the Python floats the reference multiplies by 1000
+ *   chunk_label[N], chunk_page[N]
+ *   page_chunks[N]          GLOBAL chunk ids grouped by (document, page), chunk order inside a page
+ *   run_begin[N], run_end[N]  per chunk: the [begin, end) slice of page_chunks holding its page
+ *   chunk_page_start[N]     position of the chunk's first word in its page's word list (src/_modules.py:2044)
+ *   doc_page_off[B+1], page_wh[P*2]  (optional) page sizes in pixels for the crop rectangles
+ * rdv_gather_args: hits (the score kernel's d_topk_idx / d_topk_cnt, row pitch k), options, prompt ids
+ *   (without EOS, src/VT5.py:147-148), separator ids, and the outputs:
+ *   out_ids/out_mask/out_labels (B,max_len) i64, out_boxes (B,max_len,4) i64  (out_labels may be NULL)
+ *   full_len[B]   len(input_ids)+1 before truncation: longest_seq = min(max_b full_len, max_len) (src/VT5.py:170)
+ *   status[B]     0 ok, 1 = segment workspace overflow (raise max_seg)
+ *   hit_* (B,k)   per hit in OUTPUT order: chunk index (-1 pad), page, label, #emitted words,
+ *                 bbox (f64 x4; [0,0,1,1] when no word was emitted) and crop rectangle (int32 x4; -1 without pages)
+ *   seg_ws        int32 workspace of B*k*max_seg*2
+ * Requirements: 1 <= k <= 64.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rdv_docstore {
+    int32_t B;
+    int32_t reserved;
+    const int64_t* chunk_off;
+    const int32_t* chunk_word_off;
+    const int32_t* word_tok_off;
+    const int32_t* tok_ids;
+    const double* word_box;
+    const int32_t* chunk_label;
+    const int32_t* chunk_page;
+    const int32_t* chunk_page_start;
+    const int32_t* page_chunks;
+    const int32_t* run_begin;
+    const int32_t* run_end;
+    const int32_t* doc_page_off;
+    const int32_t* page_wh;
+} rdv_docstore;
+
+typedef struct rdv_gather_args {
+    const int32_t* topk_idx;
+    const int32_t* topk_cnt;
+    int32_t k;
+    int32_t include_surroundings;
+    int32_t reorder_chunks;
+    int32_t n_sep;
+    const int32_t* prompt_off;
+    const int32_t* prompt_ids;
+    const int32_t* sep_ids;
+    int32_t eos_id;
+    int32_t pad_id;
+    int32_t max_len;
+    int32_t max_seg;
+    int32_t* seg_ws;
+    int64_t* out_ids;
+    int64_t* out_boxes;
+    int64_t* out_mask;
+    int64_t* out_labels;
+    int32_t* full_len;
+    int32_t* status;
+    int32_t* hit_chunk;
+    int32_t* hit_page;
+    int32_t* hit_label;
+    int32_t* hit_nwords;
+    double* hit_bbox;
+    int32_t* hit_rect;
+} rdv_gather_args;
+
+RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args* args, void* stream);
 
 #ifdef __cplusplus
 }

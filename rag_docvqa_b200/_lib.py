@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, c_size_t, POINTER
+from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
@@ -21,6 +21,23 @@ class RdvError(RuntimeError):
         self.code = code
 
 
+class DocStoreStruct(Structure):
+    """Mirror of `rdv_docstore` (include/rdv.h)."""
+    _fields_ = [("B", c_int32), ("reserved", c_int32)] + [(n, c_void_p) for n in (
+        "chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "word_box", "chunk_label", "chunk_page",
+        "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh")]
+
+
+class GatherArgsStruct(Structure):
+    """Mirror of `rdv_gather_args` (include/rdv.h)."""
+    _fields_ = [("topk_idx", c_void_p), ("topk_cnt", c_void_p), ("k", c_int32), ("include_surroundings", c_int32),
+                ("reorder_chunks", c_int32), ("n_sep", c_int32), ("prompt_off", c_void_p), ("prompt_ids", c_void_p),
+                ("sep_ids", c_void_p), ("eos_id", c_int32), ("pad_id", c_int32), ("max_len", c_int32),
+                ("max_seg", c_int32)] + [(n, c_void_p) for n in (
+                    "seg_ws", "out_ids", "out_boxes", "out_mask", "out_labels", "full_len", "status", "hit_chunk",
+                    "hit_page", "hit_label", "hit_nwords", "hit_bbox", "hit_rect")]
+
+
 # name -> (restype, argtypes); tests/test_abi.py checks this table against include/rdv.h
 SIGNATURES = {
     "rdv_abi_version": (c_int32, []),
@@ -30,6 +47,16 @@ SIGNATURES = {
                                      c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
     "rdv_score_tile_rows": (c_int32, [c_int64, c_int32]),
+    "rdv_topk_segments_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "rdv_mean_pool_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
+    "rdv_row_inv_norm_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "rdv_maxsim_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_maxsim_tiles_i": (c_int32, [c_int32]),
+    "rdv_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "rdv_gather_vt5_inputs": (c_int32, [POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
 }
 
 

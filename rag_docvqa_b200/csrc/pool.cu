@@ -1,0 +1,182 @@
+// Masked mean pooling (+ optional fused L2 normalisation, optional bf16 copy) -- sm_100a.
+//
+// Replaces mean_pooling (reference src/_model_utils.py:49-61, called at src/_modules.py:1474):
+//     out[i,:] = sum_t embs[i,t,:] * mask[i,t] / max(sum_t mask[i,t], 1e-9)
+// The reference materialises embs*mask (a full-size temporary) and reads it again; here every token
+// row is read exactly once and tokens whose mask is 0 are not read at all, so the traffic is
+// n*Lvalid*d*4 instead of 3*n*L*d*4.  HBM-bound: one block per chunk, thread = one float4 column of
+// d, G token-groups per block accumulate in parallel and are folded through shared memory.
+//
+// Deviation, documented: a NaN/Inf sitting at a *masked-out* token position is ignored here, whereas
+// the reference's `embs * 0` would propagate it (finite inputs: bit-for-bit the same sum order per
+// group; result within fp32 rounding of the reference).
+#include "rdv_common.cuh"
+#include <cuda_bf16.h>
+
+namespace rdv {
+
+constexpr int kPoolThreads = 256;
+constexpr int kPoolMaxL = 4096;
+
+struct PoolParams {
+    const float* embs;       // (n, L, d)
+    const int64_t* mask;     // (n, L)
+    int32_t n, L, d;
+    int32_t normalise;       // 1: divide the pooled row by max(||row||, 1e-12)  (F.normalize semantics)
+    float* out;              // (n, d) or null
+    __nv_bfloat16* out_bf16; // (n, d) or null
+    float* out_norm;         // (n,) L2 norm of the pooled row before normalisation, or null
+};
+
+__global__ void __launch_bounds__(kPoolThreads) mean_pool_kernel(const PoolParams p) {
+    extern __shared__ float4 s_part[];            // [G][d4] partial sums (G > 1 only)
+    __shared__ float s_mask[kPoolMaxL];
+    __shared__ float s_red[kPoolThreads / 32];
+    __shared__ float s_scalar[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d4 = p.d >> 2;
+    const int row = blockIdx.x;
+    const int64_t* mrow = p.mask + (size_t)row * p.L;
+
+    // mask row -> shared (as float, the reference multiplies by it), count = sum(mask)
+    float cnt = 0.f;
+    for (int t = tid; t < p.L; t += kPoolThreads) {
+        const float m = (float)mrow[t];
+        s_mask[t] = m;
+        cnt += m;
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) s_red[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        float c = 0.f;
+        for (int w = 0; w < kPoolThreads / 32; ++w) c += s_red[w];
+        s_scalar[0] = fmaxf(c, 1e-9f);            // clamp(min=1e-9)
+    }
+    __syncthreads();
+    const float denom = s_scalar[0];
+
+    // thread layout: column c = tid % cols, token group g = tid / cols
+    const int cols = d4 < kPoolThreads ? d4 : kPoolThreads;
+    const int G = kPoolThreads / cols;            // >= 1
+    const int g = tid / cols, c0 = tid - g * cols;
+    const bool active = g < G;
+    const float4* base = reinterpret_cast<const float4*>(p.embs) + (size_t)row * p.L * d4;
+
+    float ss_local = 0.f;
+    for (int c = c0; c < d4; c += cols) {         // more than one pass only when d4 > 256
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            int t = g;
+            // 4 independent loads in flight per thread
+            for (; t + 3 * G < p.L; t += 4 * G) {
+                const float m0 = s_mask[t], m1 = s_mask[t + G], m2 = s_mask[t + 2 * G], m3 = s_mask[t + 3 * G];
+                float4 v0, v1, v2, v3;
+                if (m0 != 0.f) v0 = ldg_stream(base + (size_t)t * d4 + c);
+                if (m1 != 0.f) v1 = ldg_stream(base + (size_t)(t + G) * d4 + c);
+                if (m2 != 0.f) v2 = ldg_stream(base + (size_t)(t + 2 * G) * d4 + c);
+                if (m3 != 0.f) v3 = ldg_stream(base + (size_t)(t + 3 * G) * d4 + c);
+                if (m0 != 0.f) { acc.x = fmaf(v0.x, m0, acc.x); acc.y = fmaf(v0.y, m0, acc.y); acc.z = fmaf(v0.z, m0, acc.z); acc.w = fmaf(v0.w, m0, acc.w); }
+                if (m1 != 0.f) { acc.x = fmaf(v1.x, m1, acc.x); acc.y = fmaf(v1.y, m1, acc.y); acc.z = fmaf(v1.z, m1, acc.z); acc.w = fmaf(v1.w, m1, acc.w); }
+                if (m2 != 0.f) { acc.x = fmaf(v2.x, m2, acc.x); acc.y = fmaf(v2.y, m2, acc.y); acc.z = fmaf(v2.z, m2, acc.z); acc.w = fmaf(v2.w, m2, acc.w); }
+                if (m3 != 0.f) { acc.x = fmaf(v3.x, m3, acc.x); acc.y = fmaf(v3.y, m3, acc.y); acc.z = fmaf(v3.z, m3, acc.z); acc.w = fmaf(v3.w, m3, acc.w); }
+            }
+            for (; t < p.L; t += G) {
+                const float m = s_mask[t];
+                if (m != 0.f) {
+                    const float4 v = ldg_stream(base + (size_t)t * d4 + c);
+                    acc.x = fmaf(v.x, m, acc.x); acc.y = fmaf(v.y, m, acc.y);
+                    acc.z = fmaf(v.z, m, acc.z); acc.w = fmaf(v.w, m, acc.w);
+                }
+            }
+        }
+        if (G > 1) {                               // fold the token groups (fixed order: deterministic)
+            if (active) s_part[g * cols + c0] = acc;
+            __syncthreads();
+            if (g == 0) {
+                for (int gg = 1; gg < G; ++gg) {
+                    const float4 o = s_part[gg * cols + c0];
+                    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                }
+            }
+        }
+        if (g == 0) {
+            acc.x = __fdiv_rn(acc.x, denom); acc.y = __fdiv_rn(acc.y, denom);
+            acc.z = __fdiv_rn(acc.z, denom); acc.w = __fdiv_rn(acc.w, denom);
+            ss_local += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+            if (!p.normalise) {
+                if (p.out) reinterpret_cast<float4*>(p.out)[(size_t)row * d4 + c] = acc;
+                if (p.out_bf16) {
+                    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(p.out_bf16) + ((size_t)row * d4 + c) * 2;
+                    o[0] = __floats2bfloat162_rn(acc.x, acc.y);
+                    o[1] = __floats2bfloat162_rn(acc.z, acc.w);
+                }
+            } else {
+                s_part[(size_t)G * cols + c] = acc; // stash the mean row for the second pass
+            }
+        }
+        if (G > 1) __syncthreads();
+    }
+    if (!p.normalise && !p.out_norm) return;
+
+    // row L2 norm
+    ss_local = warp_sum(ss_local);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = ss_local;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kPoolThreads / 32; ++w) s += s_red[w];
+        const float nrm = __fsqrt_rn(s);
+        s_scalar[1] = nrm;
+        if (p.out_norm) p.out_norm[row] = nrm;
+    }
+    __syncthreads();
+    if (!p.normalise) return;
+    const float inv_den = fmaxf(s_scalar[1], 1e-12f);
+    for (int c = tid; c < d4; c += kPoolThreads) {
+        float4 v = s_part[(size_t)G * cols + c];
+        v.x = __fdiv_rn(v.x, inv_den); v.y = __fdiv_rn(v.y, inv_den);
+        v.z = __fdiv_rn(v.z, inv_den); v.w = __fdiv_rn(v.w, inv_den);
+        if (p.out) reinterpret_cast<float4*>(p.out)[(size_t)row * d4 + c] = v;
+        if (p.out_bf16) {
+            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(p.out_bf16) + ((size_t)row * d4 + c) * 2;
+            o[0] = __floats2bfloat162_rn(v.x, v.y);
+            o[1] = __floats2bfloat162_rn(v.z, v.w);
+        }
+    }
+}
+
+}  // namespace rdv
+
+extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int32_t n, int32_t L, int32_t d,
+                                 int32_t normalise, float* d_out, void* d_out_bf16, float* d_out_norm,
+                                 void* stream) {
+    using namespace rdv;
+    RDV_REQUIRE(n >= 0 && L >= 0, RDV_E_INVALID, "mean_pool_f32: negative size");
+    if (n == 0) return RDV_OK;
+    RDV_REQUIRE(d_embs && d_mask && (d_out || d_out_bf16), RDV_E_INVALID, "mean_pool_f32: null pointer");
+    RDV_REQUIRE(d >= 4 && d <= 8192 && (d & 3) == 0, RDV_E_INVALID,
+                "mean_pool_f32: d=%d must be a multiple of 4 in [4, 8192]", d);
+    RDV_REQUIRE(L <= kPoolMaxL, RDV_E_LIMIT, "mean_pool_f32: L=%d > %d tokens", L, kPoolMaxL);
+    RDV_REQUIRE(aligned16(d_embs) && (!d_out || aligned16(d_out)) && (!d_out_bf16 || aligned16(d_out_bf16)),
+                RDV_E_ALIGN, "mean_pool_f32: buffers must be 16-byte aligned");
+    PoolParams p;
+    p.embs = d_embs; p.mask = d_mask; p.n = n; p.L = L; p.d = d; p.normalise = normalise ? 1 : 0;
+    p.out = d_out; p.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16); p.out_norm = d_out_norm;
+    const int d4 = d >> 2;
+    const int cols = d4 < kPoolThreads ? d4 : kPoolThreads;
+    const int G = kPoolThreads / cols;
+    // [G][cols] group partials + [d4] stash for the normalise pass
+    const size_t smem = ((size_t)G * cols + (size_t)d4) * sizeof(float4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mean_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mean_pool)");
+        attr_set = true;
+    }
+    mean_pool_kernel<<<n, kPoolThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    RDV_LAUNCH_CHECK("mean_pool_kernel");
+    return RDV_OK;
+}

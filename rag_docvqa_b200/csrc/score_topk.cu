@@ -307,3 +307,46 @@ extern "C" int rdv_score_topk_f32(const void* const* d_doc_ptr, const int64_t* d
         default:   return launch_score<0, 2>(p, smem, s);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Stand-alone segmented top-k over an existing score vector (the visual path: MaxSim scores -> top-k
+// strips, reference src/_modules.py:2408).  One block per document, same selection as above.
+// ---------------------------------------------------------------------------------------------------
+namespace rdv {
+__global__ void __launch_bounds__(kScoreThreads) topk_segments_kernel(const ScoreParams p) {
+    extern __shared__ float4 smem_dyn[];
+    __shared__ unsigned long long s_red[kScoreWarps];
+    const int b = blockIdx.x;
+    const int64_t r0 = p.row_off[b];
+    const int n = (int)(p.row_off[b + 1] - r0);
+    select_topk(p, b, p.sims + r0, n, reinterpret_cast<float*>(smem_dyn), s_red);
+}
+}  // namespace rdv
+
+extern "C" int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_off, int32_t B, int32_t k,
+                                     int32_t max_rows, int32_t* d_topk_idx, float* d_topk_val,
+                                     int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream) {
+    using namespace rdv;
+    RDV_REQUIRE(B >= 0 && max_rows >= 0, RDV_E_INVALID, "topk_segments_f32: negative size");
+    if (B == 0) return RDV_OK;
+    RDV_REQUIRE(d_row_off && d_topk_idx && d_topk_val && d_topk_cnt && d_doc_done, RDV_E_INVALID,
+                "topk_segments_f32: null pointer");
+    RDV_REQUIRE(d_scores || max_rows == 0, RDV_E_INVALID, "topk_segments_f32: null scores");
+    RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "topk_segments_f32: k=%d outside [1, 1024]", k);
+    ScoreParams p = {};
+    p.row_off = d_row_off; p.B = B; p.k = k;
+    p.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
+    p.sims = const_cast<float*>(d_scores);
+    p.topk_idx = d_topk_idx; p.topk_val = d_topk_val; p.topk_cnt = d_topk_cnt; p.doc_done = d_doc_done;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             64 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(topk_segments)");
+        attr_set = true;
+    }
+    const size_t smem = (size_t)p.cache_floats * sizeof(float) + 16;
+    topk_segments_kernel<<<B, kScoreThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    RDV_LAUNCH_CHECK("topk_segments_kernel");
+    return RDV_OK;
+}

@@ -1,0 +1,198 @@
+"""Pre-tokenised CSR document store + the device gather into the generator's input tensors.
+
+Host side: turn the reference's nested lists (words_text_chunks / words_box_chunks /
+layout_labels_chunks / page_indices, src/RAGVT5.py:208-224) into flat CSR arrays ONCE per batch of
+documents, upload them in one pinned copy.  Device side: rdv_gather_vt5_inputs (csrc/gather.cu) builds
+input_ids / boxes / attention_mask / layout labels from the top-k kernel's output without a host round
+trip (reference: src/_modules.py:2014-2142, src/utils.py:233-253, src/VT5.py:141-185).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, List, NamedTuple, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .functional import _stream_ptr
+
+_I32 = np.int32
+
+
+class PackedInputs(NamedTuple):
+    input_ids: torch.Tensor        # (B, longest) int64
+    boxes: torch.Tensor            # (B, longest, 4) int64
+    attention_mask: torch.Tensor   # (B, longest) int64
+    layout_labels: Optional[torch.Tensor]
+    longest: int
+    hit_chunk: torch.Tensor        # (B, k) int32, OUTPUT order (after reorder_chunks), -1 padded
+    hit_page: torch.Tensor
+    hit_label: torch.Tensor
+    hit_nwords: torch.Tensor
+    hit_bbox: torch.Tensor         # (B, k, 4) float64
+    hit_rect: torch.Tensor         # (B, k, 4) int32 crop rectangle (x0, y0, x1, y1), -1 without page sizes
+
+
+class DocStore:
+    """CSR view of a batch of documents on the device (see `rdv_docstore` in include/rdv.h)."""
+
+    FIELDS = ("chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "word_box", "chunk_label", "chunk_page",
+              "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh")
+
+    def __init__(self, arrays: dict, B: int, device):
+        self.B = B
+        self.device = device
+        self.host = arrays
+        # one pinned blob, one H2D copy
+        offsets, total = {}, 0
+        for name in self.FIELDS:
+            arr = arrays.get(name)
+            if arr is None:
+                continue
+            total = (total + 15) // 16 * 16
+            offsets[name] = total
+            total += arr.nbytes
+        blob = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
+        raw = blob.numpy()
+        for name, off in offsets.items():
+            arr = arrays[name]
+            raw[off:off + arr.nbytes] = np.frombuffer(arr.tobytes(), dtype=np.uint8)
+        self.blob = blob.to(device, non_blocking=True)
+        base = self.blob.data_ptr()
+        self.struct = _lib.DocStoreStruct()
+        self.struct.B = B
+        for name in self.FIELDS:
+            setattr(self.struct, name, base + offsets[name] if name in offsets else None)
+        self.n_chunks = int(arrays["chunk_off"][-1])
+        self.n_words = int(arrays["chunk_word_off"][-1])
+        self.n_tokens = int(arrays["word_tok_off"][-1])
+
+    @classmethod
+    def from_lists(cls, words_text_chunks, words_box_chunks, layout_labels_chunks, page_indices,
+                   tokenize: Callable[[str], Sequence[int]], device, images=None) -> "DocStore":
+        """tokenize(word) -> the word's token ids WITHOUT the trailing EOS (src/VT5.py:160)."""
+        B = len(words_text_chunks)
+        sizes = np.array([len(doc) for doc in words_text_chunks], dtype=np.int64)
+        chunk_off = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(sizes, out=chunk_off[1:])
+        N = int(chunk_off[-1])
+        chunk_nwords = np.zeros(N, dtype=np.int64)
+        chunk_label = np.zeros(N, dtype=_I32)
+        chunk_page = np.zeros(N, dtype=_I32)
+        tok_cache = {}
+        word_ntok, tok_ids, boxes = [], [], []
+        g = 0
+        for b in range(B):
+            for c in range(int(sizes[b])):
+                words = words_text_chunks[b][c]
+                chunk_nwords[g] = len(words)
+                chunk_label[g] = layout_labels_chunks[b][c]
+                chunk_page[g] = page_indices[b][c]
+                for w in words:
+                    toks = tok_cache.get(w)
+                    if toks is None:
+                        toks = tok_cache[w] = [int(t) for t in tokenize(w)]
+                    word_ntok.append(len(toks))
+                    tok_ids.extend(toks)
+                if len(words):
+                    boxes.extend(words_box_chunks[b][c])
+                g += 1
+        chunk_word_off = np.zeros(N + 1, dtype=np.int64)
+        np.cumsum(chunk_nwords, out=chunk_word_off[1:])
+        W = int(chunk_word_off[-1])
+        word_tok_off = np.zeros(W + 1, dtype=np.int64)
+        np.cumsum(np.asarray(word_ntok, dtype=np.int64), out=word_tok_off[1:])
+        word_box = np.asarray(boxes, dtype=np.float64).reshape(W, 4) if W else np.zeros((0, 4), dtype=np.float64)
+        # page runs: chunks grouped by (document, page), chunk order inside a page (src/_modules.py:2032-2050)
+        doc_of = np.repeat(np.arange(B, dtype=np.int64), sizes)
+        order = np.lexsort((np.arange(N), chunk_page.astype(np.int64), doc_of)) if N else np.zeros(0, dtype=np.int64)
+        key = doc_of[order] * (1 << 32) + chunk_page[order].astype(np.int64) if N else np.zeros(0, dtype=np.int64)
+        new_run = np.ones(N, dtype=bool)
+        if N > 1:
+            new_run[1:] = key[1:] != key[:-1]
+        run_id = np.cumsum(new_run) - 1 if N else np.zeros(0, dtype=np.int64)
+        run_starts = np.nonzero(new_run)[0] if N else np.zeros(0, dtype=np.int64)
+        run_ends = np.append(run_starts[1:], N) if N else np.zeros(0, dtype=np.int64)
+        nw_sorted = chunk_nwords[order] if N else np.zeros(0, dtype=np.int64)
+        csum = np.cumsum(nw_sorted) - nw_sorted if N else np.zeros(0, dtype=np.int64)
+        start_sorted = csum - csum[run_starts][run_id] if N else np.zeros(0, dtype=np.int64)
+        chunk_page_start = np.zeros(N, dtype=_I32)
+        run_begin = np.zeros(N, dtype=_I32)
+        run_end = np.zeros(N, dtype=_I32)
+        if N:
+            chunk_page_start[order] = start_sorted
+            run_begin[order] = run_starts[run_id]
+            run_end[order] = run_ends[run_id]
+        arrays = dict(
+            chunk_off=chunk_off, chunk_word_off=chunk_word_off.astype(_I32), word_tok_off=word_tok_off.astype(_I32),
+            tok_ids=np.asarray(tok_ids, dtype=_I32), word_box=np.ascontiguousarray(word_box),
+            chunk_label=chunk_label, chunk_page=chunk_page, chunk_page_start=chunk_page_start,
+            page_chunks=order.astype(_I32), run_begin=run_begin, run_end=run_end)
+        if images is not None:
+            n_pages = np.array([len(p) for p in images], dtype=np.int64)
+            doc_page_off = np.zeros(B + 1, dtype=np.int64)
+            np.cumsum(n_pages, out=doc_page_off[1:])
+            wh = np.array([[im.width, im.height] for pages in images for im in pages], dtype=_I32).reshape(-1, 2)
+            arrays["doc_page_off"] = doc_page_off.astype(_I32)
+            arrays["page_wh"] = np.ascontiguousarray(wh)
+        return cls(arrays, B, device)
+
+    # ------------------------------------------------------------------------------------------
+    def gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],
+               include_surroundings: int = 0, reorder_chunks: bool = False, sep_ids: Sequence[int] = (),
+               eos_id: int = 1, pad_id: int = 0, max_len: int = 512, with_layout_labels: bool = False,
+               max_seg: int = 32, prompt_cache=None) -> PackedInputs:
+        """Launches rdv_gather_vt5_inputs on the current stream; ONE small D2H read (full_len/status)."""
+        dev = self.device
+        B, k = topk_idx.shape
+        if B != self.B:
+            raise ValueError("gather: topk_idx has %d documents, store has %d" % (B, self.B))
+        if isinstance(include_surroundings, (tuple, list)):
+            raise ValueError("tuple include_surroundings is a VisualRetriever option")
+        p_off = np.zeros(B + 1, dtype=_I32)
+        np.cumsum([len(p) for p in prompt_ids], out=p_off[1:])
+        flat = np.fromiter((t for p in prompt_ids for t in p), dtype=_I32, count=int(p_off[-1]))
+        sep = np.asarray(list(sep_ids), dtype=_I32)
+        host = torch.empty(p_off.nbytes + flat.nbytes + sep.nbytes + 16, dtype=torch.uint8, pin_memory=True)
+        raw = host.numpy()
+        raw[:p_off.nbytes] = np.frombuffer(p_off.tobytes(), dtype=np.uint8)
+        raw[p_off.nbytes:p_off.nbytes + flat.nbytes] = np.frombuffer(flat.tobytes(), dtype=np.uint8)
+        o_sep = p_off.nbytes + flat.nbytes
+        raw[o_sep:o_sep + sep.nbytes] = np.frombuffer(sep.tobytes(), dtype=np.uint8)
+        small = host.to(dev, non_blocking=True)
+
+        i32 = dict(dtype=torch.int32, device=dev)
+        out_ids = torch.empty((B, max_len), dtype=torch.int64, device=dev)
+        out_boxes = torch.empty((B, max_len, 4), dtype=torch.int64, device=dev)
+        out_mask = torch.empty((B, max_len), dtype=torch.int64, device=dev)
+        out_labels = torch.empty((B, max_len), dtype=torch.int64, device=dev) if with_layout_labels else None
+        meta = torch.empty((2, B), **i32)                 # full_len, status
+        hit_i = torch.empty((4, B, k), **i32)             # chunk, page, label, nwords
+        hit_bbox = torch.empty((B, k, 4), dtype=torch.float64, device=dev)
+        hit_rect = torch.empty((B, k, 4), **i32)
+        seg_ws = torch.empty((B * k * max_seg * 2,), **i32)
+
+        a = _lib.GatherArgsStruct()
+        a.topk_idx = topk_idx.data_ptr(); a.topk_cnt = topk_cnt.data_ptr()
+        a.k = k; a.include_surroundings = int(include_surroundings); a.reorder_chunks = 1 if reorder_chunks else 0
+        a.n_sep = len(sep)
+        a.prompt_off = small.data_ptr(); a.prompt_ids = small.data_ptr() + p_off.nbytes
+        a.sep_ids = small.data_ptr() + o_sep
+        a.eos_id = eos_id; a.pad_id = pad_id; a.max_len = max_len; a.max_seg = max_seg
+        a.seg_ws = seg_ws.data_ptr()
+        a.out_ids = out_ids.data_ptr(); a.out_boxes = out_boxes.data_ptr(); a.out_mask = out_mask.data_ptr()
+        a.out_labels = out_labels.data_ptr() if out_labels is not None else None
+        a.full_len = meta[0].data_ptr(); a.status = meta[1].data_ptr()
+        a.hit_chunk = hit_i[0].data_ptr(); a.hit_page = hit_i[1].data_ptr()
+        a.hit_label = hit_i[2].data_ptr(); a.hit_nwords = hit_i[3].data_ptr()
+        a.hit_bbox = hit_bbox.data_ptr(); a.hit_rect = hit_rect.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.rdv_gather_vt5_inputs(ctypes.byref(self.struct), ctypes.byref(a), _stream_ptr(dev)))
+        meta_h = meta.cpu()                               # the step's one device->host read
+        if int(meta_h[1].max()) if B else 0:
+            raise _lib.RdvError(_lib.E_LIMIT, "gather: segment workspace overflow, raise max_seg (%d)" % max_seg)
+        longest = min(int(meta_h[0].max()), max_len) if B else 0
+        return PackedInputs(out_ids[:, :longest], out_boxes[:, :longest], out_mask[:, :longest],
+                            out_labels[:, :longest] if out_labels is not None else None, longest,
+                            hit_i[0], hit_i[1], hit_i[2], hit_i[3], hit_bbox, hit_rect)

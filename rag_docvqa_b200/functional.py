@@ -149,3 +149,116 @@ def score_topk(text_embeddings: Sequence[torch.Tensor], question_embeddings: tor
     with torch.cuda.device(question_embeddings.device):
         table = build_doc_table(text_embeddings, d, question_embeddings.device, tile_rows)
         return score_topk_table(table, question_embeddings, k)
+
+
+# ------------------------------------------------------------------------------------------------
+# mean pooling (a1)
+# ------------------------------------------------------------------------------------------------
+def mean_pooling(embs: torch.Tensor, attention_mask: torch.Tensor, normalise: bool = False,
+                 out_bf16: bool = False, return_norm: bool = False):
+    """Drop-in for mean_pooling (reference src/_model_utils.py:49-61): masked mean over tokens.
+
+    embs (n, L, d) CUDA fp32, attention_mask (n, L) integer/bool/float -> (n, d) fp32.
+    Extras (not in the reference signature, defaults preserve behaviour): `normalise` fuses the L2
+    normalisation of the pooled row; `out_bf16` returns a bf16 copy as well (corpus shards);
+    `return_norm` returns the pooled rows' L2 norms.
+    """
+    _require_cuda(embs, "embs")
+    if embs.dim() != 3 or attention_mask.shape != embs.shape[:2]:
+        raise ValueError("mean_pooling: embs must be (n, L, d) and attention_mask (n, L)")
+    device = embs.device
+    n, L, d = embs.shape
+    e = _f32_contig_aligned(embs)
+    m = attention_mask.to(device=device, dtype=torch.int64).contiguous()
+    out = torch.empty((n, d), dtype=torch.float32, device=device)
+    out16 = torch.empty((n, d), dtype=torch.bfloat16, device=device) if out_bf16 else None
+    norm = torch.empty((n,), dtype=torch.float32, device=device) if return_norm else None
+    with torch.cuda.device(device):
+        _lib.check(_lib_fn.rdv_mean_pool_f32(
+            e.data_ptr(), m.data_ptr(), n, L, d, 1 if normalise else 0, out.data_ptr(),
+            out16.data_ptr() if out16 is not None else None, norm.data_ptr() if norm is not None else None,
+            _stream_ptr(device)))
+    extras = tuple(x for x in (out16, norm) if x is not None)
+    return (out, *extras) if extras else out
+
+
+# ------------------------------------------------------------------------------------------------
+# MaxSim late interaction (a5)
+# ------------------------------------------------------------------------------------------------
+def late_interaction(query: torch.Tensor, patches: torch.Tensor) -> torch.Tensor:
+    """Drop-in for late_interaction (reference src/utils.py:442-458), fp32 parity mode.
+
+    query (1, Lq, d), patches (n, Lp, d) CUDA fp32 -> (n,) scores = sum_i max_j cos(q_i, p_nj).
+    """
+    _require_cuda(query, "query")
+    _require_cuda(patches, "patches")
+    if query.dim() == 2:
+        query = query.unsqueeze(0)
+    if query.dim() != 3 or query.shape[0] != 1 or patches.dim() != 3 or patches.shape[2] != query.shape[2]:
+        raise ValueError("late_interaction: query must be (1, Lq, d) and patches (n, Lp, d)")
+    device = patches.device
+    n, Lp, d = patches.shape
+    Lq = query.shape[1]
+    q = _f32_contig_aligned(query[0])
+    p = _f32_contig_aligned(patches)
+    out = torch.empty((n,), dtype=torch.float32, device=device)
+    if n == 0:
+        return out
+    with torch.cuda.device(device):
+        s = _stream_ptr(device)
+        inv_q = torch.empty((Lq,), dtype=torch.float32, device=device)
+        inv_p = torch.empty((n * Lp,), dtype=torch.float32, device=device)
+        _lib.check(_lib_fn.rdv_row_inv_norm_f32(q.data_ptr(), Lq, d, inv_q.data_ptr(), s))
+        _lib.check(_lib_fn.rdv_row_inv_norm_f32(p.data_ptr(), n * Lp, d, inv_p.data_ptr(), s))
+        tiles_i = int(_lib_fn.rdv_maxsim_tiles_i(Lq))
+        partial = torch.empty((n * tiles_i,), dtype=torch.float32, device=device)
+        counter = _Workspace.zeros_i32(device, n)
+        # grid.y is limited to 65535 strips per launch
+        for lo in range(0, n, 65535):
+            hi = min(n, lo + 65535)
+            _lib.check(_lib_fn.rdv_maxsim_f32(
+                q.data_ptr(), p.data_ptr() + lo * Lp * d * 4, inv_q.data_ptr(), inv_p.data_ptr() + lo * Lp * 4,
+                hi - lo, Lq, Lp, d, partial.data_ptr() + lo * tiles_i * 4, counter.data_ptr(),
+                out.data_ptr() + lo * 4, s))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# shard merge (corpus mode)
+# ------------------------------------------------------------------------------------------------
+def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):
+    """(Q, m) candidates (global ids, <0 = empty) -> (Q, k) values / int64 ids by (score desc, id asc)."""
+    _require_cuda(cand_val, "cand_val")
+    device = cand_val.device
+    Q, m = cand_val.shape
+    v = cand_val.float().contiguous()
+    i = cand_idx.to(torch.int64).contiguous()
+    out_v = torch.empty((Q, k), dtype=torch.float32, device=device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib_fn.rdv_topk_merge(v.data_ptr(), i.data_ptr(), Q, m, k, out_v.data_ptr(), out_i.data_ptr(),
+                                          _stream_ptr(device)))
+    return out_v, out_i
+
+
+def topk_segments(scores: Sequence[torch.Tensor], k: int):
+    """Per-document top-k (score desc, lowest index first, NaN greatest) of existing score vectors.
+    Replaces torch.topk at reference src/_modules.py:2408.  Returns (idx (B,k) int32, val, cnt)."""
+    B = len(scores)
+    if B == 0:
+        raise ValueError("topk_segments: empty batch")
+    device = scores[0].device
+    _require_cuda(scores[0], "scores")
+    sizes = [int(s.shape[0]) for s in scores]
+    flat = torch.cat([s.float().reshape(-1) for s in scores]) if sum(sizes) else torch.empty(0, device=device)
+    row_off = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(sizes, out=row_off[1:])
+    off_d = torch.from_numpy(row_off).pin_memory().to(device, non_blocking=True)
+    idx = torch.empty((B, k), dtype=torch.int32, device=device)
+    val = torch.empty((B, k), dtype=torch.float32, device=device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        done = _Workspace.zeros_i32(device, B)
+        _lib.check(_lib_fn.rdv_topk_segments_f32(flat.data_ptr(), off_d.data_ptr(), B, k, max(sizes), idx.data_ptr(),
+                                                 val.data_ptr(), cnt.data_ptr(), done.data_ptr(), _stream_ptr(device)))
+    return idx, val, cnt

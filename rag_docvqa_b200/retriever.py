@@ -1,0 +1,353 @@
+"""Drop-in replacements for the reference's retrieval classes, backed by the sm_100a kernels.
+
+    Retriever(config).retrieve(...)         reference src/_modules.py:1967-2180
+    VisualRetriever(config).retrieve(...)   reference src/_modules.py:2183-2464
+
+Same constructor (one flat config dict, same keys), same call signatures, same output format
+(nested Python lists, PIL crops, per-document similarity tensors), so src/RAGVT5.py:105,244-252 and
+src/RAGPix2Struct.py:83,157-164 run unchanged (see rag_docvqa_b200/compat and INTEGRATION.md).
+
+What moved to the GPU: every similarity (fused cosine / MaxSim), the per-document top-k (one launch for
+the whole batch instead of >= 6 launches + k host syncs per document), and -- through
+`retrieve_packed` -- the gather into the generator's input tensors.  What stays on the host: building the
+Python list/PIL view of the <= k hits per document, which only touches the hits (the reference walks
+every word of every chunk, src/_modules.py:2032-2050).
+
+Differences from the reference, all within north_star's contract:
+  * ties are broken by LOWEST index (torch.topk's tie order is unspecified);
+  * VisualRetriever returns crops / page ids in sorted (group, rectangle) order (the reference's order is
+    Python-set iteration order, src/_modules.py:2428,2445).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import functional as F
+
+_LAYOUT_MAP_4 = {0: "title", 1: "text", 2: "figure", 3: "table"}   # src/_modules.py:308-313, 636-641
+
+
+def get_layout_model_map(config: dict) -> dict:
+    """reference src/_modules.py:246-253."""
+    return dict(_LAYOUT_MAP_4) if config.get("layout_model") in ("YOLO", "DIT") else {1: "text"}
+
+
+class StatComponent:
+    """Counter plumbing every reference component carries (src/_modules.py:178-243); `stats` is read by
+    RAGVT5 (src/RAGVT5.py:294).  The three config keys are REQUIRED, as in the reference."""
+
+    def __init__(self, config: dict):
+        self.compute_stats = config["compute_stats"]
+        self.compute_stats_examples = config["compute_stats_examples"] and self.compute_stats
+        self.n_stats_examples = config["n_stats_examples"]
+        self.stats: Dict[str, Any] = {}
+        self.stats_examples: Dict[str, Dict[Any, list]] = {}
+
+    def stat_sum(self, stat: str, key: Any, value: int = 1):
+        if self.compute_stats:
+            self.stats[stat][key] = self.stats[stat].get(key, 0) + value
+
+    def stat_subtract(self, stat: str, key: Any, value: int = 1):
+        return self.stat_sum(stat, key, -value)
+
+    def stat_add_example(self, stat: str, key: Any, example: Any):
+        if self.compute_stats_examples:
+            bucket = self.stats_examples[stat].setdefault(key, [])
+            if len(bucket) < self.n_stats_examples:
+                bucket.append(example)
+
+    def stat_remove_example(self, stat: str, key: Any, example: Any):
+        if self.compute_stats_examples and key in self.stats_examples[stat]:
+            try:
+                self.stats_examples[stat][key].remove(example)
+            except ValueError:
+                pass
+
+
+def _device_of(config: dict) -> torch.device:
+    dev = torch.device(config.get("device", "cuda"))
+    if dev.type != "cuda":
+        raise RuntimeError("rag_docvqa_b200 runs on CUDA devices only (config['device']=%r)" % (config.get("device"),))
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _to_device(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    return t if t.is_cuda else t.to(dev, non_blocking=True)
+
+
+def compact_chunk(words: Sequence[str], boxes: Sequence[Sequence[float]]):
+    """One chunk of Chunker.compact_chunks (src/_modules.py:1102-1132)."""
+    if len(boxes):
+        x0, y0, x1, y1 = zip(*boxes)
+        return " ".join(words), [min(x0), min(y0), max(x1), max(y1)]
+    return " ".join(words), [0, 0, 1, 1]
+
+
+def crop_rectangle(bbox, width: int, height: int):
+    """src/_modules.py:2108-2119: int() truncation, then order fix."""
+    x0, y0, x1, y1 = int(bbox[0] * width), int(bbox[1] * height), int(bbox[2] * width), int(bbox[3] * height)
+    return [min(x0, x1), min(y0, y1), max(x0, x1), max(y0, y1)]
+
+
+class Retriever(StatComponent):
+    def __init__(self, config: dict):
+        super().__init__(config)
+        self.k = config.get("chunk_num", 10)
+        self.include_surroundings = config.get("include_surroundings", 0)
+        self.layout_map = get_layout_model_map(config)
+        self.reorder_chunks = config.get("reorder_chunks", False)
+        self.device = _device_of(config)
+        if self.compute_stats:
+            self.stats["layout_labels_topk_dist"] = {label: 0 for label in self.layout_map.values()}
+
+    # -- a4 -----------------------------------------------------------------------------------------
+    def _get_similarities(self, text_embeddings: List[torch.Tensor], question_embeddings: torch.Tensor):
+        return self._score_topk(text_embeddings, question_embeddings).similarities
+
+    def _score_topk(self, text_embeddings, question_embeddings) -> F.ScoreTopK:
+        dev = question_embeddings.device if question_embeddings.is_cuda else self.device
+        emb = [_to_device(e, dev) for e in text_embeddings]
+        return F.score_topk(emb, _to_device(question_embeddings, dev), int(self.k))
+
+    # -- a7/a8/a9: host view of the hits ----------------------------------------------------------------
+    def _hit_lists(self, hits: Sequence[Sequence[int]], words_text_chunks, words_box_chunks,
+                   layout_labels_chunks, images, page_indices):
+        s = self.include_surroundings
+        bs = len(hits)
+        out_text, out_bbox, out_labels, out_words, out_boxes, out_wlabels, out_patches, out_pages = (
+            [], [], [], [], [], [], [], [])
+        for b in range(bs):
+            doc_hits = hits[b]
+            labels = [layout_labels_chunks[b][i] for i in doc_hits]
+            pages = [page_indices[b][i] for i in doc_hits]
+            words_b, boxes_b = words_text_chunks[b], words_box_chunks[b]
+            d_words, d_boxes = [], []
+            if s == 0:
+                # ranges of distinct chunks are disjoint in the page word list: the dedup is a no-op
+                for i in doc_hits:
+                    d_words.append(list(words_b[i]))
+                    d_boxes.append(list(boxes_b[i]))
+            else:
+                page_arr = np.asarray(page_indices[b])
+                page_view = {}     # page -> (chunk ids on the page, start offsets, page length)
+                emitted = {}       # page -> list of raw [lo, hi) ranges of better hits
+                for i, p in zip(doc_hits, pages):
+                    if p not in page_view:
+                        ids = np.nonzero(page_arr == p)[0]
+                        lens = np.fromiter((len(words_b[c]) for c in ids), dtype=np.int64, count=len(ids))
+                        starts = np.cumsum(lens) - lens
+                        page_view[p] = (ids, starts, int(lens.sum()), lens)
+                        emitted[p] = []
+                    ids, starts, page_len, lens = page_view[p]
+                    slot = int(np.searchsorted(ids, i))
+                    start = int(starts[slot])
+                    lo, hi = max(0, start - s), min(page_len, start + int(lens[slot]) + s)
+                    fresh = [(lo, hi)]
+                    for (cl, ch) in emitted[p]:
+                        nxt = []
+                        for (a, z) in fresh:
+                            if ch <= a or cl >= z:
+                                nxt.append((a, z))
+                                continue
+                            if a < cl:
+                                nxt.append((a, cl))
+                            if ch < z:
+                                nxt.append((ch, z))
+                        fresh = nxt
+                    emitted[p].append((lo, hi))
+                    w_out, b_out = [], []
+                    for (a, z) in fresh:
+                        first = int(np.searchsorted(starts + lens, a, side="right"))
+                        for sl in range(first, len(ids)):
+                            cs = int(starts[sl])
+                            if cs >= z:
+                                break
+                            c = int(ids[sl])
+                            x0, x1 = max(a, cs) - cs, min(z, cs + int(lens[sl])) - cs
+                            if x0 < x1:
+                                w_out.extend(words_b[c][x0:x1])
+                                b_out.extend(boxes_b[c][x0:x1])
+                    d_words.append(w_out)
+                    d_boxes.append(b_out)
+            texts, bboxes = [], []
+            for w, bx in zip(d_words, d_boxes):
+                t, bb = compact_chunk(w, bx)
+                texts.append(t)
+                bboxes.append(bb)
+            wlabels = [[labels[j]] * len(d_words[j]) for j in range(len(d_words))]
+            patches = []
+            for j, p in enumerate(pages):
+                page = images[b][p]
+                patches.append(page.crop(crop_rectangle(bboxes[j], page.width, page.height)))
+            if self.reorder_chunks:
+                order = sorted(range(len(pages)), key=lambda j: (pages[j], bboxes[j][1], bboxes[j][0]))
+                texts = [texts[j] for j in order]
+                bboxes = [bboxes[j] for j in order]
+                labels = [labels[j] for j in order]
+                d_words = [d_words[j] for j in order]
+                d_boxes = [d_boxes[j] for j in order]
+                wlabels = [wlabels[j] for j in order]
+                patches = [patches[j] for j in order]
+                pages = [pages[j] for j in order]
+            out_text.append(texts); out_bbox.append(bboxes); out_labels.append(labels)
+            out_words.append(d_words); out_boxes.append(d_boxes); out_wlabels.append(wlabels)
+            out_patches.append(patches); out_pages.append(pages)
+        return out_text, out_bbox, out_labels, out_words, out_boxes, out_wlabels, out_patches, out_pages
+
+    def _get_top_k(self, similarities: List[torch.Tensor], words_text_chunks, words_box_chunks,
+                   layout_labels_chunks, images, page_indices):
+        """Same signature as the reference (src/_modules.py:1999): top-k of given similarity vectors."""
+        dev = self.device
+        sims = [_to_device(s_b, dev) for s_b in similarities]
+        idx, _val, cnt = F.topk_segments(sims, int(self.k))
+        hits = self._hits_to_host(idx, cnt)
+        return self._hit_lists(hits, words_text_chunks, words_box_chunks, layout_labels_chunks, images, page_indices)
+
+    @staticmethod
+    def _hits_to_host(topk_idx: torch.Tensor, topk_cnt: torch.Tensor) -> List[List[int]]:
+        packed = torch.cat([topk_idx, topk_cnt.unsqueeze(1)], dim=1).cpu().numpy()   # ONE D2H copy + sync
+        k = topk_idx.shape[1]
+        return [packed[b, :packed[b, k]].tolist() for b in range(packed.shape[0])]
+
+    # -- a11 -----------------------------------------------------------------------------------------
+    def retrieve(self, text_embeddings: List[torch.Tensor], question_embeddings: torch.Tensor,
+                 words_text_chunks: list, words_box_chunks: list, layout_labels_chunks: list,
+                 images: list, page_indices: list) -> tuple:
+        """Retrieve the top-k chunks: 9-tuple, see reference src/_modules.py:2144-2153, 2180."""
+        inputs_on_host = not question_embeddings.is_cuda
+        res = self._score_topk(text_embeddings, question_embeddings)
+        hits = self._hits_to_host(res.topk_idx, res.topk_cnt)
+        lists = self._hit_lists(hits, words_text_chunks, words_box_chunks, layout_labels_chunks, images, page_indices)
+        sims = res.similarities
+        if inputs_on_host:      # similarities live on the embeddings' device (src/_modules.py:1990-1995)
+            flat = res.sims.cpu()
+            sims = list(torch.split(flat, res.sizes))
+        return (*lists, sims)
+
+    def retrieve_packed(self, text_embeddings, question_embeddings, store, prompt_ids, sep_ids=(),
+                        eos_id: int = 1, pad_id: int = 0, max_source_length: int = 512,
+                        with_layout_labels: bool = False):
+        """B200-native fast path: score -> top-k -> device gather straight into the generator's
+        input_ids / boxes / attention_mask (what flatten + VT5.prepare_inputs_for_vqa build on the host,
+        src/utils.py:233-253, src/VT5.py:141-185) for a pre-tokenised `DocStore`.  No Python lists."""
+        res = self._score_topk(text_embeddings, question_embeddings)
+        packed = store.gather(res.topk_idx, res.topk_cnt, prompt_ids, include_surroundings=self.include_surroundings,
+                              reorder_chunks=self.reorder_chunks, sep_ids=sep_ids, eos_id=eos_id, pad_id=pad_id,
+                              max_len=max_source_length, with_layout_labels=with_layout_labels)
+        return packed, res
+
+
+# ====================================================================================================
+# visual path
+# ====================================================================================================
+def _surrounding_cells(row: int, col: int, n_rows: int, n_cols: int, include_surroundings):
+    """Neighbourhood pattern of reference src/_modules.py:2207-2282."""
+    cells = set()
+    if isinstance(include_surroundings, (tuple, list)) and len(include_surroundings) == 2:
+        rx, ry = include_surroundings
+        for r in range(row - ry, row + ry + 1):
+            for c in range(col - rx, col + rx + 1):
+                cells.add((r, c))
+    else:
+        level, phase = divmod(int(include_surroundings), 3)
+        for r in range(row - level, row + level + 1):
+            for c in range(col - level, col + level + 1):
+                cells.add((r, c))
+            if phase > 0:
+                cells.add((r, col - level - 1))
+                cells.add((r, col + level + 1))
+        if phase > 1:
+            for c in range(col - level, col + level + 1):
+                cells.add((row - level - 1, c))
+                cells.add((row + level + 1, c))
+    return [(r, c) for (r, c) in cells if 0 <= r < n_rows and 0 <= c < n_cols]
+
+
+def _merge_rectangles(rects: List[Sequence[float]]) -> List[List[float]]:
+    """Bounding box of every connected component of the strict-overlap graph
+    (src/_modules.py:2331-2375, overlap test src/utils.py:460-463)."""
+    n = len(rects)
+    parent = list(range(n))
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+    for i in range(n):
+        a = rects[i]
+        for j in range(i + 1, n):
+            b = rects[j]
+            if a[0] < b[2] and a[2] > b[0] and a[1] < b[3] and a[3] > b[1]:
+                parent[find(i)] = find(j)
+    comps: Dict[int, list] = {}
+    for i in range(n):
+        comps.setdefault(find(i), []).append(rects[i])
+    return sorted([min(r[0] for r in comp), min(r[1] for r in comp), max(r[2] for r in comp),
+                   max(r[3] for r in comp)] for comp in comps.values())
+
+
+class VisualRetriever:
+    def __init__(self, config: dict):
+        self.k = config.get("chunk_num", 10)
+        self.include_surroundings = config.get("include_surroundings", 0)
+        self.mode = config.get("chunk_mode", "horizontal")
+        self.layout_map = get_layout_model_map(config)
+        self.device = _device_of(config)
+
+    def _get_similarities(self, patch_embeddings: List[torch.Tensor], question_embeddings: torch.Tensor):
+        dev = question_embeddings.device if question_embeddings.is_cuda else self.device
+        q = _to_device(question_embeddings, dev)
+        return [F.late_interaction(q[i].unsqueeze(0), _to_device(patch_embeddings[i], dev))
+                for i in range(len(patch_embeddings))]
+
+    def _get_surrounding_patches(self, patch_coord, patches_matrix, include_surroundings=0):
+        n_rows = len(patches_matrix)
+        n_cols = len(patches_matrix[0]) if n_rows > 0 else 0
+        return _surrounding_cells(patch_coord[0], patch_coord[1], n_rows, n_cols, include_surroundings)
+
+    def _get_top_k(self, similarities, patches_flatten_indices, patches_matrix_list, patches_xyxy, images):
+        bs = len(similarities)
+        if bs == 0:
+            return [], []
+        # a document without strips still carries a (1,) dummy score (ImageEncoder returns zeros(1,2048,768),
+        # src/_modules.py:1663-1664): it must not contribute hits  (src/_modules.py:2403-2406)
+        idx, _val, cnt = F.topk_segments([_to_device(s_b, self.device) for s_b in similarities], int(self.k))
+        hits = Retriever._hits_to_host(idx, cnt)
+        crops_all, pages_all = [], []
+        for b in range(bs):
+            flat = np.asarray(patches_flatten_indices[b])
+            if len(flat) == 0:
+                crops_all.append([])
+                pages_all.append([])
+                continue
+            cells = set()
+            for i in hits[b]:
+                group = int(flat[i])
+                row = int(i - np.count_nonzero(flat < group))      # src/_modules.py:2411-2412
+                if self.mode == "square":
+                    raise NotImplementedError()                    # src/_modules.py:2413-2414
+                matrix = patches_matrix_list[b][group]
+                for (r, c) in self._get_surrounding_patches((row, 0), matrix, self.include_surroundings):
+                    cells.add((group, r, c))
+            by_group: Dict[int, list] = {}
+            for (g, r, c) in cells:
+                by_group.setdefault(g, []).append(list(patches_xyxy[b][g][r]))
+            crops = []
+            for g in sorted(by_group):
+                for rect in _merge_rectangles(by_group[g]):
+                    crops.append(images[b][g].crop(tuple(rect)))   # src/_modules.py:2381
+            crops_all.append(crops)
+            pages_all.append(sorted(int(g) for g in by_group))
+        return crops_all, pages_all
+
+    def retrieve(self, patch_embeddings: List[torch.Tensor], question_embeddings: torch.Tensor,
+                 patches_flatten_indices: list, patches_matrix_list: list, patches_xyxy: list,
+                 images: List[list]) -> tuple:
+        similarities = self._get_similarities(patch_embeddings, question_embeddings)
+        return self._get_top_k(similarities, patches_flatten_indices, patches_matrix_list, patches_xyxy, images)

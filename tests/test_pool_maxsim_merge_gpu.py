@@ -1,0 +1,115 @@
+"""GPU parity: mean pooling, MaxSim late interaction, stand-alone top-k and shard merge vs the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import compare
+from oracle import ref_restated as R
+from rag_docvqa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# fp32 tolerances, stated: pooling and MaxSim differ from torch only in summation order.
+POOL_RTOL, POOL_ATOL = 1e-5, 1e-6
+MAXSIM_RTOL = 1e-5          # north_star: scores within 1e-5 relative
+
+
+def test_mean_pooling_golden(golden_dir):
+    from rag_docvqa_b200 import functional as F
+    z = np.load(os.path.join(golden_dir, "mean_pooling.npz"))
+    got = F.mean_pooling(torch.from_numpy(z["embs"]).to(DEV), torch.from_numpy(z["mask"]).to(DEV))
+    np.testing.assert_allclose(got.cpu().numpy(), z["pooled"], rtol=POOL_RTOL, atol=POOL_ATOL)
+    assert (got[:2] == 0).all()          # all-pad rows -> exactly 0 (clamp 1e-9)
+
+
+@pytest.mark.parametrize("n,d,mean_len", [(64, 384, 96), (33, 768, 40), (20, 1024, 200), (9, 100, 12),
+                                          (5, 2048, 30), (40, 64, 8)])
+def test_mean_pooling_shapes(n, d, mean_len):
+    from rag_docvqa_b200 import functional as F
+    embs, mask = synth.make_token_batch(n, d, 11 + n, mean_len=mean_len, std_len=mean_len / 4, min_len=0,
+                                        max_len=512, all_pad_rows=1)
+    ref = R.mean_pooling(embs, mask)
+    got = F.mean_pooling(embs.to(DEV), mask.to(DEV))
+    np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=POOL_RTOL, atol=POOL_ATOL)
+
+
+def test_mean_pooling_weighted_mask_and_normalise():
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(2)
+    embs = torch.randn(12, 50, 384, generator=g)
+    mask = torch.randint(0, 3, (12, 50), generator=g)          # the reference multiplies by the mask VALUE
+    ref = R.mean_pooling(embs, mask)
+    got, bf, nrm = F.mean_pooling(embs.to(DEV), mask.to(DEV), out_bf16=True, return_norm=True)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=POOL_RTOL, atol=POOL_ATOL)
+    np.testing.assert_allclose(nrm.cpu().numpy(), ref.norm(dim=-1).numpy(), rtol=1e-5)
+    assert torch.equal(bf.cpu(), got.cpu().to(torch.bfloat16))
+    gotn = F.mean_pooling(embs.to(DEV), mask.to(DEV), normalise=True)
+    refn = torch.nn.functional.normalize(ref, p=2, dim=-1)
+    np.testing.assert_allclose(gotn.cpu().numpy(), refn.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_late_interaction_golden(golden_dir):
+    from rag_docvqa_b200 import functional as F
+    z = np.load(os.path.join(golden_dir, "late_interaction.npz"))
+    q = torch.from_numpy(z["q"]).to(DEV)
+    for b, (pk, sk) in enumerate((("p0", "s0"), ("p1", "s1"))):
+        got = F.late_interaction(q[b:b + 1], torch.from_numpy(z[pk]).to(DEV))
+        np.testing.assert_allclose(got.cpu().numpy(), z[sk], rtol=MAXSIM_RTOL)
+
+
+@pytest.mark.parametrize("n,Lq,Lp,d", [(3, 128, 128, 64), (5, 200, 77, 96), (2, 2048, 2048, 768), (7, 1, 300, 768),
+                                       (4, 130, 1, 36), (1, 257, 513, 20)])
+def test_late_interaction_shapes(n, Lq, Lp, d):
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(n * 1000 + Lq)
+    q = torch.randn(1, Lq, d, generator=g)
+    p = torch.randn(n, Lp, d, generator=g)
+    p[0, 0] = 0.0                                               # zero token: F.normalize eps path
+    ref64 = R.late_interaction_f64(q, p).numpy()
+    ref32 = R.late_interaction(q, p).numpy()
+    got = F.late_interaction(q.to(DEV), p.to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(got, ref64, rtol=MAXSIM_RTOL)
+    # no further from the float64 truth than torch's own fp32 result is (x4 slack)
+    assert np.abs(got - ref64).max() <= 4 * max(np.abs(ref32 - ref64).max(), 1e-6 * np.abs(ref64).max())
+
+
+def test_topk_segments_matches_oracle():
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(8)
+    scores = [torch.randn(n, generator=g) for n in (50, 0, 3, 20000, 1)]
+    scores[0][7] = scores[0][3]
+    scores[3][100:200] = 5.0
+    idx, val, cnt = F.topk_segments([s.to(DEV) for s in scores], 10)
+    idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+    for b, s in enumerate(scores):
+        kb = min(10, len(s))
+        assert cnt[b] == kb
+        np.testing.assert_array_equal(idx[b, :kb], R.topk_lowest_index(s, 10))
+        assert (idx[b, kb:] == -1).all()
+
+
+@pytest.mark.parametrize("world,k", [(2, 10), (8, 10), (4, 5)])
+def test_topk_merge_equals_unsharded(world, k):
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(world)
+    Q, n = 37, 4000
+    scores = torch.randn(Q, n, generator=g)
+    scores[:, 100] = scores[:, 3000]                            # cross-shard exact ties
+    shard = n // world
+    cv, ci = [], []
+    for r in range(world):
+        part = scores[:, r * shard:(r + 1) * shard]
+        loc = np.stack([R.topk_lowest_index(part[qi], k) for qi in range(Q)])
+        ci.append(torch.from_numpy(loc + r * shard))
+        cv.append(torch.gather(part, 1, torch.from_numpy(loc)))
+    cand_v, cand_i = torch.cat(cv, 1), torch.cat(ci, 1)
+    cand_i[0, 3] = -1                                           # an empty slot is skipped
+    out_v, out_i = F.topk_merge(cand_v.to(DEV), cand_i.to(DEV), k)
+    ref_v, ref_i = R.merge_topk(cand_v.numpy(), cand_i.numpy(), k)
+    np.testing.assert_array_equal(out_i.cpu().numpy(), ref_i)
+    np.testing.assert_array_equal(out_v.cpu().numpy(), ref_v)
+    for qi in range(1, Q):                                      # equals the unsharded selection
+        np.testing.assert_array_equal(out_i[qi].cpu().numpy(), R.topk_lowest_index(scores[qi], k))

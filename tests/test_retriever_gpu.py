@@ -1,0 +1,197 @@
+"""GPU parity of the drop-in classes against the reference's frozen outputs (tests/golden) and the
+oracle: Retriever.retrieve 9-tuple, VisualRetriever.retrieve, and the device gather (packed VT5 inputs)."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import compare
+from oracle import ref_restated as R
+from rag_docvqa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BASE = {"compute_stats": False, "compute_stats_examples": False, "n_stats_examples": 0, "device": DEV}
+
+
+def digest(im):
+    return [im.size[0], im.size[1], zlib.crc32(im.convert("RGB").tobytes()) & 0xFFFFFFFF]
+
+
+def load_retrieve_inputs(golden_dir):
+    with open(os.path.join(golden_dir, "retrieve_lists.json")) as f:
+        gold = json.load(f)
+    z = np.load(os.path.join(golden_dir, "retrieve_inputs.npz"))
+    sizes, cpp = gold["sizes"], gold["chunks_per_page"]
+    emb = [torch.from_numpy(z["emb_%d" % b]) for b in range(len(sizes))]
+    q = torch.from_numpy(z["q"])
+    words, boxes, labels = synth.make_words(sizes, gold["words_seed"], min_words=3, max_words=9, empty_chunk_every=11)
+    pages = synth.make_page_indices(sizes, cpp)
+    images = synth.make_images(sizes, cpp, width=gold["image_wh"][0], height=gold["image_wh"][1], ragged_sizes=True)
+    return gold, emb, q, words, boxes, labels, images, pages
+
+
+def assert_same_lists(out, ref):
+    for i in (0, 1, 2, 3, 4, 5, 7):
+        assert out[i] == ref[i], "output %d differs" % i
+    assert [[digest(im) for im in doc] for doc in out[6]] == ref[6]
+
+
+@pytest.mark.parametrize("on_device", [True, False])
+def test_retrieve_matches_reference_golden(golden_dir, on_device):
+    from rag_docvqa_b200.retriever import Retriever
+    gold, emb, q, words, boxes, labels, images, pages = load_retrieve_inputs(golden_dir)
+    emb_in = [e.to(DEV) for e in emb] if on_device else emb
+    q_in = q.to(DEV) if on_device else q
+    for var in gold["variants"]:
+        retr = Retriever({**BASE, "chunk_num": var["k"], "include_surroundings": var["include_surroundings"],
+                          "reorder_chunks": var["reorder_chunks"]})
+        out = retr.retrieve(emb_in, q_in, words, boxes, labels, images, pages)
+        ref = [var[key] for key in ("top_k_text", "top_k_boxes", "top_k_layout_labels", "top_k_words_text",
+                                    "top_k_words_boxes", "top_k_words_layout_labels", "top_k_patches",
+                                    "top_k_page_indices")]
+        assert_same_lists(out, ref[:6] + [ref[6]] + [ref[7]])
+        assert len(out[8]) == len(emb)
+        for b, s in enumerate(out[8]):
+            assert s.is_cuda == on_device
+            compare.assert_scores_close(s.cpu().numpy(), np.array(var["similarities"][b], dtype=np.float32))
+
+
+@pytest.mark.parametrize("s,reorder", [(0, False), (0, True), (2, False), (5, True), (40, False)])
+def test_retrieve_c2_slice_vs_oracle(s, reorder):
+    from rag_docvqa_b200.retriever import Retriever
+    batch = synth.make_text_batch("C2", with_lists=True, docs=10, seed=77, dup_frac=0.0)
+    args = (batch["words_text_chunks"], batch["words_box_chunks"], batch["layout_labels_chunks"],
+            batch["images"], batch["page_indices"])
+    retr = Retriever({**BASE, "chunk_num": 5, "include_surroundings": s, "reorder_chunks": reorder})
+    out = retr.retrieve([e.to(DEV) for e in batch["text_embeddings"]], batch["question_embeddings"].to(DEV), *args)
+    # the oracle gathers for the SAME hits (index parity is covered in test_score_topk_gpu.py)
+    sims = [x.cpu() for x in out[8]]
+    hits = [R.topk_lowest_index(x, 5) for x in sims]
+    ref_sims = R.score(batch["text_embeddings"], batch["question_embeddings"])
+    for b in range(len(hits)):
+        compare.assert_topk_matches(hits[b], sims[b].numpy(), ref_sims[b].numpy(), 5)
+    ref = R.gather_hits(hits, *args, include_surroundings=s, reorder_chunks=reorder)
+    for i in (0, 1, 2, 3, 4, 5, 7):
+        assert out[i] == ref[i], "output %d differs" % i
+    assert [[digest(im) for im in doc] for doc in out[6]] == [[digest(im) for im in doc] for doc in ref[6]]
+
+
+def test_retriever_contract_attributes():
+    from rag_docvqa_b200.retriever import Retriever, VisualRetriever
+    with pytest.raises(KeyError):
+        Retriever({"chunk_num": 3})                      # the three stat keys are required (reference :180-182)
+    r = Retriever({**BASE, "compute_stats": True, "layout_model": "YOLO"})
+    assert r.k == 10 and r.include_surroundings == 0 and r.reorder_chunks is False
+    assert r.stats == {"layout_labels_topk_dist": {"title": 0, "text": 0, "figure": 0, "table": 0}}
+    assert r.layout_map[1] == "text"
+    v = VisualRetriever({"chunk_num": 5, "device": DEV})
+    assert v.k == 5 and v.mode == "horizontal"
+    out = Retriever({**BASE, "chunk_num": 3}).retrieve([torch.zeros(0, 8)], torch.zeros(1, 8).to(DEV), [[]], [[]], [[]], [[]], [[]])
+    assert [o for o in out[:8]] == [[[]]] * 8 and out[8][0].shape == (0,)
+
+
+def test_visual_retrieve_golden(golden_dir):
+    from PIL import Image
+    from rag_docvqa_b200.retriever import VisualRetriever
+    with open(os.path.join(golden_dir, "visual_retrieve.json")) as f:
+        gold = json.load(f)
+    z = np.load(os.path.join(golden_dir, "visual_inputs.npz"))
+    rng = np.random.RandomState(5)
+    flat, mats, xyxy, images, patches = [], [], [], [], []
+    for b, doc in enumerate(gold["docs"]):
+        f_b, imgs, m_b = [], [], []
+        for g, n_rows in enumerate(doc["groups"]):
+            W, H = doc["image_wh"][g]
+            page = Image.fromarray(rng.randint(0, 255, size=(H, W, 3)).astype(np.uint8), "RGB")
+            imgs.append(page)
+            m_b.append([[page.crop(tuple(rc))] for rc in doc["xyxy"][g]])
+            f_b.extend([g] * n_rows)
+        flat.append(np.array(f_b, dtype=np.int64)); mats.append(m_b); xyxy.append(doc["xyxy"]); images.append(imgs)
+        patches.append(torch.from_numpy(z["p_%d" % b]).to(DEV))
+    q = torch.from_numpy(z["q"]).to(DEV)
+    for var in gold["variants"]:
+        s = tuple(var["include_surroundings"]) if isinstance(var["include_surroundings"], list) else var["include_surroundings"]
+        vr = VisualRetriever({"chunk_num": var["k"], "include_surroundings": s, "chunk_mode": "horizontal", "device": DEV})
+        sims = vr._get_similarities(patches, q)
+        for b in range(len(patches)):
+            np.testing.assert_allclose(sims[b].cpu().numpy(), np.array(var["sims"][b], dtype=np.float32), rtol=1e-5)
+        crops, page_ids = vr.retrieve(patches, q, flat, mats, xyxy, images)
+        assert [sorted(digest(im) for im in doc) for doc in crops] == var["crops"]
+        assert [sorted(doc) for doc in page_ids] == var["pages"]
+    with pytest.raises(NotImplementedError):
+        VisualRetriever({"chunk_num": 1, "chunk_mode": "square", "device": DEV}).retrieve(patches, q, flat, mats, xyxy, images)
+
+
+# ---------------------------------------------------------------------------------------------------
+# device gather -> packed VT5 inputs
+# ---------------------------------------------------------------------------------------------------
+def prompts_for(questions):
+    return [[5 + (zlib.crc32(t.encode()) % 1000) for t in ("question: {:s}  context: ".format(qs)).split()]
+            for qs in questions]
+
+
+def test_packed_inputs_match_reference_golden(golden_dir):
+    """tests/golden/vt5_pack.json holds what the reference's flatten + VT5.prepare_inputs_for_vqa built."""
+    from rag_docvqa_b200.docstore import DocStore
+    from rag_docvqa_b200.retriever import Retriever
+    gold, emb, q, words, boxes, labels, images, pages = load_retrieve_inputs(golden_dir)
+    with open(os.path.join(golden_dir, "vt5_pack.json")) as f:
+        packs = json.load(f)
+    table = synth.make_tokens_for_words(words, seed=packs["word_table_seed"])
+    store = DocStore.from_lists(words, boxes, labels, pages, lambda w: table.get(w, [2]), torch.device(DEV), images=images)
+    prompts = prompts_for(packs["questions"])
+    retr = Retriever({**BASE, "chunk_num": packs["k"]})
+    for var in packs["variants"]:
+        sep_ids = [2] if var["sep"] else []                      # FakeTokenizer maps unknown words to [2]
+        packed, res = retr.retrieve_packed([e.to(DEV) for e in emb], q.to(DEV), store, prompts, sep_ids=sep_ids,
+                                           max_source_length=var["max_source_length"],
+                                           with_layout_labels=var["use_layout_labels"] == "Embed")
+        assert packed.input_ids.cpu().tolist() == var["input_ids"]
+        assert packed.boxes.cpu().tolist() == var["boxes"]
+        assert packed.attention_mask.cpu().tolist() == var["attention_mask"]
+        if var["layout_labels"] is not None:
+            assert packed.layout_labels.cpu().tolist() == var["layout_labels"]
+
+
+@pytest.mark.parametrize("s,reorder,sep", [(0, False, False), (3, False, True), (7, True, True), (200, True, False)])
+def test_packed_inputs_vs_oracle_c2_slice(s, reorder, sep):
+    from rag_docvqa_b200.docstore import DocStore
+    from rag_docvqa_b200.retriever import Retriever
+    batch = synth.make_text_batch("C2", with_lists=True, docs=12, seed=55, dup_frac=0.0)
+    words, boxes, labels = batch["words_text_chunks"], batch["words_box_chunks"], batch["layout_labels_chunks"]
+    pages, images = batch["page_indices"], batch["images"]
+    table = synth.make_tokens_for_words(words, seed=9)
+    tok = lambda w: table.get(w, [2])
+    store = DocStore.from_lists(words, boxes, labels, pages, tok, torch.device(DEV), images=images)
+    questions = ["what is item %d about ?" % b for b in range(len(words))]
+    prompts = prompts_for(questions)
+    sep_ids = [2, 9] if sep else []
+    retr = Retriever({**BASE, "chunk_num": 5, "include_surroundings": s, "reorder_chunks": reorder})
+    packed, res = retr.retrieve_packed([e.to(DEV) for e in batch["text_embeddings"]],
+                                       batch["question_embeddings"].to(DEV), store, prompts, sep_ids=sep_ids,
+                                       max_source_length=512, with_layout_labels=True, )
+    hits = Retriever._hits_to_host(res.topk_idx, res.topk_cnt)
+    ref = R.gather_hits(hits, words, boxes, labels, images, pages, include_surroundings=s, reorder_chunks=reorder,
+                        crop=False)
+    sep_word = "<sep>" if sep else None
+    tok_ref = lambda w: sep_ids if w == "<sep>" else tok(w)
+    ids, bxs, mask, labs = R.vt5_pack(prompts, [R.flatten(x, sep_word) for x in ref[3]],
+                                      [R.flatten(x, sep_word) for x in ref[4]], tok_ref,
+                                      layout_labels=[R.flatten(x, sep_word) for x in ref[5]])
+    assert torch.equal(packed.input_ids.cpu(), ids)
+    assert torch.equal(packed.boxes.cpu(), bxs)
+    assert torch.equal(packed.attention_mask.cpu(), mask)
+    assert torch.equal(packed.layout_labels.cpu(), labs)
+    # hit metadata: bbox (a8), crop rectangle (a9), page / label, in output order
+    bbox = packed.hit_bbox.cpu().numpy(); rect = packed.hit_rect.cpu().numpy()
+    page = packed.hit_page.cpu().numpy(); label = packed.hit_label.cpu().numpy()
+    for b in range(len(words)):
+        for j in range(len(ref[1][b])):
+            assert bbox[b, j].tolist() == [float(x) for x in ref[1][b][j]]
+            assert rect[b, j].tolist() == ref[6][b][j]
+            assert page[b, j] == ref[7][b][j] and label[b, j] == ref[2][b][j]
+        assert (page[b, len(ref[1][b]):] == -1).all()
