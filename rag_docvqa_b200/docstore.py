@@ -139,11 +139,11 @@ class DocStore:
         return cls(arrays, B, device)
 
     # ------------------------------------------------------------------------------------------
-    def gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],
-               include_surroundings: int = 0, reorder_chunks: bool = False, sep_ids: Sequence[int] = (),
-               eos_id: int = 1, pad_id: int = 0, max_len: int = 512, with_layout_labels: bool = False,
-               max_seg: int = 32, prompt_cache=None) -> PackedInputs:
-        """Launches rdv_gather_vt5_inputs on the current stream; ONE small D2H read (full_len/status)."""
+    def prepare_gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],
+                       include_surroundings: int = 0, reorder_chunks: bool = False, sep_ids: Sequence[int] = (),
+                       eos_id: int = 1, pad_id: int = 0, max_len: int = 512, with_layout_labels: bool = False,
+                       max_seg: int = 32) -> "GatherPlan":
+        """Allocates the outputs and fills the argument block of rdv_gather_vt5_inputs (no launch)."""
         dev = self.device
         B, k = topk_idx.shape
         if B != self.B:
@@ -163,16 +163,17 @@ class DocStore:
         small = host.to(dev, non_blocking=True)
 
         i32 = dict(dtype=torch.int32, device=dev)
-        out_ids = torch.empty((B, max_len), dtype=torch.int64, device=dev)
-        out_boxes = torch.empty((B, max_len, 4), dtype=torch.int64, device=dev)
-        out_mask = torch.empty((B, max_len), dtype=torch.int64, device=dev)
-        out_labels = torch.empty((B, max_len), dtype=torch.int64, device=dev) if with_layout_labels else None
-        meta = torch.empty((2, B), **i32)                 # full_len, status
-        hit_i = torch.empty((4, B, k), **i32)             # chunk, page, label, nwords
-        hit_bbox = torch.empty((B, k, 4), dtype=torch.float64, device=dev)
-        hit_rect = torch.empty((B, k, 4), **i32)
-        seg_ws = torch.empty((B * k * max_seg * 2,), **i32)
-
+        t = dict(
+            small=small, topk_idx=topk_idx, topk_cnt=topk_cnt,
+            out_ids=torch.empty((B, max_len), dtype=torch.int64, device=dev),
+            out_boxes=torch.empty((B, max_len, 4), dtype=torch.int64, device=dev),
+            out_mask=torch.empty((B, max_len), dtype=torch.int64, device=dev),
+            out_labels=torch.empty((B, max_len), dtype=torch.int64, device=dev) if with_layout_labels else None,
+            meta=torch.empty((2, B), **i32),                  # full_len, status
+            hit_i=torch.empty((4, B, k), **i32),              # chunk, page, label, nwords
+            hit_bbox=torch.empty((B, k, 4), dtype=torch.float64, device=dev),
+            hit_rect=torch.empty((B, k, 4), **i32),
+            seg_ws=torch.empty((B * k * max_seg * 2,), **i32))
         a = _lib.GatherArgsStruct()
         a.topk_idx = topk_idx.data_ptr(); a.topk_cnt = topk_cnt.data_ptr()
         a.k = k; a.include_surroundings = int(include_surroundings); a.reorder_chunks = 1 if reorder_chunks else 0
@@ -180,19 +181,48 @@ class DocStore:
         a.prompt_off = small.data_ptr(); a.prompt_ids = small.data_ptr() + p_off.nbytes
         a.sep_ids = small.data_ptr() + o_sep
         a.eos_id = eos_id; a.pad_id = pad_id; a.max_len = max_len; a.max_seg = max_seg
-        a.seg_ws = seg_ws.data_ptr()
-        a.out_ids = out_ids.data_ptr(); a.out_boxes = out_boxes.data_ptr(); a.out_mask = out_mask.data_ptr()
-        a.out_labels = out_labels.data_ptr() if out_labels is not None else None
-        a.full_len = meta[0].data_ptr(); a.status = meta[1].data_ptr()
-        a.hit_chunk = hit_i[0].data_ptr(); a.hit_page = hit_i[1].data_ptr()
-        a.hit_label = hit_i[2].data_ptr(); a.hit_nwords = hit_i[3].data_ptr()
-        a.hit_bbox = hit_bbox.data_ptr(); a.hit_rect = hit_rect.data_ptr()
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib.rdv_gather_vt5_inputs(ctypes.byref(self.struct), ctypes.byref(a), _stream_ptr(dev)))
-        meta_h = meta.cpu()                               # the step's one device->host read
-        if int(meta_h[1].max()) if B else 0:
-            raise _lib.RdvError(_lib.E_LIMIT, "gather: segment workspace overflow, raise max_seg (%d)" % max_seg)
-        longest = min(int(meta_h[0].max()), max_len) if B else 0
-        return PackedInputs(out_ids[:, :longest], out_boxes[:, :longest], out_mask[:, :longest],
-                            out_labels[:, :longest] if out_labels is not None else None, longest,
-                            hit_i[0], hit_i[1], hit_i[2], hit_i[3], hit_bbox, hit_rect)
+        a.seg_ws = t["seg_ws"].data_ptr()
+        a.out_ids = t["out_ids"].data_ptr(); a.out_boxes = t["out_boxes"].data_ptr()
+        a.out_mask = t["out_mask"].data_ptr()
+        a.out_labels = t["out_labels"].data_ptr() if t["out_labels"] is not None else None
+        a.full_len = t["meta"][0].data_ptr(); a.status = t["meta"][1].data_ptr()
+        a.hit_chunk = t["hit_i"][0].data_ptr(); a.hit_page = t["hit_i"][1].data_ptr()
+        a.hit_label = t["hit_i"][2].data_ptr(); a.hit_nwords = t["hit_i"][3].data_ptr()
+        a.hit_bbox = t["hit_bbox"].data_ptr(); a.hit_rect = t["hit_rect"].data_ptr()
+        return GatherPlan(self, a, t, max_len, max_seg)
+
+    def gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],
+               **options) -> PackedInputs:
+        """prepare + launch rdv_gather_vt5_inputs on the current stream + ONE small D2H read."""
+        plan = self.prepare_gather(topk_idx, topk_cnt, prompt_ids, **options)
+        plan.launch()
+        return plan.finish()
+
+
+class GatherPlan:
+    """A filled argument block of rdv_gather_vt5_inputs: launch() enqueues the kernel (no sync),
+    finish() reads full_len/status back (the step's one device->host read) and slices the outputs."""
+
+    def __init__(self, store: DocStore, args, tensors: dict, max_len: int, max_seg: int):
+        self.store, self.args, self.t, self.max_len, self.max_seg = store, args, tensors, max_len, max_seg
+        self._ds_ref = ctypes.byref(store.struct)
+        self._args_ref = ctypes.byref(args)
+
+    def launch(self, stream: Optional[int] = None) -> None:
+        dev = self.store.device
+        rc = _lib.lib.rdv_gather_vt5_inputs(self._ds_ref, self._args_ref,
+                                            _stream_ptr(dev) if stream is None else stream)
+        if rc:
+            _lib.check(rc)
+
+    def finish(self) -> PackedInputs:
+        t = self.t
+        meta_h = t["meta"].cpu()
+        B = meta_h.shape[1]
+        if B and int(meta_h[1].max()):
+            raise _lib.RdvError(_lib.E_LIMIT, "gather: segment workspace overflow, raise max_seg (%d)" % self.max_seg)
+        longest = min(int(meta_h[0].max()), self.max_len) if B else 0
+        labels = t["out_labels"]
+        return PackedInputs(t["out_ids"][:, :longest], t["out_boxes"][:, :longest], t["out_mask"][:, :longest],
+                            labels[:, :longest] if labels is not None else None, longest,
+                            t["hit_i"][0], t["hit_i"][1], t["hit_i"][2], t["hit_i"][3], t["hit_bbox"], t["hit_rect"])

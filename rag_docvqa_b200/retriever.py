@@ -94,9 +94,45 @@ def crop_rectangle(bbox, width: int, height: int):
     return [min(x0, x1), min(y0, y1), max(x0, x1), max(y0, y1)]
 
 
+def _lazy_crop_class():
+    from PIL import Image
+
+    class LazyCrop(Image.Image):
+        """A PIL image whose pixels are cut out of `page` on first use -- the same deferred-load protocol
+        PIL's own file images follow (every PIL operation calls load() before touching the pixels), so it
+        behaves exactly like the eager `page.crop(rect)` of reference src/_modules.py:2119."""
+
+        def __init__(self, page, rect):
+            super().__init__()
+            self._page, self._rect = page, tuple(int(v) for v in rect)
+            self._mode = page.mode
+            self._size = (self._rect[2] - self._rect[0], self._rect[3] - self._rect[1])
+            self.info = dict(page.info)
+
+        def load(self):
+            if self._im is None and self._page is not None:
+                real = self._page.crop(self._rect)
+                self._im, self.palette = real.im, real.palette
+                self._page = None
+            return super().load()
+    return LazyCrop
+
+
+_LazyCrop = None
+
+
+def lazy_crop(page, rect):
+    global _LazyCrop
+    if _LazyCrop is None:
+        _LazyCrop = _lazy_crop_class()
+    return _LazyCrop(page, rect)
+
+
 class Retriever(StatComponent):
     def __init__(self, config: dict):
         super().__init__(config)
+        # optional key (default preserves the reference's eager crops): cut the patch pixels on first use
+        self.lazy_patches = bool(config.get("retrieval_lazy_patches", False))
         self.k = config.get("chunk_num", 10)
         self.include_surroundings = config.get("include_surroundings", 0)
         self.layout_map = get_layout_model_map(config)
@@ -183,7 +219,8 @@ class Retriever(StatComponent):
             patches = []
             for j, p in enumerate(pages):
                 page = images[b][p]
-                patches.append(page.crop(crop_rectangle(bboxes[j], page.width, page.height)))
+                rect = crop_rectangle(bboxes[j], page.width, page.height)
+                patches.append(lazy_crop(page, rect) if self.lazy_patches else page.crop(rect))
             if self.reorder_chunks:
                 order = sorted(range(len(pages)), key=lambda j: (pages[j], bboxes[j][1], bboxes[j][0]))
                 texts = [texts[j] for j in order]

@@ -125,14 +125,22 @@ def make_words(sizes: List[int], seed: int, min_words: int = 40, max_words: int 
 
 
 def make_images(sizes: List[int], chunks_per_page: int, width: int = 850, height: int = 1100,
-                ragged_sizes: bool = False):
-    """One blank-ish RGB page per page index (PIL).  Content is a cheap gradient so crops differ."""
+                ragged_sizes: bool = False, share_pool: int = 0):
+    """One blank-ish RGB page per page index (PIL).  Content is a cheap gradient so crops differ.
+    share_pool > 0: documents share a pool of that many distinct page images (bench memory saver;
+    every document still indexes its own page list)."""
     from PIL import Image
     out = []
+    pool = {}
     for b, n in enumerate(sizes):
         n_pages = max(1, -(-n // chunks_per_page))
         pages = []
         for p in range(n_pages):
+            if share_pool:
+                key = (b * 7 + p) % share_pool
+                if key in pool:
+                    pages.append(pool[key])
+                    continue
             w = width + (17 * p if ragged_sizes else 0)
             h = height - (13 * p if ragged_sizes else 0)
             arr = np.empty((h, w, 3), dtype=np.uint8)
@@ -140,27 +148,32 @@ def make_images(sizes: List[int], chunks_per_page: int, width: int = 850, height
             arr[..., 1] = (np.arange(h, dtype=np.uint32) * 255 // max(1, h - 1)).astype(np.uint8)[:, None]
             arr[..., 2] = (b * 37 + p * 11) % 256
             pages.append(Image.fromarray(arr, "RGB"))
+            if share_pool:
+                pool[(b * 7 + p) % share_pool] = pages[-1]
         out.append(pages)
     return out
 
 
 def make_text_batch(name: str, with_lists: bool = False, device="cpu", normalised: bool = True,
                     seed: Optional[int] = None, docs: Optional[int] = None, full: bool = False,
-                    dup_frac: float = 0.01, ragged_edge_cases: bool = True, with_images: bool = True):
-    """One batch of workload `name` (C1/C2/C3).  `docs` overrides B (for slices)."""
+                    dup_frac: float = 0.01, ragged_edge_cases: bool = True, with_images: bool = True,
+                    share_image_pool: int = 0, emb_seed: Optional[int] = None):
+    """One batch of workload `name` (C1/C2/C3).  `docs` overrides B (for slices); `emb_seed` reseeds the
+    embedding VALUES only (same document sizes / lists) -- used to rotate distinct resident batches."""
     w = WORKLOADS[name]
     if docs is not None:
         w = dataclasses.replace(w, docs=docs)
     seed = SEED_BASE + w.config_id if seed is None else seed
     sizes = doc_sizes(w, seed, ragged_edge_cases=ragged_edge_cases, full=full)
-    emb, q = make_embeddings(sizes, w.dim, seed, device=device, normalised=normalised, dup_frac=dup_frac)
+    emb, q = make_embeddings(sizes, w.dim, seed if emb_seed is None else emb_seed, device=device,
+                             normalised=normalised, dup_frac=dup_frac)
     batch = dict(workload=w, sizes=sizes, text_embeddings=emb, question_embeddings=q,
                  page_indices=make_page_indices(sizes, w.chunks_per_page))
     if with_lists:
         words, boxes, labels = make_words(sizes, seed + 7)
         batch.update(words_text_chunks=words, words_box_chunks=boxes, layout_labels_chunks=labels)
         if with_images:
-            batch["images"] = make_images(sizes, w.chunks_per_page)
+            batch["images"] = make_images(sizes, w.chunks_per_page, share_pool=share_image_pool)
     return batch
 
 
