@@ -279,7 +279,7 @@ def run_ours(args):
     R = max(2, min(16, int(np.ceil(2.2 * L2_BYTES / max(1, step_bytes)))))
     batches = [synth.make_text_batch(args.workload, device=dev, seed=base_seed, emb_seed=base_seed + 1000 * (r + 1))
                for r in range(R)]
-    tables = [F.build_doc_table(b["text_embeddings"], w.dim, dev) for b in batches]
+    tables = [F.build_doc_table(b["text_embeddings"], w.dim, dev, algo=args.algo) for b in batches]
     outs = [dict(sims=torch.empty(t.total_rows, dtype=torch.float32, device=dev),
                  idx=torch.empty((t.B, w.k), dtype=torch.int32, device=dev),
                  val=torch.empty((t.B, w.k), dtype=torch.float32, device=dev),
@@ -289,9 +289,9 @@ def run_ours(args):
     score_fn = _lib.lib.rdv_score_topk_f32
     score_args = []
     for t, o, b in zip(tables, outs, batches):
-        p_ptr, p_row, p_tile = t.pointers()
-        score_args.append((p_ptr, p_row, p_tile, b["question_embeddings"].data_ptr(), t.B, t.d, w.k, t.tile_rows,
-                           t.total_tiles, t.max_rows, o["sims"].data_ptr(), o["idx"].data_ptr(),
+        p_tiles, p_row = t.pointers()
+        score_args.append((p_tiles, t.total_tiles, t.tile_rows, t.algo, p_row, b["question_embeddings"].data_ptr(),
+                           t.B, t.d, w.k, t.max_rows, o["sims"].data_ptr(), o["idx"].data_ptr(),
                            o["val"].data_ptr(), o["cnt"].data_ptr(), done.data_ptr(), stream))
     plans = None
     if with_lists:
@@ -397,7 +397,7 @@ def run_ours(args):
                    "parallelism": "documents sharded across ranks (dp%d), no data-path collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                     "kernel": "score_topk_f32_kernel", "algorithmic_bytes_per_launch": step_bytes,
+                     "kernel": "score_topk_tma_kernel" if tables[0].algo == 2 else "score_topk_ldg_kernel", "algorithmic_bytes_per_launch": step_bytes,
                      "ms_per_launch": ms_score},
         "e2e": e2e,
         "gpu_launches": args.steps * launches_per_step,
@@ -464,6 +464,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=["C2", "C3"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 LDG kernel, 2 TMA kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

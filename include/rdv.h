@@ -55,26 +55,48 @@ RDV_API int rdv_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_mi
  * k_b = min(k, n_b), descending score, ties broken by LOWEST index, NaN greatest, -0 == +0.
  *
  * Documents are ragged and live in separate allocations (BiEncoder.batch_forward returns one tensor
- * per document, src/_modules.py:1415-1416), so the kernel takes a table of row-block pointers
- * instead of one packed matrix; a packed CSR matrix is the special case ptr[b] = base + row_off[b]*d.
+ * per document, src/_modules.py:1415-1416).  The caller cuts the batch into row tiles that never cross
+ * a document and passes one 32-byte descriptor per tile (a packed CSR matrix is the special case
+ * src = base + row * d * 4):
+ *   rdv_tile_desc.src       first row of the tile: `rows` consecutive rows of d fp32, 16-byte aligned
+ *   rdv_tile_desc.sims_off  index of that row in d_sims (global chunk number)
+ *   rdv_tile_desc.rows      1 .. tile_rows
+ *   rdv_tile_desc.doc       document (= question) the tile belongs to
+ *   rdv_tile_desc.doc_rows  n_b of that document
+ * Tiles of one document must be contiguous in d_tiles and ordered by sims_off.
  *
- *   d_doc_ptr   [B]    device pointers to (n_b, d) fp32, row-major, row pitch = d floats; 16-byte aligned
- *   d_row_off   [B+1]  exclusive prefix sum of n_b (int64): document b writes sims[row_off[b] ..)
- *   d_tile_off  [B+1]  exclusive prefix sum of ceil(n_b / tile_rows) (int32)
+ *   d_row_off   [B+1]  exclusive prefix sum of n_b (int64)
  *   d_q         (B,d)  fp32 question embeddings, 16-byte aligned
  *   d_sims      [N]    out: every similarity, chunk order (the 9th output of Retriever.retrieve)
  *   d_topk_idx  (B,k)  out: int32 chunk index within the document, rank order, -1 padded
  *   d_topk_val  (B,k)  out: fp32 score of each hit (-inf padded)
  *   d_topk_cnt  [B]    out: k_b
  *   d_doc_done  [B]    int32 workspace, all zero on entry; the kernel leaves it all zero again
- *   tile_rows          rows per thread block: a multiple of 8 in [8, 256] (see rdv_score_tile_rows)
+ *   tile_rows          the maximum rdv_tile_desc.rows used (from rdv_score_plan)
+ *   algo               RDV_SCORE_TMA: persistent kernel, bulk-async-copy (TMA) ring in shared memory,
+ *                      d in {128,256,384,512,768,1024};  RDV_SCORE_LDG: one block per tile, any d % 4 == 0
  *   max_rows           max_b n_b (sizes the shared-memory cache of the selection pass)
  * Requirements: d % 4 == 0, 4 <= d <= 8192, 1 <= k <= 1024, B >= 0.
  * ------------------------------------------------------------------------------------------- */
-RDV_API int rdv_score_topk_f32(const void* const* d_doc_ptr, const int64_t* d_row_off,
-                               const int32_t* d_tile_off, const float* d_q, int32_t B, int32_t d,
-                               int32_t k, int32_t tile_rows, int32_t total_tiles, int32_t max_rows,
-                               float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
+typedef struct rdv_tile_desc {
+    const void* src;
+    int64_t sims_off;
+    int32_t rows;
+    int32_t doc;
+    int32_t doc_rows;
+    int32_t reserved;
+} rdv_tile_desc;
+
+#define RDV_SCORE_AUTO 0
+#define RDV_SCORE_LDG 1
+#define RDV_SCORE_TMA 2
+
+/* Picks the kernel (AUTO -> TMA when d allows it) and the tile height for a batch of total_rows rows. */
+RDV_API int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows);
+
+RDV_API int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
+                               const int64_t* d_row_off, const float* d_q, int32_t B, int32_t d, int32_t k,
+                               int32_t max_rows, float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
                                int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
 
 /* Stand-alone segmented top-k over an existing score vector (same ordering rules as above); used
@@ -84,9 +106,7 @@ RDV_API int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_of
                                   int32_t max_rows, int32_t* d_topk_idx, float* d_topk_val,
                                   int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
 
-/* Launch heuristic for tile_rows given the batch's total row count (keeps >= ~8 tiles per SM for
- * small batches so the hardware scheduler can balance ragged documents). */
-RDV_API int32_t rdv_score_tile_rows(int64_t total_rows, int32_t d);
+
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -10,9 +10,10 @@ from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
+SCORE_AUTO, SCORE_LDG, SCORE_TMA = 0, 1, 2
 
 
 class RdvError(RuntimeError):
@@ -43,10 +44,9 @@ SIGNATURES = {
     "rdv_abi_version": (c_int32, []),
     "rdv_last_error": (c_char_p, []),
     "rdv_device_info": (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
-    "rdv_score_topk_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
-                                     c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p]),
-    "rdv_score_tile_rows": (c_int32, [c_int64, c_int32]),
+    "rdv_score_plan": (c_int32, [c_int64, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32)]),
+    "rdv_score_topk_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_topk_segments_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
     "rdv_mean_pool_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,

@@ -60,10 +60,14 @@ class ScoreTopK(NamedTuple):
     sizes: List[int]
 
 
+TILE_DTYPE = np.dtype([("src", "<u8"), ("sims_off", "<i8"), ("rows", "<i4"), ("doc", "<i4"),
+                       ("doc_rows", "<i4"), ("reserved", "<i4")])      # rdv_tile_desc, 32 bytes
+
+
 class DocTable(NamedTuple):
     """Device-side description of a ragged batch of documents (see rdv_score_topk_f32)."""
-    desc: torch.Tensor     # uint8 blob on device: ptr[B] u64 | row_off[B+1] i64 | tile_off[B+1] i32
-    keepalive: tuple       # tensors whose storage the pointer table references
+    desc: torch.Tensor     # uint8 blob on device: row_off[B+1] i64 | pad | tiles[T] rdv_tile_desc
+    keepalive: tuple       # tensors whose storage the tile descriptors point into
     B: int
     d: int
     sizes: List[int]
@@ -71,14 +75,24 @@ class DocTable(NamedTuple):
     total_tiles: int
     tile_rows: int
     max_rows: int
+    algo: int
+    tiles_offset: int
 
     def pointers(self):
+        """(d_tiles, d_row_off)"""
         base = self.desc.data_ptr()
-        return base, base + 8 * self.B, base + 8 * self.B + 8 * (self.B + 1)
+        return base + self.tiles_offset, base
 
 
-def build_doc_table(docs: Sequence[torch.Tensor], d: int, device, tile_rows: int = 0) -> DocTable:
-    """Uploads the pointer / offset table of a ragged batch in ONE pinned H2D copy."""
+def plan_score(total_rows: int, d: int, algo: int = _lib.SCORE_AUTO):
+    algo_out, tile_rows = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib_fn.rdv_score_plan(total_rows, d, algo, ctypes.byref(algo_out), ctypes.byref(tile_rows)))
+    return algo_out.value, tile_rows.value
+
+
+def build_doc_table(docs: Sequence[torch.Tensor], d: int, device, tile_rows: int = 0,
+                    algo: int = _lib.SCORE_AUTO) -> DocTable:
+    """Cuts a ragged batch into row tiles and uploads offsets + tile descriptors in ONE pinned H2D copy."""
     B = len(docs)
     keep = []
     sizes = np.empty(B, dtype=np.int64)
@@ -93,24 +107,34 @@ def build_doc_table(docs: Sequence[torch.Tensor], d: int, device, tile_rows: int
         sizes[b] = t.shape[0]
         ptrs[b] = t.data_ptr() if t.shape[0] else 0
     total_rows = int(sizes.sum()) if B else 0
+    algo, planned_rows = plan_score(total_rows, d, algo)
     if tile_rows <= 0:
-        tile_rows = int(_lib_fn.rdv_score_tile_rows(total_rows, d))
+        tile_rows = planned_rows
     row_off = np.zeros(B + 1, dtype=np.int64)
     np.cumsum(sizes, out=row_off[1:])
-    tile_off = np.zeros(B + 1, dtype=np.int64)
-    np.cumsum((sizes + tile_rows - 1) // tile_rows, out=tile_off[1:])
-    if tile_off[-1] >= 2 ** 31 - 1:
+    tiles_per_doc = (sizes + tile_rows - 1) // tile_rows
+    T = int(tiles_per_doc.sum()) if B else 0
+    if T >= 2 ** 31 - 1:
         raise ValueError("too many tiles for one launch")
-    nbytes = 8 * B + 8 * (B + 1) + 4 * (B + 1)
-    nbytes = (nbytes + 15) // 16 * 16
-    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    tiles = np.zeros(T, dtype=TILE_DTYPE)
+    if T:
+        doc = np.repeat(np.arange(B, dtype=np.int64), tiles_per_doc)
+        first = np.cumsum(tiles_per_doc) - tiles_per_doc
+        row0 = (np.arange(T, dtype=np.int64) - first[doc]) * tile_rows
+        tiles["src"] = ptrs[doc] + (row0 * (d * 4)).astype(np.uint64)
+        tiles["sims_off"] = row_off[doc] + row0
+        tiles["rows"] = np.minimum(tile_rows, sizes[doc] - row0)
+        tiles["doc"] = doc
+        tiles["doc_rows"] = sizes[doc]
+    tiles_offset = (8 * (B + 1) + 31) // 32 * 32
+    host = torch.empty(tiles_offset + 32 * max(T, 1), dtype=torch.uint8, pin_memory=True)
     raw = host.numpy()
-    raw[:8 * B].view(np.uint64)[:] = ptrs
-    raw[8 * B:8 * B + 8 * (B + 1)].view(np.int64)[:] = row_off
-    raw[16 * B + 8:16 * B + 8 + 4 * (B + 1)].view(np.int32)[:] = tile_off.astype(np.int32)
+    raw[:8 * (B + 1)].view(np.int64)[:] = row_off
+    if T:
+        raw[tiles_offset:tiles_offset + 32 * T] = tiles.view(np.uint8)
     desc = host.to(device, non_blocking=True)
-    return DocTable(desc, tuple(keep), B, d, [int(s) for s in sizes], total_rows, int(tile_off[-1]),
-                    tile_rows, int(sizes.max()) if B else 0)
+    return DocTable(desc, tuple(keep), B, d, [int(s) for s in sizes], total_rows, T, tile_rows,
+                    int(sizes.max()) if B else 0, algo, tiles_offset)
 
 
 def score_topk_table(table: DocTable, questions: torch.Tensor, k: int) -> ScoreTopK:
@@ -124,9 +148,9 @@ def score_topk_table(table: DocTable, questions: torch.Tensor, k: int) -> ScoreT
     topk_cnt = torch.empty((B,), dtype=torch.int32, device=device)
     if B:
         done = _Workspace.zeros_i32(device, B)
-        p_ptr, p_row, p_tile = table.pointers()
+        p_tiles, p_row = table.pointers()
         _lib.check(_lib_fn.rdv_score_topk_f32(
-            p_ptr, p_row, p_tile, q.data_ptr(), B, d, k, table.tile_rows, table.total_tiles,
+            p_tiles, table.total_tiles, table.tile_rows, table.algo, p_row, q.data_ptr(), B, d, k,
             table.max_rows, sims.data_ptr(), topk_idx.data_ptr(), topk_val.data_ptr(),
             topk_cnt.data_ptr(), done.data_ptr(), _stream_ptr(device)))
     views = list(torch.split(sims, table.sizes)) if B else []
@@ -134,7 +158,7 @@ def score_topk_table(table: DocTable, questions: torch.Tensor, k: int) -> ScoreT
 
 
 def score_topk(text_embeddings: Sequence[torch.Tensor], question_embeddings: torch.Tensor, k: int,
-               tile_rows: int = 0) -> ScoreTopK:
+               tile_rows: int = 0, algo: int = _lib.SCORE_AUTO) -> ScoreTopK:
     """Cosine score of question b against every chunk of document b + per-document top-k.
 
     Replaces Retriever._get_similarities + torch.topk (reference src/_modules.py:1978-1997, 2015-2016).
@@ -147,7 +171,7 @@ def score_topk(text_embeddings: Sequence[torch.Tensor], question_embeddings: tor
         raise ValueError("k must be >= 1")
     d = question_embeddings.shape[1]
     with torch.cuda.device(question_embeddings.device):
-        table = build_doc_table(text_embeddings, d, question_embeddings.device, tile_rows)
+        table = build_doc_table(text_embeddings, d, question_embeddings.device, tile_rows, algo)
         return score_topk_table(table, question_embeddings, k)
 
 

@@ -18,10 +18,13 @@ pytestmark = pytest.mark.gpu
 TEXT_CASES = ["c1", "ragged_norm", "ragged_raw", "k20_d1024"]
 
 
-def run_case(emb, q, k, tile_rows=0):
+LDG, TMA = 1, 2
+
+
+def run_case(emb, q, k, tile_rows=0, algo=0):
     from rag_docvqa_b200 import functional as F
     dev = torch.device("cuda:0")
-    res = F.score_topk([e.to(dev) for e in emb], q.to(dev), k, tile_rows=tile_rows)
+    res = F.score_topk([e.to(dev) for e in emb], q.to(dev), k, tile_rows=tile_rows, algo=algo)
     torch.cuda.synchronize()
     return res
 
@@ -44,31 +47,33 @@ def check_against_oracle(res, emb, q, k, ref_sims=None):
         np.testing.assert_array_equal(val[b, :kb], own[idx[b, :kb]])
 
 
+@pytest.mark.parametrize("algo", [LDG, TMA])
 @pytest.mark.parametrize("name", TEXT_CASES)
-def test_golden_cases(golden_dir, name):
+def test_golden_cases(golden_dir, name, algo):
     z = np.load(os.path.join(golden_dir, "score_topk_%s.npz" % name))
     sizes = z["sizes"].tolist()
     k = int(z["k"])
     emb = [torch.from_numpy(z["emb_%d" % b]) for b in range(len(sizes))]
     q = torch.from_numpy(z["q"])
     ref = [z["sims_%d" % b] for b in range(len(sizes))]
-    res = run_case(emb, q, k)
+    res = run_case(emb, q, k, algo=algo)
     check_against_oracle(res, emb, q, k, ref_sims=ref)   # the reference's own frozen outputs
 
 
-@pytest.mark.parametrize("tile_rows", [8, 32, 128])
+@pytest.mark.parametrize("algo,tile_rows", [(LDG, 8), (LDG, 32), (LDG, 128), (TMA, 1), (TMA, 8), (TMA, 16), (TMA, 40)])
 @pytest.mark.parametrize("normalised", [True, False])
-def test_c2_full(tile_rows, normalised):
+def test_c2_full(algo, tile_rows, normalised):
     batch = synth.make_text_batch("C2", normalised=normalised)
-    res = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, tile_rows=tile_rows)
+    res = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, tile_rows=tile_rows, algo=algo)
     check_against_oracle(res, batch["text_embeddings"], batch["question_embeddings"], 5)
 
 
+@pytest.mark.parametrize("algo", [LDG, TMA])
 @pytest.mark.parametrize("k", [1, 5, 10, 20, 64])
-def test_k_sweep_with_duplicates(k):
+def test_k_sweep_with_duplicates(k, algo):
     sizes = [300, 17, 0, 64, 1, 1000]
     emb, q = synth.make_embeddings(sizes, 384, 31 + k, dup_frac=0.2)
-    res = run_case(emb, q, k)
+    res = run_case(emb, q, k, algo=algo)
     check_against_oracle(res, emb, q, k)
 
 
@@ -78,6 +83,14 @@ def test_dims(d):
     emb, q = synth.make_embeddings(sizes, d, 7 + d, normalised=False, dup_frac=0.05)
     res = run_case(emb, q, 5)
     check_against_oracle(res, emb, q, 5)
+    if d in (128, 256, 384, 512, 768, 1024):
+        for algo in (LDG, TMA):
+            res = run_case(emb, q, 5, algo=algo)
+            check_against_oracle(res, emb, q, 5)
+    else:
+        from rag_docvqa_b200 import _lib
+        with pytest.raises(_lib.RdvError):
+            run_case(emb, q, 5, algo=TMA)
 
 
 def test_special_values():
@@ -117,17 +130,20 @@ def test_all_empty_and_zero_question():
 
 def test_workspace_left_clean_and_repeatable():
     batch = synth.make_text_batch("C2", docs=16)
-    a = run_case(batch["text_embeddings"], batch["question_embeddings"], 5)
-    b = run_case(batch["text_embeddings"], batch["question_embeddings"], 5)
-    assert torch.equal(a.topk_idx, b.topk_idx)
+    a = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=TMA)
+    b = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=TMA)
+    c = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=LDG)
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_idx, c.topk_idx)
     assert torch.equal(a.sims, b.sims)          # deterministic: fixed summation order
+    assert torch.equal(a.sims, c.sims)          # both kernels use the same per-lane order and butterfly
 
 
-def test_c3_slice_large_docs():
-    # documents above the selection cache (12288 scores) exercise the L2-resident selection path
+@pytest.mark.parametrize("algo", [LDG, TMA])
+def test_c3_slice_large_docs(algo):
+    # documents above the selection cache (8192 scores) exercise the L2-resident selection path
     sizes = [20000, 13000, 500]
     emb, q = synth.make_embeddings(sizes, 768, 5, dup_frac=0.01)
-    res = run_case(emb, q, 10)
+    res = run_case(emb, q, 10, algo=algo)
     check_against_oracle(res, emb, q, 10)
 
 
