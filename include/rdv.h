@@ -91,7 +91,8 @@ typedef struct rdv_tile_desc {
 #define RDV_SCORE_LDG 1
 #define RDV_SCORE_TMA 2
 
-/* Picks the kernel (AUTO -> TMA when d allows it) and the tile height for a batch of total_rows rows. */
+/* Picks the kernel (AUTO -> the one measured faster on B200, currently LDG) and the tile height for a batch
+ * of total_rows rows. */
 RDV_API int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows);
 
 RDV_API int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
@@ -165,6 +166,7 @@ RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, i
  *   chunk_off[B+1] i64      first global chunk of each document (== d_row_off of the score kernel)
  *   chunk_word_off[N+1]     first global word of each chunk        word_tok_off[W+1]  first token of each word
  *   tok_ids[T]              token ids (the tokenizer's ids without EOS, src/VT5.py:160)
+ *   tok_word[T]             global word index of each token
  *   word_box[W*4] f64       word boxes, 0..1, as the Python floats the reference multiplies by 1000
  *   chunk_label[N], chunk_page[N]
  *   page_chunks[N]          GLOBAL chunk ids grouped by (document, page), chunk order inside a page
@@ -188,6 +190,7 @@ typedef struct rdv_docstore {
     const int32_t* chunk_word_off;
     const int32_t* word_tok_off;
     const int32_t* tok_ids;
+    const int32_t* tok_word;
     const double* word_box;
     const int32_t* chunk_label;
     const int32_t* chunk_page;
@@ -229,6 +232,42 @@ typedef struct rdv_gather_args {
 } rdv_gather_args;
 
 RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args* args, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * bf16 tensor-core scoring (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+ *
+ * rdv_rows_to_bf16      fp32 (rows, d) -> bf16 copy, optionally L2-normalised first (F.normalize,
+ *                       src/utils.py:445-446); d_inv_norm (optional) = 1 / ||bf16 row||.
+ * rdv_bf16_inv_norm     inverse row norms of a bf16 matrix (built once per corpus shard).
+ *
+ * rdv_corpus_score_topk_bf16 -- corpus mode (BASELINE.json configs[4]): n_questions x n_rows cosine
+ *   (formula of src/_modules.py:1990-1993 on every pair) with the per-question top-k folded into the
+ *   accumulator epilogue; the score matrix is never written.  Row chunks (`groups`, from
+ *   rdv_corpus_groups) are scored independently; outputs are per-question CANDIDATE lists
+ *   d_cand_val / d_cand_idx (n_questions, groups * rdv_tc_candidates_per_group()) with global ids
+ *   id_offset + row (empty slots: id -1), ready for rdv_topk_merge (locally, and again after the
+ *   all-gather across shards).  d_part_val / d_part_idx: workspace of
+ *   groups * ceil(n_questions / rdv_tc_tile_m()) * rdv_tc_tile_m() * rdv_tc_candidates_per_group().
+ *   bf16 mode is reported as recall@k against the fp32 result, not as bit parity.
+ *   Requirements: d % 8 == 0, 1 <= k <= rdv_tc_candidates_per_group(), n_rows < 2^31.
+ *
+ * rdv_maxsim_bf16_tc -- fast mode of late_interaction (src/utils.py:442-458): d_qn_bf16 (Lq, d) and
+ *   d_pn_bf16 (n, Lp, d) are the L2-NORMALISED bf16 copies (rdv_rows_to_bf16 with normalise = 1);
+ *   d_partial: workspace of n * ceil(Lq / rdv_tc_tile_m()) floats; d_out (n).
+ * ------------------------------------------------------------------------------------------- */
+RDV_API int rdv_rows_to_bf16(const float* d_x, int64_t rows, int32_t d, int32_t normalise, void* d_out_bf16,
+                             float* d_inv_norm, void* stream);
+RDV_API int rdv_bf16_inv_norm(const void* d_x_bf16, int64_t rows, int32_t d, float* d_inv_norm, void* stream);
+RDV_API int32_t rdv_corpus_groups(int64_t n_rows, int32_t n_questions);
+RDV_API int32_t rdv_tc_tile_m(void);
+RDV_API int32_t rdv_tc_candidates_per_group(void);
+RDV_API int rdv_corpus_score_topk_bf16(const void* d_e_bf16, const float* d_e_inv_norm, int64_t n_rows, int32_t d,
+                                       const void* d_q_bf16, const float* d_q_inv_norm, int32_t n_questions,
+                                       int32_t k, int64_t id_offset, int32_t groups, float* d_part_val,
+                                       int32_t* d_part_idx, float* d_cand_val, int64_t* d_cand_idx, void* stream);
+RDV_API int rdv_maxsim_bf16_tc(const void* d_qn_bf16, const void* d_pn_bf16, int32_t n, int32_t Lq, int32_t Lp,
+                               int32_t d, float* d_partial, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

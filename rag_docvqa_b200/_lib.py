@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 2
+ABI_VERSION = 4
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA = 0, 1, 2
@@ -25,7 +25,7 @@ class RdvError(RuntimeError):
 class DocStoreStruct(Structure):
     """Mirror of `rdv_docstore` (include/rdv.h)."""
     _fields_ = [("B", c_int32), ("reserved", c_int32)] + [(n, c_void_p) for n in (
-        "chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "word_box", "chunk_label", "chunk_page",
+        "chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "tok_word", "word_box", "chunk_label", "chunk_page",
         "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh")]
 
 
@@ -56,6 +56,15 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_maxsim_tiles_i": (c_int32, [c_int32]),
     "rdv_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "rdv_rows_to_bf16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "rdv_bf16_inv_norm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "rdv_corpus_groups": (c_int32, [c_int64, c_int32]),
+    "rdv_tc_tile_m": (c_int32, []),
+    "rdv_tc_candidates_per_group": (c_int32, []),
+    "rdv_corpus_score_topk_bf16": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                             c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_maxsim_bf16_tc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                     c_void_p]),
     "rdv_gather_vt5_inputs": (c_int32, [POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
 }
 

@@ -1,0 +1,73 @@
+"""Swaps the B200 path into an importable reference tree (Pikurrot/RAG-DocVQA) without editing it.
+
+    import rag_docvqa_b200.compat as compat
+    compat.install()          # before or after `import src.RAGVT5` / `import src.RAGPix2Struct`
+
+After install(), src/RAGVT5.py:105 (`self.retriever = Retriever(config)`) and src/RAGPix2Struct.py:83
+(`VisualRetriever(config)`) construct the drop-ins of rag_docvqa_b200.retriever, and src._modules'
+`mean_pooling` / `late_interaction` names point at the CUDA implementations.  The permanent form of the
+same change is the four-line patch in INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import sys
+
+_PATCHED = {}
+_REPLACEMENTS = None
+
+
+def replacements():
+    global _REPLACEMENTS
+    if _REPLACEMENTS is None:
+        _REPLACEMENTS = _make_replacements()
+    return _REPLACEMENTS
+
+
+def _make_replacements():
+    from . import functional, retriever
+    return {
+        "Retriever": retriever.Retriever,
+        "VisualRetriever": retriever.VisualRetriever,
+        "mean_pooling": _mean_pooling_dispatch(functional),
+        "late_interaction": _late_interaction_dispatch(functional),
+    }
+
+
+def _mean_pooling_dispatch(functional):
+    def mean_pooling(embs, attention_mask):
+        """reference signature (src/_model_utils.py:49); CUDA tensors only -- no CPU fallback."""
+        return functional.mean_pooling(embs, attention_mask)
+    return mean_pooling
+
+
+def _late_interaction_dispatch(functional):
+    def late_interaction(query, patches):
+        """reference signature (src/utils.py:442); CUDA tensors only -- no CPU fallback."""
+        return functional.late_interaction(query, patches)
+    return late_interaction
+
+
+def install(modules=None) -> list:
+    """Rebinds the four names in every loaded `src.*` module of the reference that defines or imported
+    them.  Returns the list of (module, name) pairs patched.  Idempotent; undo with uninstall()."""
+    repl = replacements()
+    done = []
+    for mod_name, mod in list(sys.modules.items()):
+        if mod is None or not (mod_name == "src" or mod_name.startswith("src.")):
+            continue
+        if modules is not None and mod_name not in modules:
+            continue
+        for name, new in repl.items():
+            if hasattr(mod, name) and getattr(mod, name) is not new:
+                _PATCHED.setdefault((mod_name, name), getattr(mod, name))
+                setattr(mod, name, new)
+                done.append((mod_name, name))
+    return done
+
+
+def uninstall() -> None:
+    for (mod_name, name), old in list(_PATCHED.items()):
+        mod = sys.modules.get(mod_name)
+        if mod is not None:
+            setattr(mod, name, old)
+        del _PATCHED[(mod_name, name)]

@@ -54,17 +54,30 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
         const int gc = (int)(c0 + a.topk_idx[(size_t)b * k + tid]);
         const int start = ds.chunk_page_start[gc];
         const int nw = ds.chunk_word_off[gc + 1] - ds.chunk_word_off[gc];
-        const int last = ds.page_chunks[ds.run_end[gc] - 1];
-        const int page_len = ds.chunk_page_start[last] + (ds.chunk_word_off[last + 1] - ds.chunk_word_off[last]);
         s_chunk[tid] = gc;
         s_page[tid] = ds.chunk_page[gc];
-        s_lo[tid] = max(0, start - a.include_surroundings);
-        s_hi[tid] = min(page_len, start + nw + a.include_surroundings);
+        if (a.include_surroundings == 0) {
+            s_lo[tid] = start; s_hi[tid] = start + nw;         // no neighbours: the page length is not needed
+        } else {
+            const int last = ds.page_chunks[ds.run_end[gc] - 1];
+            const int page_len = ds.chunk_page_start[last] + (ds.chunk_word_off[last + 1] - ds.chunk_word_off[last]);
+            s_lo[tid] = max(0, start - a.include_surroundings);
+            s_hi[tid] = min(page_len, start + nw + a.include_surroundings);
+        }
     }
     __syncthreads();
 
     // ---- B: fresh sub-intervals (minus better hits on the same page) -> global word segments ------
-    if (tid < cnt) {
+    if (tid < cnt && a.include_surroundings == 0) {
+        // ranges of distinct chunks are disjoint in the page word list: the hit is exactly its own words
+        const int gc = s_chunk[tid];
+        const int wb = ds.chunk_word_off[gc], we = ds.chunk_word_off[gc + 1];
+        int* segs = seg_ws + (size_t)tid * (2 * a.max_seg);
+        segs[0] = wb; segs[1] = we;
+        s_nseg[tid] = we > wb ? 1 : 0;
+        s_nwords[tid] = we - wb;
+        s_ntok[tid] = ds.word_tok_off[we] - ds.word_tok_off[wb];
+    } else if (tid < cnt) {
         Interval fresh[kMaxFresh];
         int nf = 1;
         bool overflow = false;
@@ -246,10 +259,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
                     while (o >= nt) { o -= nt; ++sidx; wb = segs[2 * sidx]; we = segs[2 * sidx + 1];
                                       nt = ds.word_tok_off[we] - ds.word_tok_off[wb]; }
                     const int t = ds.word_tok_off[wb] + o;
-                    int lo = wb, hi = we;                        // last word w in [wb, we) with tok_off[w] <= t
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ds.word_tok_off[mid] <= t) lo = mid; else hi = mid; }
                     id = ds.tok_ids[t];
-                    const double* wbx = ds.word_box + (size_t)lo * 4;
+                    const double* wbx = ds.word_box + (size_t)ds.tok_word[t] * 4;   // token -> its word's box
                     bx0 = (int64_t)(wbx[0] * 1000.0); bx1 = (int64_t)(wbx[1] * 1000.0);   // f64 -> i64 truncation
                     bx2 = (int64_t)(wbx[2] * 1000.0); bx3 = (int64_t)(wbx[3] * 1000.0);
                     lb = ds.chunk_label[s_chunk[i]];
@@ -276,7 +287,7 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
     RDV_REQUIRE(args->max_len >= 2 && args->max_seg >= 1 && args->n_sep >= 0 && args->include_surroundings >= 0,
                 RDV_E_INVALID, "gather_vt5_inputs: bad max_len / max_seg / n_sep / include_surroundings");
     RDV_REQUIRE(ds->chunk_off && ds->chunk_word_off && ds->word_tok_off && ds->tok_ids && ds->word_box &&
-                ds->chunk_label && ds->chunk_page && ds->chunk_page_start && ds->page_chunks && ds->run_begin &&
+                ds->tok_word && ds->chunk_label && ds->chunk_page && ds->chunk_page_start && ds->page_chunks && ds->run_begin &&
                 ds->run_end, RDV_E_INVALID, "gather_vt5_inputs: docstore has a null array");
     RDV_REQUIRE(args->topk_idx && args->topk_cnt && args->prompt_off && args->prompt_ids && args->seg_ws &&
                 args->out_ids && args->out_boxes && args->out_mask && args->full_len && args->status &&

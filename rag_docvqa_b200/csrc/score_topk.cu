@@ -430,7 +430,9 @@ extern "C" int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32
     using namespace rdv;
     RDV_REQUIRE(algo_out && tile_rows, RDV_E_INVALID, "score_plan: null output");
     RDV_REQUIRE(algo >= RDV_SCORE_AUTO && algo <= RDV_SCORE_TMA, RDV_E_INVALID, "score_plan: unknown algo %d", algo);
-    if (algo == RDV_SCORE_AUTO) algo = tma_supported(d) ? RDV_SCORE_TMA : RDV_SCORE_LDG;
+    // measured on B200 (profiles/): the LDG kernel is ahead at every size so far, so AUTO picks it; the TMA
+    // kernel stays selectable (its consumers serialise on one tile at a time -- see DESIGN.md, next steps)
+    if (algo == RDV_SCORE_AUTO) algo = RDV_SCORE_LDG;
     RDV_REQUIRE(algo != RDV_SCORE_TMA || tma_supported(d), RDV_E_INVALID,
                 "score_plan: the TMA kernel supports d in {128,256,384,512,768,1024}, got %d", d);
     *algo_out = algo;

@@ -1,0 +1,509 @@
+// bf16 tensor-core scoring for the two dense contractions of the path (sm_100a: tcgen05 + TMEM + TMA).
+//
+//   * corpus mode (BASELINE.json configs[4]): Q questions x N chunk embeddings, cosine + per-question
+//     top-k with the top-k folded into the accumulator epilogue -- the (Q x N) score matrix is never
+//     written.  Scoring formula: Retriever._get_similarities (reference src/_modules.py:1990-1993) applied
+//     to every (question, chunk) pair; the reference itself only ever scores one question per document.
+//   * MaxSim mode (fast mode of late_interaction, reference src/utils.py:442-458): operands are the
+//     L2-normalised bf16 copies of Q and P; epilogue = running row maximum over a strip's tokens.
+//
+// One GEMM main loop serves both:  D[128 x 256] (fp32, TMEM) += A[128 x K] * B[256 x K]^T, both K-major.
+//   A rows = questions / question tokens  -> TMEM lanes  -> one epilogue THREAD per row, so the per-row
+//     reduction over B rows (top-k / max) is register-resident and needs no cross-thread traffic;
+//   B rows = corpus chunks / strip tokens -> TMEM columns.
+// Warp roles (192 threads): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier
+// ring of 48 KB stages), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16,
+// kind::f16 bf16 x bf16 -> fp32), warps 2-5 = epilogue (tcgen05.ld 32x32b.x32, one TMEM lane quarter
+// each).  The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Persistent: one block per SM loops over work items.
+#include "rdv_common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace rdv {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 192;
+constexpr int kTopK = 16;                 // register-resident candidates per question and work item
+constexpr uint32_t kTmemCols = 512;       // 2 accumulators x 256 fp32 columns
+
+enum Mode { kCorpus = 0, kMaxSim = 1 };
+
+struct Params {
+    int mode;
+    int n_a;                // A tiles (question blocks / question-token blocks)
+    int n_groups;           // corpus: row chunks; maxsim: strips
+    int tiles_total;        // corpus: total B tiles;  maxsim: B tiles per strip
+    int k_blocks;           // ceil(K / 64)
+    int a_rows, b_rows;     // valid A rows (Q / Lq) and B rows (N_local / Lp)
+    // corpus epilogue
+    const float* inv_norm;  // (N_local) 1 / max(||e||, tiny)
+    float* part_val;        // (n_groups, n_a*128, kTopK)
+    int32_t* part_idx;
+    // maxsim epilogue
+    float* partial;         // (n_groups = strips, n_a)
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(s32(dst)), "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {   // arrives on `bar` when all prior MMAs of this thread retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile (rows at a 128 B pitch, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);      // start address >> 4            bits [0,14)
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset = 1024 B   bits [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct Item { int a_tile, group, t0, t1, z; };
+__device__ __forceinline__ Item decode_item(const Params& p, int item) {
+    Item it;
+    it.group = item / p.n_a;
+    it.a_tile = item - it.group * p.n_a;
+    if (p.mode == kCorpus) {
+        it.t0 = (int)((long long)it.group * p.tiles_total / p.n_groups);
+        it.t1 = (int)((long long)(it.group + 1) * p.tiles_total / p.n_groups);
+        it.z = 0;
+    } else {
+        it.t0 = 0; it.t1 = p.tiles_total; it.z = it.group;
+    }
+    return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_unaligned[];
+    // 128-byte swizzle atoms repeat every 1024 bytes: the operand ring must start on a 1024-byte boundary
+    unsigned char* smem = smem_unaligned + ((1024u - (s32(smem_unaligned) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ __align__(16) float s_inv[2][BN];
+    __shared__ float s_sum[4];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.n_a * p.n_groups;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s_tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                for (int t = it.t0; t < it.t1; ++t) {
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(&s_empty[stage], phase ^ 1);
+                        unsigned char* sa = smem + (size_t)stage * kStageBytes;
+                        mbar_expect_tx(&s_full[stage], kStageBytes);
+                        tma_load_3d(sa, &map_a, &s_full[stage], kb * BK, it.a_tile * BM, 0);
+                        tma_load_3d(sa + kABytes, &map_b, &s_full[stage], kb * BK, t * BN, it.z);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                for (int t = it.t0; t < it.t1; ++t) {
+                    mbar_wait(&s_tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(&s_full[stage], phase);               // TMA bytes have landed
+                        tc_fence_after();
+                        const uint32_t a_addr = s32(smem + (size_t)stage * kStageBytes);
+                        const uint64_t da = smem_desc(a_addr), db = smem_desc(a_addr + kABytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)                 // 32 bytes (>>4 = 2) per K=16 step
+                            tc_mma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                        tc_commit(&s_empty[stage]);                       // frees the smem stage when the MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&s_tfull[acc]);                             // accumulator complete
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: 4 warps, thread = one A row =====================
+        const int quarter = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int row_in_tile = quarter * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;                          // 0..127 among epilogue threads
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Item it = decode_item(p, item);
+            float vals[kTopK]; int idxs[kTopK];
+#pragma unroll
+            for (int j = 0; j < kTopK; ++j) { vals[j] = -INFINITY; idxs[j] = -1; }
+            float runmax = -INFINITY;
+            for (int t = it.t0; t < it.t1; ++t) {
+                if (p.mode == kCorpus) {                                // stage this tile's inverse norms
+                    for (int c = et; c < BN; c += 128) {
+                        const int row = t * BN + c;
+                        s_inv[acc][c] = row < p.b_rows ? p.inv_norm[row] : 0.f;
+                    }
+                }
+                mbar_wait(&s_tfull[acc], acc_phase);
+                tc_fence_after();
+                asm volatile("bar.sync 2, 128;" ::: "memory");          // s_inv visible to all epilogue threads
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tc_ld32(taddr + c0, r);
+                    if (p.mode == kCorpus) {
+                        const int nbase = t * BN + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(r[j]) * s_inv[acc][c0 + j];
+                            if (s > vals[kTopK - 1] && nbase + j < p.b_rows) {
+                                float v = s; int id = nbase + j;        // sorted insert (rare after warm-up)
+#pragma unroll
+                                for (int q = 0; q < kTopK; ++q) {
+                                    if (v > vals[q]) {
+                                        const float tv = vals[q]; vals[q] = v; v = tv;
+                                        const int ti = idxs[q]; idxs[q] = id; id = ti;
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        const int jbase = t * BN + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (jbase + j < p.b_rows) runmax = fmaxf(runmax, __uint_as_float(r[j]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_tempty[acc]);             // accumulator may be overwritten
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            const int a_row = it.a_tile * BM + row_in_tile;
+            if (p.mode == kCorpus) {
+                const size_t o = ((size_t)it.group * ((size_t)p.n_a * BM) + (size_t)a_row) * kTopK;
+#pragma unroll
+                for (int j = 0; j < kTopK; ++j) { p.part_val[o + j] = vals[j]; p.part_idx[o + j] = idxs[j]; }
+            } else {
+                float v = a_row < p.a_rows ? runmax : 0.f;
+                v = warp_sum(v);
+                if (lane == 0) s_sum[warp - 2] = v;
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (et == 0) p.partial[(size_t)it.group * p.n_a + it.a_tile] = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ---- small helper kernels ------------------------------------------------------------------------
+// out_bf16[r,:] = x[r,:] (optionally / max(||x[r]||, 1e-12));  inv_norm[r] = 1 / max(||bf16(x[r])||, 1e-30)
+__global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restrict__ x, int64_t rows, int d, int normalise,
+                                                           __nv_bfloat16* __restrict__ out, float* __restrict__ inv_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* src = reinterpret_cast<const float4*>(x) + row * (d >> 2);
+    float scale = 1.f;
+    if (normalise) {
+        float ss = 0.f;
+        for (int i = lane; i < (d >> 2); i += 32) {
+            const float4 v = src[i];
+            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        }
+        scale = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(warp_sum(ss)), 1e-12f));
+    }
+    float ssb = 0.f;
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out) + row * (d >> 1);
+    for (int i = lane; i < (d >> 2); i += 32) {
+        const float4 v = src[i];
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * scale, v.y * scale);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z * scale, v.w * scale);
+        dst[2 * i] = lo; dst[2 * i + 1] = hi;
+        const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+        ssb = fmaf(a.x, a.x, ssb); ssb = fmaf(a.y, a.y, ssb); ssb = fmaf(b.x, b.x, ssb); ssb = fmaf(b.y, b.y, ssb);
+    }
+    if (inv_norm) {
+        ssb = warp_sum(ssb);
+        if (lane == 0) inv_norm[row] = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(ssb), 1e-30f));
+    }
+}
+
+// inv_norm[r] = 1 / max(||E[r]||, 1e-30) for a bf16 matrix
+__global__ void __launch_bounds__(256) bf16_inv_norm_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int d,
+                                                            float* __restrict__ inv_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint4* src = reinterpret_cast<const uint4*>(x) + row * (d >> 3);
+    float ss = 0.f;
+    for (int i = lane; i < (d >> 3); i += 32) {
+        const uint4 v = ldg_stream_u4(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+            ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss);
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) inv_norm[row] = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(ss), 1e-30f));
+}
+
+// out[s] = sum_t partial[s, t]  (fixed order)
+__global__ void strip_sum_kernel(const float* __restrict__ partial, int n, int tiles, float* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float acc = 0.f;
+    for (int t = 0; t < tiles; ++t) acc += partial[(size_t)s * tiles + t];
+    out[s] = acc;
+}
+
+// (groups, rows, 16) partial candidates -> (rows, groups*16) candidate lists with global int64 ids, scaled by 1/||q||
+__global__ void corpus_candidates_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx,
+                                         const float* __restrict__ inv_q, int groups, int rows_padded, int Q,
+                                         int64_t id_offset, float* __restrict__ cand_val, int64_t* __restrict__ cand_idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)Q * groups * kTopK;
+    if (i >= total) return;
+    const int j = (int)(i % kTopK);
+    const int g = (int)((i / kTopK) % groups);
+    const int q = (int)(i / ((int64_t)kTopK * groups));
+    const size_t src = ((size_t)g * rows_padded + q) * kTopK + j;
+    const int32_t id = part_idx[src];
+    cand_val[i] = id >= 0 ? part_val[src] * inv_q[q] : -INFINITY;
+    cand_idx[i] = id >= 0 ? id_offset + id : -1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// bf16 tensor (z, rows, K) row-major -> 3-D map with a (64 x box_rows x 1) box, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t z, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    RDV_REQUIRE(fn, RDV_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)z};
+    cuuint64_t gstride[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RDV_REQUIRE(r == CUDA_SUCCESS, RDV_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return RDV_OK;
+}
+
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)kStages * kStageBytes + 1024;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_score_kernel)");
+        attr_set = true;
+    }
+    int grid = sm_count();
+    const int items = p.n_a * p.n_groups;
+    if (grid > items) grid = items;
+    tc_score_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, p);
+    RDV_LAUNCH_CHECK("tc_score_kernel");
+    return RDV_OK;
+}
+
+}  // namespace tc
+}  // namespace rdv
+
+using namespace rdv;
+
+extern "C" int rdv_rows_to_bf16(const float* d_x, int64_t rows, int32_t d, int32_t normalise, void* d_out_bf16,
+                                float* d_inv_norm, void* stream) {
+    RDV_REQUIRE(rows >= 0, RDV_E_INVALID, "rows_to_bf16: negative size");
+    if (rows == 0) return RDV_OK;
+    RDV_REQUIRE(d_x && d_out_bf16, RDV_E_INVALID, "rows_to_bf16: null pointer");
+    RDV_REQUIRE(d >= 8 && (d & 7) == 0, RDV_E_INVALID, "rows_to_bf16: d=%d must be a multiple of 8", d);
+    RDV_REQUIRE(aligned16(d_x) && aligned16(d_out_bf16), RDV_E_ALIGN, "rows_to_bf16: buffers not 16-byte aligned");
+    const int64_t blocks = (rows + 7) / 8;
+    RDV_REQUIRE(blocks < (1ll << 31), RDV_E_LIMIT, "rows_to_bf16: too many rows");
+    tc::rows_to_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_x, rows, d, normalise, static_cast<__nv_bfloat16*>(d_out_bf16), d_inv_norm);
+    RDV_LAUNCH_CHECK("rows_to_bf16_kernel");
+    return RDV_OK;
+}
+
+extern "C" int rdv_bf16_inv_norm(const void* d_x_bf16, int64_t rows, int32_t d, float* d_inv_norm, void* stream) {
+    RDV_REQUIRE(rows >= 0, RDV_E_INVALID, "bf16_inv_norm: negative size");
+    if (rows == 0) return RDV_OK;
+    RDV_REQUIRE(d_x_bf16 && d_inv_norm, RDV_E_INVALID, "bf16_inv_norm: null pointer");
+    RDV_REQUIRE(d >= 8 && (d & 7) == 0, RDV_E_INVALID, "bf16_inv_norm: d=%d must be a multiple of 8", d);
+    RDV_REQUIRE(aligned16(d_x_bf16), RDV_E_ALIGN, "bf16_inv_norm: x not 16-byte aligned");
+    const int64_t blocks = (rows + 7) / 8;
+    RDV_REQUIRE(blocks < (1ll << 31), RDV_E_LIMIT, "bf16_inv_norm: too many rows");
+    tc::bf16_inv_norm_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(d_x_bf16), rows, d, d_inv_norm);
+    RDV_LAUNCH_CHECK("bf16_inv_norm_kernel");
+    return RDV_OK;
+}
+
+extern "C" int32_t rdv_corpus_groups(int64_t n_rows, int32_t n_questions) {
+    // work items = question blocks x row chunks; aim at ~2 items per SM, at least one B tile per chunk
+    const int n_a = (n_questions + tc::BM - 1) / tc::BM;
+    const int64_t tiles = (n_rows + tc::BN - 1) / tc::BN;
+    int64_t g = (2 * (int64_t)sm_count() + n_a - 1) / (n_a > 0 ? n_a : 1);
+    if (g > tiles) g = tiles;
+    if (g < 1) g = 1;
+    return (int32_t)g;
+}
+
+extern "C" int rdv_corpus_score_topk_bf16(const void* d_e_bf16, const float* d_e_inv_norm, int64_t n_rows, int32_t d,
+                                          const void* d_q_bf16, const float* d_q_inv_norm, int32_t n_questions,
+                                          int32_t k, int64_t id_offset, int32_t groups, float* d_part_val,
+                                          int32_t* d_part_idx, float* d_cand_val, int64_t* d_cand_idx, void* stream) {
+    RDV_REQUIRE(n_rows >= 0 && n_questions >= 0, RDV_E_INVALID, "corpus_score_topk_bf16: negative size");
+    RDV_REQUIRE(d_e_bf16 && d_e_inv_norm && d_q_bf16 && d_q_inv_norm && d_part_val && d_part_idx && d_cand_val &&
+                d_cand_idx, RDV_E_INVALID, "corpus_score_topk_bf16: null pointer");
+    RDV_REQUIRE(d >= 8 && (d & 7) == 0, RDV_E_INVALID, "corpus_score_topk_bf16: d=%d must be a multiple of 8", d);
+    RDV_REQUIRE(k >= 1 && k <= tc::kTopK, RDV_E_LIMIT, "corpus_score_topk_bf16: k=%d outside [1, %d]", k, tc::kTopK);
+    RDV_REQUIRE(n_rows < (1ll << 31) - tc::BN, RDV_E_LIMIT, "corpus_score_topk_bf16: shard rows must fit int32");
+    RDV_REQUIRE(n_rows >= 1 && n_questions >= 1 && groups >= 1, RDV_E_INVALID, "corpus_score_topk_bf16: empty shard / batch");
+    RDV_REQUIRE(aligned16(d_e_bf16) && aligned16(d_q_bf16), RDV_E_ALIGN, "corpus_score_topk_bf16: operands not 16-byte aligned");
+    tc::Params p = {};
+    p.mode = tc::kCorpus;
+    p.n_a = (n_questions + tc::BM - 1) / tc::BM;
+    p.tiles_total = (int)((n_rows + tc::BN - 1) / tc::BN);
+    p.n_groups = groups < p.tiles_total ? groups : p.tiles_total;
+    RDV_REQUIRE(p.n_groups == groups, RDV_E_INVALID, "corpus_score_topk_bf16: groups=%d exceeds the %d row tiles", groups, p.tiles_total);
+    p.k_blocks = (d + tc::BK - 1) / tc::BK;
+    p.a_rows = n_questions; p.b_rows = (int)n_rows;
+    p.inv_norm = d_e_inv_norm; p.part_val = d_part_val; p.part_idx = d_part_idx;
+    CUtensorMap ma, mb;
+    int rc = tc::make_map(&ma, d_q_bf16, d, n_questions, 1, tc::BM);
+    if (rc) return rc;
+    rc = tc::make_map(&mb, d_e_bf16, d, n_rows, 1, tc::BN);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = tc::launch(ma, mb, p, s);
+    if (rc) return rc;
+    const int64_t total = (int64_t)n_questions * groups * tc::kTopK;
+    tc::corpus_candidates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        d_part_val, d_part_idx, d_q_inv_norm, groups, p.n_a * tc::BM, n_questions, id_offset, d_cand_val, d_cand_idx);
+    RDV_LAUNCH_CHECK("corpus_candidates_kernel");
+    return RDV_OK;
+}
+
+extern "C" int rdv_maxsim_bf16_tc(const void* d_qn_bf16, const void* d_pn_bf16, int32_t n, int32_t Lq, int32_t Lp,
+                                  int32_t d, float* d_partial, float* d_out, void* stream) {
+    RDV_REQUIRE(n >= 0 && Lq >= 0, RDV_E_INVALID, "maxsim_bf16_tc: negative size");
+    if (n == 0) return RDV_OK;
+    RDV_REQUIRE(Lp >= 1 && Lq >= 1, RDV_E_INVALID, "maxsim_bf16_tc: empty operand");
+    RDV_REQUIRE(d_qn_bf16 && d_pn_bf16 && d_partial && d_out, RDV_E_INVALID, "maxsim_bf16_tc: null pointer");
+    RDV_REQUIRE(d >= 8 && (d & 7) == 0, RDV_E_INVALID, "maxsim_bf16_tc: d=%d must be a multiple of 8", d);
+    RDV_REQUIRE(aligned16(d_qn_bf16) && aligned16(d_pn_bf16), RDV_E_ALIGN, "maxsim_bf16_tc: operands not 16-byte aligned");
+    tc::Params p = {};
+    p.mode = tc::kMaxSim;
+    p.n_a = (Lq + tc::BM - 1) / tc::BM;
+    p.n_groups = n;
+    p.tiles_total = (Lp + tc::BN - 1) / tc::BN;
+    p.k_blocks = (d + tc::BK - 1) / tc::BK;
+    p.a_rows = Lq; p.b_rows = Lp;
+    p.partial = d_partial;
+    CUtensorMap ma, mb;
+    int rc = tc::make_map(&ma, d_qn_bf16, d, Lq, 1, tc::BM);
+    if (rc) return rc;
+    rc = tc::make_map(&mb, d_pn_bf16, d, Lp, n, tc::BN);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = tc::launch(ma, mb, p, s);
+    if (rc) return rc;
+    tc::strip_sum_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_partial, n, p.n_a, d_out);
+    RDV_LAUNCH_CHECK("strip_sum_kernel");
+    return RDV_OK;
+}
+
+extern "C" int32_t rdv_tc_tile_m(void) { return tc::BM; }
+extern "C" int32_t rdv_tc_candidates_per_group(void) { return tc::kTopK; }

@@ -37,7 +37,7 @@ class PackedInputs(NamedTuple):
 class DocStore:
     """CSR view of a batch of documents on the device (see `rdv_docstore` in include/rdv.h)."""
 
-    FIELDS = ("chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "word_box", "chunk_label", "chunk_page",
+    FIELDS = ("chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "tok_word", "word_box", "chunk_label", "chunk_page",
               "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh")
 
     def __init__(self, arrays: dict, B: int, device):
@@ -126,7 +126,9 @@ class DocStore:
             run_end[order] = run_ends[run_id]
         arrays = dict(
             chunk_off=chunk_off, chunk_word_off=chunk_word_off.astype(_I32), word_tok_off=word_tok_off.astype(_I32),
-            tok_ids=np.asarray(tok_ids, dtype=_I32), word_box=np.ascontiguousarray(word_box),
+            tok_ids=np.asarray(tok_ids, dtype=_I32),
+            tok_word=np.repeat(np.arange(W, dtype=_I32), np.asarray(word_ntok, dtype=np.int64)) if W else np.zeros(0, dtype=_I32),
+            word_box=np.ascontiguousarray(word_box),
             chunk_label=chunk_label, chunk_page=chunk_page, chunk_page_start=chunk_page_start,
             page_chunks=order.astype(_I32), run_begin=run_begin, run_end=run_end)
         if images is not None:

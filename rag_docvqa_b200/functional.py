@@ -286,3 +286,54 @@ def topk_segments(scores: Sequence[torch.Tensor], k: int):
         _lib.check(_lib_fn.rdv_topk_segments_f32(flat.data_ptr(), off_d.data_ptr(), B, k, max(sizes), idx.data_ptr(),
                                                  val.data_ptr(), cnt.data_ptr(), done.data_ptr(), _stream_ptr(device)))
     return idx, val, cnt
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core modes (tcgen05 / TMEM / TMA)
+# ------------------------------------------------------------------------------------------------
+def rows_to_bf16(x: torch.Tensor, normalise: bool = False, return_inv_norm: bool = False):
+    """fp32 (..., d) rows -> bf16 copy (optionally L2-normalised first, F.normalize semantics)."""
+    _require_cuda(x, "x")
+    d = x.shape[-1]
+    xf = _f32_contig_aligned(x)
+    rows = xf.numel() // d
+    out = torch.empty(xf.shape, dtype=torch.bfloat16, device=x.device)
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device) if return_inv_norm else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib_fn.rdv_rows_to_bf16(xf.data_ptr(), rows, d, 1 if normalise else 0, out.data_ptr(),
+                                            inv.data_ptr() if inv is not None else None, _stream_ptr(x.device)))
+    return (out, inv) if return_inv_norm else out
+
+
+def bf16_inv_norm(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "x")
+    if x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise ValueError("bf16_inv_norm: expected a contiguous bf16 matrix")
+    rows, d = x.shape
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib_fn.rdv_bf16_inv_norm(x.data_ptr(), rows, d, inv.data_ptr(), _stream_ptr(x.device)))
+    return inv
+
+
+def late_interaction_bf16(query: torch.Tensor, patches: torch.Tensor) -> torch.Tensor:
+    """MaxSim fast mode: same contract as late_interaction, bf16 operands on the tcgen05 tensor cores
+    (fp32 accumulation in TMEM).  Reported against the fp32 mode as a score error / top-k recall."""
+    _require_cuda(query, "query")
+    _require_cuda(patches, "patches")
+    if query.dim() == 2:
+        query = query.unsqueeze(0)
+    n, Lp, d = patches.shape
+    Lq = query.shape[1]
+    device = patches.device
+    out = torch.empty((n,), dtype=torch.float32, device=device)
+    if n == 0:
+        return out
+    qn = rows_to_bf16(query[0], normalise=True)
+    pn = rows_to_bf16(patches, normalise=True)
+    tiles = (Lq + int(_lib_fn.rdv_tc_tile_m()) - 1) // int(_lib_fn.rdv_tc_tile_m())
+    partial = torch.empty((n * tiles,), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib_fn.rdv_maxsim_bf16_tc(qn.data_ptr(), pn.data_ptr(), n, Lq, Lp, d, partial.data_ptr(),
+                                              out.data_ptr(), _stream_ptr(device)))
+    return out

@@ -1,0 +1,94 @@
+"""GPU checks of the bf16 tensor-core modes (tcgen05 / TMEM / TMA): corpus score + fused top-k, MaxSim.
+
+bf16 mode is not a bit-parity mode (north_star): it is held to (a) the exact result of the SAME bf16
+operands computed in float64 on the CPU, within fp32-accumulation error, and (b) recall@k against the
+fp32 oracle on the un-rounded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import compare
+from oracle import ref_restated as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).to(torch.float64)
+
+
+def exact_scores_of_bf16_operands(E, Q):
+    Eb, Qb = bf16_round(E), bf16_round(Q)
+    dots = Qb @ Eb.T
+    return (dots / (Qb.norm(dim=-1)[:, None] * Eb.norm(dim=-1)[None, :])).numpy()
+
+
+@pytest.mark.parametrize("n,d,Qn,k", [(256, 64, 128, 5), (1000, 128, 37, 10), (5000, 768, 300, 10), (70000, 384, 130, 16),
+                                      (300, 72, 5, 3)])
+def test_corpus_topk_matches_exact_bf16_math(n, d, Qn, k):
+    from rag_docvqa_b200.sharded import CorpusShard
+    g = torch.Generator().manual_seed(n + d)
+    u = torch.randn(d, generator=g)
+    E = torch.randn(n, d, generator=g) + 0.5 * u
+    Q = torch.randn(Qn, d, generator=g) + 0.5 * u
+    E[7] = E[3]                                       # exact duplicate rows: lowest id first
+    shard = CorpusShard.from_f32(E.to(DEV), id_offset=1000)
+    val, idx = shard.search_local(Q.to(DEV), k)
+    torch.cuda.synchronize()
+    val, idx = val.cpu().numpy(), idx.cpu().numpy()
+    exact = exact_scores_of_bf16_operands(E, Q)
+    assert idx.shape == (Qn, k)
+    for q in range(Qn):
+        ids = idx[q] - 1000
+        assert (ids >= 0).all() and (ids < n).all() and len(set(ids.tolist())) == k
+        np.testing.assert_allclose(val[q], exact[q][ids], rtol=2e-5, atol=2e-6)
+        # the selection is the exact top-k of those scores up to fp32 accumulation noise at the boundary
+        kth = np.sort(exact[q])[::-1][k - 1]
+        assert (exact[q][ids] >= kth - 1e-5).all()
+        assert set(np.nonzero(exact[q] > kth + 1e-5)[0].tolist()) <= set(ids.tolist())
+        assert (np.diff(val[q]) <= 0).all()
+        if 3 in ids and 7 in ids:
+            assert list(ids).index(3) < list(ids).index(7)
+    # recall@k against the fp32 oracle on the un-rounded inputs
+    ref = R.corpus_scores(E, Q).numpy()
+    ref_idx = np.stack([R.topk_lowest_index(ref[q], k) for q in range(Qn)])
+    assert compare.recall_at_k(idx - 1000, ref_idx) >= 0.9
+
+
+def test_corpus_sharded_equals_unsharded():
+    from rag_docvqa_b200 import sharded
+    g = torch.Generator().manual_seed(5)
+    n, d, Qn, k, world = 9000, 256, 200, 10, 4
+    E = torch.randn(n, d, generator=g)
+    Q = torch.randn(Qn, d, generator=g)
+    E[8000] = E[10]                                   # a cross-shard exact tie
+    full = sharded.CorpusShard.from_f32(E.to(DEV))
+    v_full, i_full = full.search_local(Q.to(DEV), k)
+    vals, idxs = [], []
+    for r in range(world):                            # ranks emulated as slices on one GPU (B200 guide)
+        lo, hi = sharded.shard_bounds(n, world, r)
+        sh = sharded.CorpusShard.from_f32(E[lo:hi].to(DEV), id_offset=lo)
+        v, i = sh.search_local(Q.to(DEV), k)
+        vals.append(v); idxs.append(i)
+    v_m, i_m = sharded.merge_candidates(torch.cat(vals, 1), torch.cat(idxs, 1), k)
+    assert torch.equal(i_m, i_full)
+    assert torch.equal(v_m, v_full)
+
+
+@pytest.mark.parametrize("n,Lq,Lp,d", [(3, 128, 256, 64), (5, 200, 300, 128), (4, 2048, 2048, 768), (2, 77, 513, 96)])
+def test_maxsim_bf16_tc(n, Lq, Lp, d):
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(n + Lq)
+    q = torch.randn(1, Lq, d, generator=g)
+    p = torch.randn(n, Lp, d, generator=g)
+    got = F.late_interaction_bf16(q.to(DEV), p.to(DEV)).cpu().numpy()
+    # exact math on the same normalised-then-rounded operands
+    qn = bf16_round(torch.nn.functional.normalize(q, dim=-1))
+    pn = bf16_round(torch.nn.functional.normalize(p, dim=-1))
+    exact = torch.bmm(qn.expand(n, -1, -1), pn.transpose(1, 2)).max(dim=-1).values.sum(dim=-1).numpy()
+    np.testing.assert_allclose(got, exact, rtol=2e-5)
+    ref = R.late_interaction_f64(q, p).numpy()          # fp32-mode truth: bf16 rounding error only
+    np.testing.assert_allclose(got, ref, rtol=5e-3)
+    fp32 = F.late_interaction(q.to(DEV), p.to(DEV)).cpu().numpy()
+    assert (np.argsort(-got)[:1] == np.argsort(-fp32)[:1]).all() or n < 2
