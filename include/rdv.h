@@ -250,7 +250,7 @@ RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args*
  *   all-gather across shards).  d_part_val / d_part_idx: workspace of
  *   groups * ceil(n_questions / rdv_tc_tile_m()) * rdv_tc_tile_m() * rdv_tc_candidates_per_group().
  *   bf16 mode is reported as recall@k against the fp32 result, not as bit parity.
- *   Requirements: d % 8 == 0, 1 <= k <= rdv_tc_candidates_per_group(), n_rows < 2^31.
+ *   Requirements: d % 8 == 0, 1 <= k <= 16, n_rows < 2^31.
  *
  * rdv_maxsim_bf16_tc -- fast mode of late_interaction (src/utils.py:442-458): d_qn_bf16 (Lq, d) and
  *   d_pn_bf16 (n, Lp, d) are the L2-NORMALISED bf16 copies (rdv_rows_to_bf16 with normalise = 1);

@@ -11,10 +11,10 @@
 //   A rows = questions / question tokens  -> TMEM lanes  -> one epilogue THREAD per row, so the per-row
 //     reduction over B rows (top-k / max) is register-resident and needs no cross-thread traffic;
 //   B rows = corpus chunks / strip tokens -> TMEM columns.
-// Warp roles (192 threads): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier
+// Warp roles (320 threads): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier
 // ring of 48 KB stages), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16,
-// kind::f16 bf16 x bf16 -> fp32), warps 2-5 = epilogue (tcgen05.ld 32x32b.x32, one TMEM lane quarter
-// each).  The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+// kind::f16 bf16 x bf16 -> fp32), warps 2-9 = epilogue (tcgen05.ld 32x32b.x32; two warps per TMEM lane
+// quarter, one column half each).  The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.  Persistent: one block per SM loops over work items.
 #include "rdv_common.cuh"
 
@@ -27,7 +27,7 @@ namespace tc {
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTopK = 16;                 // register-resident candidates per question and work item
 constexpr uint32_t kTmemCols = 512;       // 2 accumulators x 256 fp32 columns
 
@@ -129,13 +129,15 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __shared__ uint32_t s_tmem_base;
     __shared__ __align__(16) float s_inv[2][BN];
     __shared__ float s_sum[4];
+    // per-epilogue-thread scratch row of 16 scores, slot-major so a warp's accesses are conflict-free
+    float* q_val = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = p.n_a * p.n_groups;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -193,10 +195,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else {
-        // ===================== epilogue: 4 warps, thread = one A row =====================
+        // ===================== epilogue: 8 warps =====================
+        // Two warps per TMEM lane quarter; each takes one half (128) of the accumulator's columns, so a
+        // thread = (one A row, one column half).  Two warps per scheduler hide each other's latencies.
         const int quarter = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                               // column half: warps 2-5 -> 0, 6-9 -> 1
         const int row_in_tile = quarter * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;                          // 0..127 among epilogue threads
+        const int et = (warp - 2) * 32 + lane;                          // 0..255 among epilogue threads
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const Item it = decode_item(p, item);
@@ -205,38 +210,65 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int j = 0; j < kTopK; ++j) { vals[j] = -INFINITY; idxs[j] = -1; }
             float runmax = -INFINITY;
             for (int t = it.t0; t < it.t1; ++t) {
-                if (p.mode == kCorpus) {                                // stage this tile's inverse norms
-                    for (int c = et; c < BN; c += 128) {
-                        const int row = t * BN + c;
-                        s_inv[acc][c] = row < p.b_rows ? p.inv_norm[row] : 0.f;
-                    }
+                if (p.mode == kCorpus) {
+                    // stage this tile's inverse norms; rows past the shard get NaN so they never compare greater
+                    const int row = t * BN + et;
+                    s_inv[acc][et] = row < p.b_rows ? p.inv_norm[row] : __int_as_float(0x7fc00000);
                 }
                 mbar_wait(&s_tfull[acc], acc_phase);
                 tc_fence_after();
-                asm volatile("bar.sync 2, 128;" ::: "memory");          // s_inv visible to all epilogue threads
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BN;
+                asm volatile("bar.sync 2, 256;" ::: "memory");          // s_inv visible to all epilogue threads
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = 0; c0 < BN / 2; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32(taddr + c0, r);
                     if (p.mode == kCorpus) {
-                        const int nbase = t * BN + c0;
+                        // Common case (nothing beats the thread's 16th best): ~3 independent instructions per
+                        // score.  Otherwise the 16 scaled scores go to a per-thread shared-memory row and the
+                        // few that passed are folded in by ONE rolled insertion loop (the fully unrolled variant
+                        // was instruction-fetch bound).
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(r[j]) * s_inv[acc][c0 + j];
-                            if (s > vals[kTopK - 1] && nbase + j < p.b_rows) {
-                                float v = s; int id = nbase + j;        // sorted insert (rare after warm-up)
+                        for (int h = 0; h < 2; ++h) {
+                            const int cbase = half * (BN / 2) + c0 + 16 * h;
+                            const float thr = vals[kTopK - 1];
+                            float sc[16];
+                            unsigned mask = 0;
 #pragma unroll
-                                for (int q = 0; q < kTopK; ++q) {
-                                    if (v > vals[q]) {
-                                        const float tv = vals[q]; vals[q] = v; v = tv;
-                                        const int ti = idxs[q]; idxs[q] = id; id = ti;
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 iv = *reinterpret_cast<const float4*>(&s_inv[acc][cbase + 4 * j4]);
+                                sc[4 * j4 + 0] = __uint_as_float(r[16 * h + 4 * j4 + 0]) * iv.x;
+                                sc[4 * j4 + 1] = __uint_as_float(r[16 * h + 4 * j4 + 1]) * iv.y;
+                                sc[4 * j4 + 2] = __uint_as_float(r[16 * h + 4 * j4 + 2]) * iv.z;
+                                sc[4 * j4 + 3] = __uint_as_float(r[16 * h + 4 * j4 + 3]) * iv.w;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) mask |= (sc[j] > thr ? 1u : 0u) << j;
+                            if (mask) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) q_val[j * 256 + et] = sc[j];
+                                const int nbase = t * BN + cbase;
+                                while (mask) {
+                                    const int j = __ffs(mask) - 1;
+                                    mask &= mask - 1;
+                                    const float v = q_val[j * 256 + et];
+                                    const int id = nbase + j;
+                                    if (v > vals[kTopK - 1]) {      // sorted insert: later (higher id) ties stay below
+#pragma unroll
+                                        for (int q = kTopK - 1; q >= 1; --q) {
+                                            const bool here = v > vals[q], above = v > vals[q - 1];
+                                            vals[q] = here ? (above ? vals[q - 1] : v) : vals[q];
+                                            idxs[q] = here ? (above ? idxs[q - 1] : id) : idxs[q];
+                                        }
+                                        const bool top = v > vals[0];
+                                        vals[0] = top ? v : vals[0];
+                                        idxs[0] = top ? id : idxs[0];
                                     }
                                 }
                             }
                         }
                     } else {
-                        const int jbase = t * BN + c0;
+                        const int jbase = t * BN + half * (BN / 2) + c0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (jbase + j < p.b_rows) runmax = fmaxf(runmax, __uint_as_float(r[j]));
@@ -249,16 +281,20 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             const int a_row = it.a_tile * BM + row_in_tile;
             if (p.mode == kCorpus) {
-                const size_t o = ((size_t)it.group * ((size_t)p.n_a * BM) + (size_t)a_row) * kTopK;
+                const size_t o = (((size_t)it.group * 2 + half) * ((size_t)p.n_a * BM) + (size_t)a_row) * kTopK;
 #pragma unroll
                 for (int j = 0; j < kTopK; ++j) { p.part_val[o + j] = vals[j]; p.part_idx[o + j] = idxs[j]; }
             } else {
-                float v = a_row < p.a_rows ? runmax : 0.f;
+                // max over the two column halves of the same row, then the sum over the block's 128 rows
+                q_val[et] = runmax;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                float v = 0.f;
+                if (half == 0 && a_row < p.a_rows) v = fmaxf(runmax, q_val[et + 128]);
                 v = warp_sum(v);
-                if (lane == 0) s_sum[warp - 2] = v;
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (half == 0 && lane == 0) s_sum[warp - 2] = v;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (et == 0) p.partial[(size_t)it.group * p.n_a + it.a_tile] = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");
             }
         }
     }
@@ -382,7 +418,7 @@ static int make_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows,
 
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
     static bool attr_set = false;
-    const size_t smem = (size_t)kStages * kStageBytes + 1024;
+    const size_t smem = (size_t)kStages * kStageBytes + 1024 + 16 * 256 * 4;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_score_kernel)");
@@ -469,9 +505,9 @@ extern "C" int rdv_corpus_score_topk_bf16(const void* d_e_bf16, const float* d_e
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rc = tc::launch(ma, mb, p, s);
     if (rc) return rc;
-    const int64_t total = (int64_t)n_questions * groups * tc::kTopK;
+    const int64_t total = (int64_t)n_questions * groups * 2 * tc::kTopK;
     tc::corpus_candidates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-        d_part_val, d_part_idx, d_q_inv_norm, groups, p.n_a * tc::BM, n_questions, id_offset, d_cand_val, d_cand_idx);
+        d_part_val, d_part_idx, d_q_inv_norm, groups * 2, p.n_a * tc::BM, n_questions, id_offset, d_cand_val, d_cand_idx);
     RDV_LAUNCH_CHECK("corpus_candidates_kernel");
     return RDV_OK;
 }
@@ -506,4 +542,4 @@ extern "C" int rdv_maxsim_bf16_tc(const void* d_qn_bf16, const void* d_pn_bf16, 
 }
 
 extern "C" int32_t rdv_tc_tile_m(void) { return tc::BM; }
-extern "C" int32_t rdv_tc_candidates_per_group(void) { return tc::kTopK; }
+extern "C" int32_t rdv_tc_candidates_per_group(void) { return 2 * tc::kTopK; }   // two column halves x 16
