@@ -1,0 +1,77 @@
+"""N > 1 host logic on CPU ranks (gloo, world_size 2): shard bounds, the all-gather of per-rank
+candidates and the final merge must reproduce the unsharded oracle exactly.  (The per-rank scoring
+kernel is covered on the GPU in tests/test_tc_gpu.py; CUDA tensors take rdv_topk_merge instead of the
+torch merge used here.)"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ref_restated as R
+from rag_docvqa_b200 import sharded
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, d, Qn, k, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11)
+        E = torch.randn(n, d, generator=g)
+        Q = torch.randn(Qn, d, generator=g)
+        E[n - 3] = E[2]                                     # a cross-shard exact tie
+        lo, hi = sharded.shard_bounds(n, world, rank)
+        scores = R.corpus_scores(E[lo:hi], Q)
+        loc = np.stack([R.topk_lowest_index(scores[q], k) for q in range(Qn)])
+        if loc.shape[1] < k:                                # a shard smaller than k pads with empty slots
+            loc = np.pad(loc, ((0, 0), (0, k - loc.shape[1])), constant_values=-1)
+        val = torch.where(torch.from_numpy(loc) >= 0,
+                          torch.gather(scores, 1, torch.from_numpy(np.maximum(loc, 0))),
+                          torch.full((Qn, k), float("-inf")))
+        idx = torch.where(torch.from_numpy(loc) >= 0, torch.from_numpy(loc) + lo, torch.full((Qn, k), -1))
+        m_val, m_idx = sharded.merge_across_ranks(val, idx, k)
+        full = R.corpus_scores(E, Q)
+        ref = np.stack([R.topk_lowest_index(full[q], k) for q in range(Qn)])
+        ok = bool(np.array_equal(m_idx.numpy(), ref)) and bool(
+            torch.equal(m_val, torch.gather(full, 1, torch.from_numpy(ref))))
+        with open(os.path.join(out_dir, "rank%d.txt" % rank), "w") as f:
+            f.write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,k", [(101, 10), (12, 10)])
+def test_two_rank_merge_equals_unsharded(tmp_path, n, k):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n, 16, 7, k, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / ("rank%d.txt" % r)).read_text() == "ok"
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 10_000_000):
+        for world in (1, 2, 3, 8):
+            spans = [sharded.shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_merge_orders_by_score_then_id():
+    val = torch.tensor([[0.5, 0.9, 0.9, 0.1, 0.9]])
+    idx = torch.tensor([[7, 30, 4, 2, -1]])
+    v, i = sharded.merge_candidates(val, idx, 3)
+    assert i.tolist() == [[4, 30, 7]] and torch.equal(v, torch.tensor([[0.9, 0.9, 0.5]]))
+    ref_v, ref_i = R.merge_topk(val.numpy(), idx.numpy(), 3)
+    assert np.array_equal(i.numpy(), ref_i)
