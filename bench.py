@@ -260,7 +260,33 @@ def stage_extras(dev, hbm_peak, steps):
     ms = timed_loop(lambda i: F.late_interaction(q[0:1], patches[0]), 5, sync) / 5
     out["maxsim_f32"] = {"shape": "50 strips x 2048 x 768 vs 2048 x 768", "ms": ms, "TFLOPs": flops / ms / 1e9,
                          "bound": "CUDA-core FFMA (fp32 parity mode)", "questions_per_s": 1e3 / ms}
+    # the same document through the bf16 tcgen05 mode (normalise + cast included)
+    _, tf_peak, _ = measured_peaks()
+    for _ in range(2):
+        F.late_interaction_bf16(q[0:1], patches[0])
+    ms = timed_loop(lambda i: F.late_interaction_bf16(q[0:1], patches[0]), 10, sync) / 10
+    out["maxsim_bf16_tc"] = {"shape": "50 strips x 2048 x 768 vs 2048 x 768", "ms": ms, "TFLOPs": flops / ms / 1e9,
+                             "frac_tensor": flops / ms / 1e9 / tf_peak, "bound": "tensor (tcgen05, fp32 accumulate in TMEM)",
+                             "questions_per_s": 1e3 / ms, "includes": "fp32->normalised bf16 cast of Q and P"}
     del patches, q
+
+    # corpus mode at C5's per-rank shape: 1.25 M x 768 bf16 rows, 1024 questions, k=10
+    from rag_docvqa_b200 import sharded
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    rows = torch.empty((1_250_000, 768), dtype=torch.bfloat16, device=dev)
+    for a in range(0, rows.shape[0], 250_000):
+        rows[a:a + 250_000] = torch.randn(250_000, 768, generator=g, device=dev).to(torch.bfloat16)
+    shard = sharded.CorpusShard(rows)
+    qs = torch.randn(1024, 768, generator=g, device=dev)
+    for _ in range(2):
+        shard.search_local(qs, 10)
+    ms = timed_loop(lambda i: shard.search_local(qs, 10), 10, sync) / 10
+    cflops = 2.0 * 1024 * rows.shape[0] * 768
+    out["corpus_bf16_tc_per_rank_C5"] = {"shape": "1024 questions x 1.25 M x 768 bf16, k=10", "ms": ms,
+                                         "TFLOPs": cflops / ms / 1e9, "frac_tensor": cflops / ms / 1e9 / tf_peak,
+                                         "questions_per_s": 1024 / ms * 1e3}
+    del rows, shard, qs
 
     # score+top-k on C3 (long documents, 768-d, k=10): far above L2, shows the kernel's streaming rate
     w3 = synth.WORKLOADS["C3"]
