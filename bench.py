@@ -47,6 +47,16 @@ L2_BYTES = 126 * 1024 * 1024
 METRIC = "retrieval_queries_per_sec"
 
 
+def ncu_traffic(key):
+    """Per-launch DRAM traffic of a kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -457,7 +467,8 @@ def run_ours(args):
                        R, R * step_bytes / 1e6),
                    "parallelism": "documents sharded across ranks (dp%d), no data-path collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / hbm_peak, "peak_kind": peak_kind,
+                     "traffic": ncu_traffic("score_topk_ldg_kernel:%s" % w.name) if tables[0].algo == 1 and rank == 0 and base_seed == synth.SEED_BASE + w.config_id else None,
                      "kernel": "score_topk_tma_kernel" if tables[0].algo == 2 else "score_topk_ldg_kernel", "algorithmic_bytes_per_launch": step_bytes,
                      "ms_per_launch": ms_score},
         "e2e": e2e,
