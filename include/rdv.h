@@ -73,8 +73,10 @@ RDV_API int rdv_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_mi
  *   d_topk_cnt  [B]    out: k_b
  *   d_doc_done  [B]    int32 workspace, all zero on entry; the kernel leaves it all zero again
  *   tile_rows          the maximum rdv_tile_desc.rows used (from rdv_score_plan)
- *   algo               RDV_SCORE_TMA: persistent kernel, bulk-async-copy (TMA) ring in shared memory,
- *                      d in {128,256,384,512,768,1024};  RDV_SCORE_LDG: one block per tile, any d % 4 == 0
+ *   algo               RDV_SCORE_TMA (d in {128,256,384,512,768,1024}), RDV_SCORE_LDG or RDV_SCORE_LDG_FUSED
+ *                      (any d % 4 == 0); see the defines below.  TMA / LDG launch the streaming score kernel
+ *                      followed by the per-document selection kernel (two launches, no device-scope fence on
+ *                      the streaming path); LDG_FUSED does both in one launch.
  *   max_rows           max_b n_b (sizes the shared-memory cache of the selection pass)
  * Requirements: d % 4 == 0, 4 <= d <= 8192, 1 <= k <= 1024, B >= 0.
  * ------------------------------------------------------------------------------------------- */
@@ -88,11 +90,12 @@ typedef struct rdv_tile_desc {
 } rdv_tile_desc;
 
 #define RDV_SCORE_AUTO 0
-#define RDV_SCORE_LDG 1
-#define RDV_SCORE_TMA 2
+#define RDV_SCORE_LDG 1        /* one block per tile, 128-bit loads; selection in a second kernel        */
+#define RDV_SCORE_TMA 2        /* persistent, bulk-async-copy (TMA) rings in shared memory; selection in a second kernel */
+#define RDV_SCORE_LDG_FUSED 3  /* LDG kernel with the selection fused in (last block per document): ONE launch */
 
-/* Picks the kernel (AUTO -> the one measured faster on B200, currently LDG) and the tile height for a batch
- * of total_rows rows. */
+/* Picks the kernel (AUTO -> TMA when d allows it, else LDG) and the tile height for a batch of
+ * total_rows rows. */
 RDV_API int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows);
 
 RDV_API int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
@@ -100,12 +103,17 @@ RDV_API int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles
                                int32_t max_rows, float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
                                int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
 
-/* Stand-alone segmented top-k over an existing score vector (same ordering rules as above); used
- * for the visual path, where the scores come from MaxSim (torch.topk at src/_modules.py:2408).
- * d_scores [N] fp32, d_row_off [B+1] int64; outputs / workspace as in rdv_score_topk_f32. */
+/* Scores only (the streaming half of rdv_score_topk_f32): writes d_sims.  Used when the selection runs
+ * elsewhere (rdv_topk_segments_f32, or inside rdv_gather_vt5_inputs).  algo: RDV_SCORE_LDG or RDV_SCORE_TMA. */
+RDV_API int rdv_score_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
+                          const float* d_q, int32_t B, int32_t d, float* d_sims, void* stream);
+
+/* Stand-alone segmented top-k over an existing score vector (same ordering rules as above); the
+ * selection half of rdv_score_topk_f32, and the visual path's top-k over MaxSim scores (torch.topk at
+ * src/_modules.py:2408).  d_scores [N] fp32, d_row_off [B+1] int64; outputs as in rdv_score_topk_f32. */
 RDV_API int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_off, int32_t B, int32_t k,
                                   int32_t max_rows, int32_t* d_topk_idx, float* d_topk_val,
-                                  int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
+                                  int32_t* d_topk_cnt, void* stream);
 
 
 
@@ -181,6 +189,9 @@ RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, i
  *   hit_* (B,k)   per hit in OUTPUT order: chunk index (-1 pad), page, label, #emitted words,
  *                 bbox (f64 x4; [0,0,1,1] when no word was emitted) and crop rectangle (int32 x4; -1 without pages)
  *   seg_ws        int32 workspace of B*k*max_seg*2
+ *   sims / topk_val / max_rows   optional fused selection: when `sims` is non-NULL the kernel first selects the
+ *                 top-k of sims[chunk_off[b] .. chunk_off[b+1]) itself (same ordering as rdv_score_topk_f32)
+ *                 and WRITES topk_idx / topk_val / topk_cnt, so a step is rdv_score_f32 + this kernel.
  * Requirements: 1 <= k <= 64.
  * ------------------------------------------------------------------------------------------- */
 typedef struct rdv_docstore {
@@ -203,8 +214,8 @@ typedef struct rdv_docstore {
 } rdv_docstore;
 
 typedef struct rdv_gather_args {
-    const int32_t* topk_idx;
-    const int32_t* topk_cnt;
+    int32_t* topk_idx;
+    int32_t* topk_cnt;
     int32_t k;
     int32_t include_surroundings;
     int32_t reorder_chunks;
@@ -229,6 +240,10 @@ typedef struct rdv_gather_args {
     int32_t* hit_nwords;
     double* hit_bbox;
     int32_t* hit_rect;
+    const float* sims;
+    float* topk_val;
+    int32_t max_rows;
+    int32_t reserved;
 } rdv_gather_args;
 
 RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args* args, void* stream);

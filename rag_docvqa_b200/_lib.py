@@ -10,10 +10,10 @@ from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
-SCORE_AUTO, SCORE_LDG, SCORE_TMA = 0, 1, 2
+SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
 
 
 class RdvError(RuntimeError):
@@ -36,7 +36,8 @@ class GatherArgsStruct(Structure):
                 ("sep_ids", c_void_p), ("eos_id", c_int32), ("pad_id", c_int32), ("max_len", c_int32),
                 ("max_seg", c_int32)] + [(n, c_void_p) for n in (
                     "seg_ws", "out_ids", "out_boxes", "out_mask", "out_labels", "full_len", "status", "hit_chunk",
-                    "hit_page", "hit_label", "hit_nwords", "hit_bbox", "hit_rect")]
+                    "hit_page", "hit_label", "hit_nwords", "hit_bbox", "hit_rect", "sims", "topk_val")] + [
+                    ("max_rows", c_int32), ("reserved", c_int32)]
 
 
 # name -> (restype, argtypes); tests/test_abi.py checks this table against include/rdv.h
@@ -47,8 +48,9 @@ SIGNATURES = {
     "rdv_score_plan": (c_int32, [c_int64, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32)]),
     "rdv_score_topk_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                      c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_score_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "rdv_topk_segments_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p]),
     "rdv_mean_pool_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "rdv_row_inv_norm_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),

@@ -12,7 +12,7 @@
 // One thread block per document; everything is index arithmetic over CSR arrays (int32 / f64), driven
 // by the top-k kernel's device output -- no host round trip between scoring and the generator input.
 // Byte/integer work: bit-exact against the oracle.
-#include "rdv_common.cuh"
+#include "select.cuh"
 
 namespace rdv {
 
@@ -44,8 +44,19 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     __shared__ int s_total;
     __shared__ int s_overflow;
 
-    const int cnt = a.topk_cnt[b];
     const int64_t c0 = ds.chunk_off[b];
+    if (a.sims) {
+        // fused selection: this block owns document b, so the top-k needs no cross-block traffic at all
+        extern __shared__ float4 smem_dyn[];
+        __shared__ unsigned long long s_red[kScoreWarps];
+        SelectArgs sel;
+        sel.k = k; sel.cache_floats = a.max_rows < kMaxCacheFloats ? a.max_rows : kMaxCacheFloats;
+        sel.topk_idx = a.topk_idx; sel.topk_val = a.topk_val; sel.topk_cnt = a.topk_cnt; sel.doc_done = nullptr;
+        select_topk(sel, b, a.sims + c0, (int)(ds.chunk_off[b + 1] - c0), reinterpret_cast<float*>(smem_dyn), s_red,
+                    BlockSync());
+        __syncthreads();
+    }
+    const int cnt = a.topk_cnt[b];
     int32_t* seg_ws = a.seg_ws + ((size_t)b * k) * (2 * a.max_seg);
     if (tid == 0) s_overflow = 0;
 
@@ -294,10 +305,22 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
                 args->hit_chunk && args->hit_page && args->hit_label && args->hit_nwords && args->hit_bbox &&
                 args->hit_rect && (args->n_sep == 0 || args->sep_ids), RDV_E_INVALID,
                 "gather_vt5_inputs: args has a null array");
+    RDV_REQUIRE(!args->sims || (args->topk_val && args->max_rows >= 0), RDV_E_INVALID,
+                "gather_vt5_inputs: fused selection needs topk_val and max_rows");
     GatherParams P;
     P.ds = *ds;
     P.a = *args;
-    gather_vt5_kernel<<<ds->B, kGatherThreads, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    size_t smem = 0;
+    if (args->sims) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(gather_vt5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gather_vt5)");
+            attr_set = true;
+        }
+        smem = (size_t)(args->max_rows < kMaxCacheFloats ? args->max_rows : kMaxCacheFloats) * sizeof(float) + 16;
+    }
+    gather_vt5_kernel<<<ds->B, kGatherThreads, smem, static_cast<cudaStream_t>(stream)>>>(P);
     RDV_LAUNCH_CHECK("gather_vt5_kernel");
     return RDV_OK;
 }

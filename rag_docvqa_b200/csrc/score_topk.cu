@@ -7,51 +7,39 @@
 // HBM-bound, and for the small batches the reference actually runs (tens of MB) latency-bound.  The
 // batch is cut on the host into row tiles that never cross a document (rdv_tile_desc, 32 bytes each).
 //
-// Two kernels share the descriptor, the arithmetic and the selection epilogue:
+// Kernels (all read every byte of E from HBM exactly once and write every similarity -- the reference
+// returns the full vector, src/_modules.py:2176-2180):
 //
-//  * score_topk_tma_kernel (default for d in {128,256,384,512,768,1024}): persistent, one block per SM,
-//    each block owns a contiguous run of tiles.  A producer warp streams the tiles (and the tile's
-//    question vector) into a shared-memory ring with 1-D bulk async copies (cp.async.bulk -> UBLKCP,
-//    completion on an mbarrier), up to ~190 KB in flight per SM independent of occupancy; eight
-//    consumer warps take one row each out of shared memory (conflict-free LDS.128), produce the dot
-//    product and the squared norm from the same registers, and release the stage.  Every byte of E is read
-//    from HBM exactly once.
-//  * score_topk_ldg_kernel (any d % 4 == 0): one block per tile, a warp per row, ROWS rows in flight
-//    per warp as independent 128-bit no-allocate loads.
+//  * score_ldg_kernel (any d % 4 == 0): one block per tile, a warp per row, ROWS rows in flight per warp as
+//    independent 128-bit no-allocate loads; the question vector is loaded in the same burst.
+//    fused = 1: a device-scope row counter per document tells which block finished the document, and
+//    that block runs the selection (one launch for score + top-k).
+//    fused = 0: scores only; the selection runs in topk_segments_kernel / inside the gather kernel, so no
+//    device-scope fence or atomic sits on the streaming path.
+//  * score_tma_kernel (d in {128,256,384,512,768,1024}): persistent, one block per SM owning a contiguous
+//    run of tiles.  A producer warp streams the tiles into per-warp shared-memory rings with 1-D bulk
+//    async copies (cp.async.bulk -> SASS UBLKCP, completion on mbarriers), ~190 KB in flight per SM
+//    independent of occupancy; each of the 8 consumer warps owns its ring (no cross-warp barrier), reads
+//    rows with conflict-free LDS.128 and produces dot and squared norm from the same registers.
 //
-// Epilogue (both): every similarity is written (the reference returns the full vector,
-// src/_modules.py:2176-2180); a device-scope row counter per document tells which block finished the
-// document, and that block runs the selection out of L2 / shared memory: k rounds of a block-wide arg-max
-// over packed (score, ~index) keys, which makes "descending score, lowest index first" one u64 compare.
-#include "rdv_common.cuh"
+// Selection (select.cuh): k rounds of a block-wide arg-max over packed (score, ~index) u64 keys, which
+// makes "descending score, lowest index first" one integer compare.
+#include "select.cuh"
 
 namespace rdv {
 
-constexpr int kScoreThreads = 256;            // 8 compute warps
-constexpr int kScoreWarps = kScoreThreads / 32;
-constexpr int kMaxCacheFloats = 8192;         // selection pass caches up to this many scores in smem (32 KB)
 constexpr int kTmaThreads = kScoreThreads + 32;   // + 1 producer warp
-constexpr int kTmaMaxStages = 16;
-constexpr int kTmaRingBytes = 176 * 1024;
+constexpr int kTmaMaxStages = 4;                  // per consumer warp
+constexpr int kTmaRingBytes = 192 * 1024;         // all warps
 
 struct ScoreParams {
     const rdv_tile_desc* tiles;
     const int64_t* row_off;
     const float* q;
-    int32_t B, d, k, total_tiles, cache_floats;
-    int32_t tile_rows, stages;                // TMA kernel: rows per stage (max), ring depth
+    int32_t B, d, total_tiles, fused;
+    int32_t tile_rows, stages;                // TMA kernel: rows per stage (max), ring depth per warp
     float* sims;
-    int32_t* topk_idx;
-    float* topk_val;
-    int32_t* topk_cnt;
-    int32_t* doc_done;
-};
-
-struct BlockSync {       // whole block
-    __device__ __forceinline__ void operator()() const { __syncthreads(); }
-};
-struct ConsumerSync {    // the 256 consumer threads of the TMA kernel (named barrier 1)
-    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+    SelectArgs sel;
 };
 
 __device__ __forceinline__ float cosine(float dot, float ss_e, float ss_q) {
@@ -59,65 +47,14 @@ __device__ __forceinline__ float cosine(float dot, float ss_e, float ss_q) {
     return __fdiv_rn(dot, __fadd_rn(__fmul_rn(__fsqrt_rn(ss_e), __fsqrt_rn(ss_q)), 1e-8f));
 }
 
-// Selection of the k best (score desc, index asc) among n scores of one document by 256 threads.
-template <class Sync>
-__device__ void select_topk(const ScoreParams& p, int b, const float* __restrict__ src, int n,
-                            float* cache, unsigned long long* s_red, Sync sync) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool cached = n <= p.cache_floats;
-    if (cached) {
-        for (int i = tid; i < n; i += kScoreThreads) cache[i] = __ldcg(src + i);
-        sync();
-    }
-    const int k_min = n < p.k ? n : p.k;
-    unsigned long long prev = 0;
-    for (int r = 0; r < k_min; ++r) {
-        unsigned long long best = 0;   // every real key is > 0 (order_key(-inf) = 0x007FFFFF)
-        if (cached) {
-#pragma unroll 4
-            for (int i = tid; i < n; i += kScoreThreads) {
-                unsigned long long key = pack_key(cache[i], (uint32_t)i);
-                if ((r == 0 || key < prev) && key > best) best = key;
-            }
-        } else {
-#pragma unroll 4
-            for (int i = tid; i < n; i += kScoreThreads) {
-                unsigned long long key = pack_key(__ldcg(src + i), (uint32_t)i);
-                if ((r == 0 || key < prev) && key > best) best = key;
-            }
-        }
-        best = warp_max_u64(best);
-        if (lane == 0) s_red[warp] = best;
-        sync();
-        unsigned long long win = s_red[0];
-#pragma unroll
-        for (int w = 1; w < kScoreWarps; ++w) win = s_red[w] > win ? s_red[w] : win;
-        sync();
-        if (tid == 0) {
-            uint32_t idx = key_index(win);
-            p.topk_idx[(size_t)b * p.k + r] = (int32_t)idx;
-            p.topk_val[(size_t)b * p.k + r] = cached ? cache[idx] : __ldcg(src + idx);
-        }
-        prev = win;
-    }
-    for (int r = k_min + tid; r < p.k; r += kScoreThreads) {
-        p.topk_idx[(size_t)b * p.k + r] = -1;
-        p.topk_val[(size_t)b * p.k + r] = -INFINITY;
-    }
-    if (tid == 0) {
-        p.topk_cnt[b] = k_min;
-        p.doc_done[b] = 0;   // leave the workspace zeroed for the next call
-    }
-}
-
 // documents with no chunks own no tile: their (empty) results are written by block 0
 __device__ __forceinline__ void write_empty_docs(const ScoreParams& p, int tid, int nthreads) {
     for (int b = tid; b < p.B; b += nthreads) {
         if (p.row_off[b + 1] == p.row_off[b]) {
-            p.topk_cnt[b] = 0;
-            for (int r = 0; r < p.k; ++r) {
-                p.topk_idx[(size_t)b * p.k + r] = -1;
-                p.topk_val[(size_t)b * p.k + r] = -INFINITY;
+            p.sel.topk_cnt[b] = 0;
+            for (int r = 0; r < p.sel.k; ++r) {
+                p.sel.topk_idx[(size_t)b * p.sel.k + r] = -1;
+                p.sel.topk_val[(size_t)b * p.sel.k + r] = -INFINITY;
             }
         }
     }
@@ -131,12 +68,12 @@ __device__ __forceinline__ void publish_rows(const ScoreParams& p, int b, int ro
     __threadfence();
     sync();
     if (threadIdx.x == 0) {
-        const int prev = atomicAdd(p.doc_done + b, rows);
+        const int prev = atomicAdd(p.sel.doc_done + b, rows);
         *s_last = (prev + rows == doc_rows);
         __threadfence();
     }
     sync();
-    if (*s_last) select_topk(p, b, p.sims + p.row_off[b], doc_rows, cache, s_red, sync);
+    if (*s_last) select_topk(p.sel, b, p.sims + p.row_off[b], doc_rows, cache, s_red, sync);
 }
 
 template <int VPL>
@@ -166,7 +103,7 @@ __device__ __forceinline__ float sumsq(const float4 (&q)[VPL]) {
 // LDG kernel: one block per tile.  VPL > 0: d == 128 * VPL, everything in registers.  VPL == 0: any d % 4 == 0.
 // =====================================================================================================
 template <int VPL, int ROWS>
-__global__ void __launch_bounds__(kScoreThreads) score_topk_ldg_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kScoreThreads) score_ldg_kernel(const ScoreParams p) {
     extern __shared__ float4 smem_dyn[];
     __shared__ unsigned long long s_red[kScoreWarps];
     __shared__ int s_last;
@@ -175,7 +112,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_topk_ldg_kernel(const Sco
     const int d4 = p.d >> 2;
     float* cache = reinterpret_cast<float*>(smem_dyn);
 
-    if (blockIdx.x == 0) write_empty_docs(p, tid, kScoreThreads);
+    if (p.fused && blockIdx.x == 0) write_empty_docs(p, tid, kScoreThreads);
     if ((int)blockIdx.x >= p.total_tiles) return;
 
     const rdv_tile_desc t = p.tiles[blockIdx.x];          // one broadcast 32-byte load, no search
@@ -244,7 +181,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_topk_ldg_kernel(const Sco
             if (lane < ROWS && r + lane < t.rows) out[r + lane] = mine;
         }
     }
-    publish_rows(p, t.doc, t.rows, t.doc_rows, cache, s_red, &s_last, BlockSync());
+    if (p.fused) publish_rows(p, t.doc, t.rows, t.doc_rows, cache, s_red, &s_last, BlockSync());
 }
 
 // =====================================================================================================
@@ -277,101 +214,99 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(kTmaThreads, 1) score_topk_tma_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kTmaThreads, 1) score_tma_kernel(const ScoreParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[kTmaMaxStages];
-    __shared__ __align__(8) uint64_t s_empty[kTmaMaxStages];
-    __shared__ rdv_tile_desc s_desc[kTmaMaxStages];
-    __shared__ unsigned long long s_red[kScoreWarps];
-    __shared__ int s_last;
+    __shared__ __align__(8) uint64_t s_full[kScoreWarps][kTmaMaxStages];
+    __shared__ __align__(8) uint64_t s_empty[kScoreWarps][kTmaMaxStages];
 
     constexpr int D4 = 32 * VPL;                       // float4 per row
     constexpr uint32_t kRowBytes = D4 * 16;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.stages;
-    const uint32_t stage_bytes = (uint32_t)(p.tile_rows + 1) * kRowBytes;   // [question row][tile rows]
-    float* cache = reinterpret_cast<float*>(smem_raw + (size_t)S * stage_bytes);
+    const uint32_t stage_bytes = (uint32_t)p.tile_rows * kRowBytes;
 
-    // contiguous run of tiles for this block
+    // contiguous run of tiles for this block; local tile li belongs to consumer warp li % 8
     const int G = gridDim.x;
     const int t0 = (int)((long long)blockIdx.x * p.total_tiles / G);
     const int t1 = (int)((long long)(blockIdx.x + 1) * p.total_tiles / G);
+    const int ntiles = t1 - t0;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kScoreWarps); }
+        for (int w = 0; w < kScoreWarps; ++w)
+            for (int s = 0; s < S; ++s) { mbar_init(&s_full[w][s], 1); mbar_init(&s_empty[w][s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == kScoreWarps) {
-        // ===== producer warp: descriptors are fetched 32 at a time, lane 0 issues the copies =====
-        int stage = 0; uint32_t phase = 0;
-        for (int base = t0; base < t1; base += 32) {
+        // ===== producer warp: descriptors fetched 32 at a time, lane 0 issues the bulk copies =====
+        for (int base = 0; base < ntiles; base += 32) {
             rdv_tile_desc mine = {};
-            if (base + lane < t1) mine = p.tiles[base + lane];
-            const int cnt = min(32, t1 - base);
+            if (base + lane < ntiles) mine = p.tiles[t0 + base + lane];
+            const int cnt = min(32, ntiles - base);
             for (int j = 0; j < cnt; ++j) {
-                rdv_tile_desc t;
-                t.src = reinterpret_cast<const void*>(__shfl_sync(0xffffffffu, (unsigned long long)mine.src, j));
-                t.sims_off = __shfl_sync(0xffffffffu, mine.sims_off, j);
-                t.rows = __shfl_sync(0xffffffffu, mine.rows, j);
-                t.doc = __shfl_sync(0xffffffffu, mine.doc, j);
-                t.doc_rows = __shfl_sync(0xffffffffu, mine.doc_rows, j);
-                t.reserved = 0;
+                const void* src = reinterpret_cast<const void*>(__shfl_sync(0xffffffffu, (unsigned long long)mine.src, j));
+                const int rows = __shfl_sync(0xffffffffu, mine.rows, j);
                 if (lane == 0) {
-                    mbar_wait(&s_empty[stage], phase ^ 1);
-                    unsigned char* dst = smem_raw + (size_t)stage * stage_bytes;
-                    s_desc[stage] = t;
-                    const uint32_t bytes = (uint32_t)t.rows * kRowBytes;
-                    mbar_expect_tx(&s_full[stage], bytes + kRowBytes);
-                    bulk_g2s(dst, p.q + (size_t)t.doc * (D4 * 4), kRowBytes, &s_full[stage]);
-                    bulk_g2s(dst + kRowBytes, t.src, bytes, &s_full[stage]);
+                    const int li = base + j, w = li & (kScoreWarps - 1), u = li >> 3;
+                    const int st = u % S;
+                    const uint32_t ph = (uint32_t)(u / S) & 1u;
+                    mbar_wait(&s_empty[w][st], ph ^ 1);
+                    const uint32_t bytes = (uint32_t)rows * kRowBytes;
+                    mbar_expect_tx(&s_full[w][st], bytes);
+                    bulk_g2s(smem_raw + ((size_t)w * S + st) * stage_bytes, src, bytes, &s_full[w][st]);
                 }
-                if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
         return;
     }
 
-    // ===== consumers: 8 warps, warp w takes rows w, w+8, ... of every tile =====
-    if (blockIdx.x == 0) write_empty_docs(p, tid, kScoreThreads);
-    int stage = 0; uint32_t phase = 0;
-    int pend_doc = -1, pend_rows = 0, pend_n = 0;
-    for (int t_idx = t0; t_idx < t1; ++t_idx) {
-        mbar_wait(&s_full[stage], phase);
-        const rdv_tile_desc t = s_desc[stage];
-        if (t.doc != pend_doc) {
-            if (pend_doc >= 0) publish_rows(p, pend_doc, pend_rows, pend_n, cache, s_red, &s_last, ConsumerSync());
-            pend_doc = t.doc; pend_rows = 0; pend_n = t.doc_rows;
-        }
-        const float4* sq = reinterpret_cast<const float4*>(smem_raw + (size_t)stage * stage_bytes);
-        const float4* se = sq + D4;
-        float4 qv[VPL];
+    // ===== consumer warps: each owns its ring; no cross-warp synchronisation =====
+    int cur_doc = -1;
+    float4 qv[VPL];
+    float ss_q = 0.f;
+    for (int ubase = 0; warp + 8 * ubase < ntiles; ubase += 32) {
+        // this warp's next 32 tile descriptors, one per lane
+        rdv_tile_desc mine = {};
+        const int my_li = warp + 8 * (ubase + lane);
+        if (my_li < ntiles) mine = p.tiles[t0 + my_li];
+        for (int j = 0; j < 32; ++j) {
+            const int u = ubase + j;
+            if (warp + 8 * u >= ntiles) break;
+            const int doc = __shfl_sync(0xffffffffu, mine.doc, j);
+            const int rows = __shfl_sync(0xffffffffu, mine.rows, j);
+            const long long sims_off = __shfl_sync(0xffffffffu, mine.sims_off, j);
+            if (doc != cur_doc) {                          // question vector: issued before waiting on the copy
+                const float4* Q = reinterpret_cast<const float4*>(p.q) + (size_t)doc * D4;
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) qv[i] = sq[lane + 32 * i];
-        const float ss_q = sumsq<VPL>(qv);
-        float* __restrict__ out = p.sims + t.sims_off;
-        for (int r = warp; r < t.rows; r += 2 * kScoreWarps) {
-            const bool two = r + kScoreWarps < t.rows;
-            float4 e0[VPL], e1[VPL];
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                e0[i] = se[(size_t)r * D4 + lane + 32 * i];
-                e1[i] = two ? se[(size_t)(r + kScoreWarps) * D4 + lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < VPL; ++i) qv[i] = __ldg(Q + lane + 32 * i);
+                ss_q = sumsq<VPL>(qv);
+                cur_doc = doc;
             }
-            float d0, s0, d1, s1;
-            fma_row<VPL>(e0, qv, d0, s0);
-            fma_row<VPL>(e1, qv, d1, s1);
-            d0 = warp_sum(d0); s0 = warp_sum(s0); d1 = warp_sum(d1); s1 = warp_sum(s1);
-            if (lane == 0) out[r] = cosine(d0, s0, ss_q);
-            if (lane == 1 && two) out[r + kScoreWarps] = cosine(d1, s1, ss_q);
+            const int st = u % S;
+            const uint32_t ph = (uint32_t)(u / S) & 1u;
+            mbar_wait(&s_full[warp][st], ph);
+            const float4* se = reinterpret_cast<const float4*>(smem_raw + ((size_t)warp * S + st) * stage_bytes);
+            float* __restrict__ out = p.sims + sims_off;
+            for (int r = 0; r < rows; r += 2) {
+                const bool two = r + 1 < rows;
+                float4 e0[VPL], e1[VPL];
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    e0[i] = se[(size_t)r * D4 + lane + 32 * i];
+                    e1[i] = two ? se[(size_t)(r + 1) * D4 + lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float d0, s0, d1, s1;
+                fma_row<VPL>(e0, qv, d0, s0);
+                fma_row<VPL>(e1, qv, d1, s1);
+                d0 = warp_sum(d0); s0 = warp_sum(s0); d1 = warp_sum(d1); s1 = warp_sum(s1);
+                if (lane == 0) out[r] = cosine(d0, s0, ss_q);
+                if (lane == 1 && two) out[r + 1] = cosine(d1, s1, ss_q);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[warp][st]);   // the producer may overwrite this stage
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[stage]);      // stage may be overwritten by the producer
-        pend_rows += t.rows;
-        if (++stage == S) { stage = 0; phase ^= 1; }
     }
-    if (pend_doc >= 0) publish_rows(p, pend_doc, pend_rows, pend_n, cache, s_red, &s_last, ConsumerSync());
 }
 
 // ---- launch plumbing ------------------------------------------------------------------------------
@@ -379,44 +314,51 @@ template <int VPL, int ROWS>
 static int launch_ldg(const ScoreParams& p, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(score_topk_ldg_kernel<VPL, ROWS>,
+        cudaError_t e = cudaFuncSetAttribute(score_ldg_kernel<VPL, ROWS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_topk_ldg)");
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_ldg)");
         attr_set = true;
     }
-    const int grid = p.total_tiles > 0 ? p.total_tiles : 1;
-    const size_t smem = (size_t)p.cache_floats * sizeof(float) + 16;
-    score_topk_ldg_kernel<VPL, ROWS><<<grid, kScoreThreads, smem, stream>>>(p);
-    RDV_LAUNCH_CHECK("score_topk_ldg_kernel");
+    const int grid = p.total_tiles > 0 ? p.total_tiles : (p.fused ? 1 : 0);
+    if (grid == 0) return RDV_OK;
+    const size_t smem = (p.fused ? (size_t)p.sel.cache_floats * sizeof(float) : 0) + 16;
+    score_ldg_kernel<VPL, ROWS><<<grid, kScoreThreads, smem, stream>>>(p);
+    RDV_LAUNCH_CHECK("score_ldg_kernel");
     return RDV_OK;
 }
 
-static int tma_stage_plan(int d, int tile_rows, int* stages) {
-    const int stage_bytes = (tile_rows + 1) * d * 4;
-    int s = kTmaRingBytes / stage_bytes;
-    if (s > kTmaMaxStages) s = kTmaMaxStages;
+// rows per stage and stages per warp for the TMA kernel (~12 KB stages, 24 KB per consumer warp)
+static void tma_plan(int d, int* tile_rows, int* stages) {
+    int rows = (12 * 1024) / (d * 4);
+    rows = rows < 1 ? 1 : (rows > 16 ? 16 : rows);
+    int s = (kTmaRingBytes / kScoreWarps) / (rows * d * 4);
+    s = s > kTmaMaxStages ? kTmaMaxStages : s;
+    *tile_rows = rows;
     *stages = s;
-    return stage_bytes;
 }
 
 template <int VPL>
 static int launch_tma(ScoreParams p, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(score_topk_tma_kernel<VPL>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_topk_tma)");
+        cudaError_t e = cudaFuncSetAttribute(score_tma_kernel<VPL>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaRingBytes + 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_tma)");
         attr_set = true;
     }
-    int stages = 0;
-    const int stage_bytes = tma_stage_plan(p.d, p.tile_rows, &stages);
-    RDV_REQUIRE(stages >= 2, RDV_E_LIMIT, "score_topk_f32: tile_rows=%d too large for the TMA ring at d=%d", p.tile_rows, p.d);
+    if (p.total_tiles == 0) return RDV_OK;
+    int max_rows = 0, stages = 0;
+    tma_plan(p.d, &max_rows, &stages);
+    RDV_REQUIRE(p.tile_rows >= 1 && p.tile_rows <= 16, RDV_E_LIMIT, "score (TMA): tile_rows=%d outside [1, 16]", p.tile_rows);
+    stages = (kTmaRingBytes / kScoreWarps) / (p.tile_rows * p.d * 4);
+    if (stages > kTmaMaxStages) stages = kTmaMaxStages;
+    RDV_REQUIRE(stages >= 1, RDV_E_LIMIT, "score (TMA): tile_rows=%d too large for the ring at d=%d", p.tile_rows, p.d);
     p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + (size_t)p.cache_floats * sizeof(float) + 16;
+    const size_t smem = (size_t)kScoreWarps * stages * p.tile_rows * p.d * 4 + 128;
     int grid = sm_count();
-    if (grid > p.total_tiles) grid = p.total_tiles > 0 ? p.total_tiles : 1;
-    score_topk_tma_kernel<VPL><<<grid, kTmaThreads, smem, stream>>>(p);
-    RDV_LAUNCH_CHECK("score_topk_tma_kernel");
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    score_tma_kernel<VPL><<<grid, kTmaThreads, smem, stream>>>(p);
+    RDV_LAUNCH_CHECK("score_tma_kernel");
     return RDV_OK;
 }
 
@@ -424,59 +366,9 @@ static bool tma_supported(int d) {
     return d == 128 || d == 256 || d == 384 || d == 512 || d == 768 || d == 1024;
 }
 
-}  // namespace rdv
-
-extern "C" int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows) {
-    using namespace rdv;
-    RDV_REQUIRE(algo_out && tile_rows, RDV_E_INVALID, "score_plan: null output");
-    RDV_REQUIRE(algo >= RDV_SCORE_AUTO && algo <= RDV_SCORE_TMA, RDV_E_INVALID, "score_plan: unknown algo %d", algo);
-    // measured on B200 (profiles/): the LDG kernel is ahead at every size so far, so AUTO picks it; the TMA
-    // kernel stays selectable (its consumers serialise on one tile at a time -- see DESIGN.md, next steps)
-    if (algo == RDV_SCORE_AUTO) algo = RDV_SCORE_LDG;
-    RDV_REQUIRE(algo != RDV_SCORE_TMA || tma_supported(d), RDV_E_INVALID,
-                "score_plan: the TMA kernel supports d in {128,256,384,512,768,1024}, got %d", d);
-    *algo_out = algo;
+static int launch_stream(const ScoreParams& p, int algo, cudaStream_t s) {
     if (algo == RDV_SCORE_TMA) {
-        // ~24 KB stages: deep ring, and >= 8 tiles per SM on the small batches so the static split balances
-        int rows = (24 * 1024) / (d * 4);
-        rows = rows >= 16 ? 16 : 8;
-        *tile_rows = rows;
-    } else {
-        const int64_t want_tiles = (int64_t)sm_count() * 8;
-        int t = 128;
-        while (t > 32 && total_rows / t < want_tiles) t >>= 1;
-        *tile_rows = t;
-    }
-    return RDV_OK;
-}
-
-extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
-                                  const int64_t* d_row_off, const float* d_q, int32_t B, int32_t d, int32_t k,
-                                  int32_t max_rows, float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
-                                  int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream) {
-    using namespace rdv;
-    RDV_REQUIRE(B >= 0 && total_tiles >= 0 && max_rows >= 0, RDV_E_INVALID, "score_topk_f32: negative size");
-    if (B == 0) return RDV_OK;
-    RDV_REQUIRE(d_row_off && d_q && d_topk_idx && d_topk_val && d_topk_cnt && d_doc_done, RDV_E_INVALID,
-                "score_topk_f32: null pointer");
-    RDV_REQUIRE((d_sims && d_tiles) || total_tiles == 0, RDV_E_INVALID, "score_topk_f32: null sims / tiles");
-    RDV_REQUIRE(d >= 4 && d <= 8192 && (d & 3) == 0, RDV_E_INVALID,
-                "score_topk_f32: d=%d must be a multiple of 4 in [4, 8192]", d);
-    RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "score_topk_f32: k=%d outside [1, 1024]", k);
-    RDV_REQUIRE(tile_rows >= 1 && tile_rows <= 1024, RDV_E_INVALID, "score_topk_f32: tile_rows=%d outside [1, 1024]", tile_rows);
-    RDV_REQUIRE(algo == RDV_SCORE_LDG || algo == RDV_SCORE_TMA, RDV_E_INVALID,
-                "score_topk_f32: algo must be RDV_SCORE_LDG or RDV_SCORE_TMA (resolve AUTO with rdv_score_plan)");
-    RDV_REQUIRE(aligned16(d_q) && aligned16(d_tiles), RDV_E_ALIGN, "score_topk_f32: q / tiles not 16-byte aligned");
-
-    ScoreParams p = {};
-    p.tiles = d_tiles; p.row_off = d_row_off; p.q = d_q;
-    p.B = B; p.d = d; p.k = k; p.total_tiles = total_tiles; p.tile_rows = tile_rows;
-    p.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
-    p.sims = d_sims; p.topk_idx = d_topk_idx; p.topk_val = d_topk_val; p.topk_cnt = d_topk_cnt;
-    p.doc_done = d_doc_done;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (algo == RDV_SCORE_TMA) {
-        switch (d) {
+        switch (p.d) {
             case 128:  return launch_tma<1>(p, s);
             case 256:  return launch_tma<2>(p, s);
             case 384:  return launch_tma<3>(p, s);
@@ -484,11 +376,11 @@ extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_ti
             case 768:  return launch_tma<6>(p, s);
             case 1024: return launch_tma<8>(p, s);
             default:
-                set_error("score_topk_f32: the TMA kernel supports d in {128,256,384,512,768,1024}, got %d", d);
+                set_error("score: the TMA kernel supports d in {128,256,384,512,768,1024}, got %d", p.d);
                 return RDV_E_INVALID;
         }
     }
-    switch (d) {
+    switch (p.d) {
         case 128:  return launch_ldg<1, 8>(p, s);
         case 256:  return launch_ldg<2, 4>(p, s);
         case 384:  return launch_ldg<3, 4>(p, s);
@@ -499,45 +391,117 @@ extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_ti
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Stand-alone segmented top-k over an existing score vector (the visual path: MaxSim scores -> top-k
-// strips, reference src/_modules.py:2408).  One block per document, same selection as above.
-// ---------------------------------------------------------------------------------------------------
-namespace rdv {
-__global__ void __launch_bounds__(kScoreThreads) topk_segments_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kScoreThreads) topk_segments_kernel(const int64_t* __restrict__ row_off,
+                                                                      const float* __restrict__ scores,
+                                                                      const SelectArgs sel) {
     extern __shared__ float4 smem_dyn[];
     __shared__ unsigned long long s_red[kScoreWarps];
     const int b = blockIdx.x;
-    const int64_t r0 = p.row_off[b];
-    const int n = (int)(p.row_off[b + 1] - r0);
-    select_topk(p, b, p.sims + r0, n, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
+    const int64_t r0 = row_off[b];
+    const int n = (int)(row_off[b + 1] - r0);
+    select_topk(sel, b, scores + r0, n, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
 }
-}  // namespace rdv
 
-extern "C" int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_off, int32_t B, int32_t k,
-                                     int32_t max_rows, int32_t* d_topk_idx, float* d_topk_val,
-                                     int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream) {
-    using namespace rdv;
-    RDV_REQUIRE(B >= 0 && max_rows >= 0, RDV_E_INVALID, "topk_segments_f32: negative size");
-    if (B == 0) return RDV_OK;
-    RDV_REQUIRE(d_row_off && d_topk_idx && d_topk_val && d_topk_cnt && d_doc_done, RDV_E_INVALID,
-                "topk_segments_f32: null pointer");
-    RDV_REQUIRE(d_scores || max_rows == 0, RDV_E_INVALID, "topk_segments_f32: null scores");
-    RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "topk_segments_f32: k=%d outside [1, 1024]", k);
-    ScoreParams p = {};
-    p.row_off = d_row_off; p.B = B; p.k = k;
-    p.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
-    p.sims = const_cast<float*>(d_scores);
-    p.topk_idx = d_topk_idx; p.topk_val = d_topk_val; p.topk_cnt = d_topk_cnt; p.doc_done = d_doc_done;
+static int launch_segments(const float* scores, const int64_t* row_off, int B, const SelectArgs& sel, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(topk_segments)");
         attr_set = true;
     }
-    const size_t smem = (size_t)p.cache_floats * sizeof(float) + 16;
-    topk_segments_kernel<<<B, kScoreThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    const size_t smem = (size_t)sel.cache_floats * sizeof(float) + 16;
+    topk_segments_kernel<<<B, kScoreThreads, smem, s>>>(row_off, scores, sel);
     RDV_LAUNCH_CHECK("topk_segments_kernel");
     return RDV_OK;
+}
+
+}  // namespace rdv
+
+using namespace rdv;
+
+extern "C" int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows) {
+    RDV_REQUIRE(algo_out && tile_rows, RDV_E_INVALID, "score_plan: null output");
+    RDV_REQUIRE(algo >= RDV_SCORE_AUTO && algo <= RDV_SCORE_LDG_FUSED, RDV_E_INVALID, "score_plan: unknown algo %d", algo);
+    if (algo == RDV_SCORE_AUTO) algo = tma_supported(d) ? RDV_SCORE_TMA : RDV_SCORE_LDG;
+    RDV_REQUIRE(algo != RDV_SCORE_TMA || tma_supported(d), RDV_E_INVALID,
+                "score_plan: the TMA kernel supports d in {128,256,384,512,768,1024}, got %d", d);
+    *algo_out = algo;
+    if (algo == RDV_SCORE_TMA) {
+        int stages = 0;
+        tma_plan(d, tile_rows, &stages);
+    } else {
+        // one block per tile: >= ~8 tiles per SM on small batches so the hardware scheduler balances ragged docs
+        const int64_t want_tiles = (int64_t)sm_count() * 8;
+        int t = 128;
+        while (t > 32 && total_rows / t < want_tiles) t >>= 1;
+        *tile_rows = t;
+    }
+    return RDV_OK;
+}
+
+static int check_score_args(const char* who, const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows,
+                            int32_t algo, const float* d_q, int32_t B, int32_t d, const float* d_sims) {
+    RDV_REQUIRE(B >= 0 && total_tiles >= 0, RDV_E_INVALID, "%s: negative size", who);
+    RDV_REQUIRE(d_q, RDV_E_INVALID, "%s: null q", who);
+    RDV_REQUIRE((d_sims && d_tiles) || total_tiles == 0, RDV_E_INVALID, "%s: null sims / tiles", who);
+    RDV_REQUIRE(d >= 4 && d <= 8192 && (d & 3) == 0, RDV_E_INVALID, "%s: d=%d must be a multiple of 4 in [4, 8192]", who, d);
+    RDV_REQUIRE(tile_rows >= 1 && tile_rows <= 1024, RDV_E_INVALID, "%s: tile_rows=%d outside [1, 1024]", who, tile_rows);
+    RDV_REQUIRE(algo == RDV_SCORE_LDG || algo == RDV_SCORE_TMA || algo == RDV_SCORE_LDG_FUSED, RDV_E_INVALID,
+                "%s: algo must be RDV_SCORE_LDG, RDV_SCORE_TMA or RDV_SCORE_LDG_FUSED (resolve AUTO with rdv_score_plan)", who);
+    RDV_REQUIRE(aligned16(d_q) && aligned16(d_tiles), RDV_E_ALIGN, "%s: q / tiles not 16-byte aligned", who);
+    return RDV_OK;
+}
+
+extern "C" int rdv_score_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
+                             const float* d_q, int32_t B, int32_t d, float* d_sims, void* stream) {
+    int rc = check_score_args("score_f32", d_tiles, total_tiles, tile_rows, algo, d_q, B, d, d_sims);
+    if (rc) return rc;
+    RDV_REQUIRE(algo != RDV_SCORE_LDG_FUSED, RDV_E_INVALID, "score_f32: the fused kernel needs rdv_score_topk_f32");
+    if (B == 0 || total_tiles == 0) return RDV_OK;
+    ScoreParams p = {};
+    p.tiles = d_tiles; p.q = d_q; p.B = B; p.d = d; p.total_tiles = total_tiles; p.tile_rows = tile_rows;
+    p.fused = 0; p.sims = d_sims;
+    return launch_stream(p, algo, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
+                                  const int64_t* d_row_off, const float* d_q, int32_t B, int32_t d, int32_t k,
+                                  int32_t max_rows, float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
+                                  int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream) {
+    int rc = check_score_args("score_topk_f32", d_tiles, total_tiles, tile_rows, algo, d_q, B, d, d_sims);
+    if (rc) return rc;
+    RDV_REQUIRE(max_rows >= 0, RDV_E_INVALID, "score_topk_f32: negative size");
+    if (B == 0) return RDV_OK;
+    RDV_REQUIRE(d_row_off && d_topk_idx && d_topk_val && d_topk_cnt && d_doc_done, RDV_E_INVALID,
+                "score_topk_f32: null pointer");
+    RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "score_topk_f32: k=%d outside [1, 1024]", k);
+    ScoreParams p = {};
+    p.tiles = d_tiles; p.row_off = d_row_off; p.q = d_q;
+    p.B = B; p.d = d; p.total_tiles = total_tiles; p.tile_rows = tile_rows; p.sims = d_sims;
+    p.sel.k = k; p.sel.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
+    p.sel.topk_idx = d_topk_idx; p.sel.topk_val = d_topk_val; p.sel.topk_cnt = d_topk_cnt; p.sel.doc_done = d_doc_done;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (algo == RDV_SCORE_LDG_FUSED) {
+        p.fused = 1;
+        return launch_stream(p, RDV_SCORE_LDG, s);
+    }
+    p.fused = 0;
+    rc = launch_stream(p, algo, s);
+    if (rc) return rc;
+    p.sel.doc_done = nullptr;            // the split path needs no counters
+    return launch_segments(d_sims, d_row_off, B, p.sel, s);
+}
+
+extern "C" int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_off, int32_t B, int32_t k,
+                                     int32_t max_rows, int32_t* d_topk_idx, float* d_topk_val,
+                                     int32_t* d_topk_cnt, void* stream) {
+    RDV_REQUIRE(B >= 0 && max_rows >= 0, RDV_E_INVALID, "topk_segments_f32: negative size");
+    if (B == 0) return RDV_OK;
+    RDV_REQUIRE(d_row_off && d_topk_idx && d_topk_val && d_topk_cnt, RDV_E_INVALID, "topk_segments_f32: null pointer");
+    RDV_REQUIRE(d_scores || max_rows == 0, RDV_E_INVALID, "topk_segments_f32: null scores");
+    RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "topk_segments_f32: k=%d outside [1, 1024]", k);
+    SelectArgs sel = {};
+    sel.k = k; sel.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
+    sel.topk_idx = d_topk_idx; sel.topk_val = d_topk_val; sel.topk_cnt = d_topk_cnt; sel.doc_done = nullptr;
+    return launch_segments(d_scores, d_row_off, B, sel, static_cast<cudaStream_t>(stream));
 }

@@ -144,8 +144,11 @@ class DocStore:
     def prepare_gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],
                        include_surroundings: int = 0, reorder_chunks: bool = False, sep_ids: Sequence[int] = (),
                        eos_id: int = 1, pad_id: int = 0, max_len: int = 512, with_layout_labels: bool = False,
-                       max_seg: int = 32) -> "GatherPlan":
-        """Allocates the outputs and fills the argument block of rdv_gather_vt5_inputs (no launch)."""
+                       max_seg: int = 32, sims: Optional[torch.Tensor] = None, topk_val: Optional[torch.Tensor] = None,
+                       max_rows: int = 0) -> "GatherPlan":
+        """Allocates the outputs and fills the argument block of rdv_gather_vt5_inputs (no launch).
+        With `sims` (all similarities of the batch, chunk order) the kernel selects the top-k itself and
+        writes topk_idx / topk_val / topk_cnt: a step is then score kernel + this kernel."""
         dev = self.device
         B, k = topk_idx.shape
         if B != self.B:
@@ -191,6 +194,11 @@ class DocStore:
         a.hit_chunk = t["hit_i"][0].data_ptr(); a.hit_page = t["hit_i"][1].data_ptr()
         a.hit_label = t["hit_i"][2].data_ptr(); a.hit_nwords = t["hit_i"][3].data_ptr()
         a.hit_bbox = t["hit_bbox"].data_ptr(); a.hit_rect = t["hit_rect"].data_ptr()
+        if sims is not None:
+            if topk_val is None:
+                raise ValueError("fused selection needs topk_val")
+            t["sims"], t["topk_val"] = sims, topk_val
+            a.sims = sims.data_ptr(); a.topk_val = topk_val.data_ptr(); a.max_rows = int(max_rows)
         return GatherPlan(self, a, t, max_len, max_seg)
 
     def gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],

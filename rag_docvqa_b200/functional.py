@@ -282,9 +282,8 @@ def topk_segments(scores: Sequence[torch.Tensor], k: int):
     val = torch.empty((B, k), dtype=torch.float32, device=device)
     cnt = torch.empty((B,), dtype=torch.int32, device=device)
     with torch.cuda.device(device):
-        done = _Workspace.zeros_i32(device, B)
         _lib.check(_lib_fn.rdv_topk_segments_f32(flat.data_ptr(), off_d.data_ptr(), B, k, max(sizes), idx.data_ptr(),
-                                                 val.data_ptr(), cnt.data_ptr(), done.data_ptr(), _stream_ptr(device)))
+                                                 val.data_ptr(), cnt.data_ptr(), _stream_ptr(device)))
     return idx, val, cnt
 
 
@@ -337,3 +336,17 @@ def late_interaction_bf16(query: torch.Tensor, patches: torch.Tensor) -> torch.T
         _lib.check(_lib_fn.rdv_maxsim_bf16_tc(qn.data_ptr(), pn.data_ptr(), n, Lq, Lp, d, partial.data_ptr(),
                                               out.data_ptr(), _stream_ptr(device)))
     return out
+
+
+def score_table(table: DocTable, questions: torch.Tensor) -> torch.Tensor:
+    """Scores only (rdv_score_f32): every similarity of the batch, (N,) fp32.  The selection then runs in
+    topk_segments or inside the gather kernel (DocStore.prepare_gather(..., sims=...))."""
+    device = questions.device
+    q = _f32_contig_aligned(questions)
+    sims = torch.empty(table.total_rows, dtype=torch.float32, device=device)
+    algo = _lib.SCORE_LDG if table.algo == _lib.SCORE_LDG_FUSED else table.algo
+    if table.B and table.total_tiles:
+        p_tiles, _ = table.pointers()
+        _lib.check(_lib_fn.rdv_score_f32(p_tiles, table.total_tiles, table.tile_rows, algo, q.data_ptr(), table.B,
+                                         table.d, sims.data_ptr(), _stream_ptr(device)))
+    return sims

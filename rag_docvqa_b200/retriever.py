@@ -272,10 +272,27 @@ class Retriever(StatComponent):
         """B200-native fast path: score -> top-k -> device gather straight into the generator's
         input_ids / boxes / attention_mask (what flatten + VT5.prepare_inputs_for_vqa build on the host,
         src/utils.py:233-253, src/VT5.py:141-185) for a pre-tokenised `DocStore`.  No Python lists."""
-        res = self._score_topk(text_embeddings, question_embeddings)
-        packed = store.gather(res.topk_idx, res.topk_cnt, prompt_ids, include_surroundings=self.include_surroundings,
-                              reorder_chunks=self.reorder_chunks, sep_ids=sep_ids, eos_id=eos_id, pad_id=pad_id,
-                              max_len=max_source_length, with_layout_labels=with_layout_labels)
+        dev = question_embeddings.device if question_embeddings.is_cuda else self.device
+        emb = [_to_device(e, dev) for e in text_embeddings]
+        q = _to_device(question_embeddings, dev)
+        k = int(self.k)
+        with torch.cuda.device(dev):
+            # two launches: streaming score kernel, then ONE block per document selects its top-k and gathers
+            table = F.build_doc_table(emb, q.shape[1], dev)
+            sims = F.score_table(table, q)
+            B = table.B
+            topk_idx = torch.empty((B, k), dtype=torch.int32, device=dev)
+            topk_val = torch.empty((B, k), dtype=torch.float32, device=dev)
+            topk_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+            plan = store.prepare_gather(topk_idx, topk_cnt, prompt_ids, include_surroundings=self.include_surroundings,
+                                        reorder_chunks=self.reorder_chunks, sep_ids=sep_ids, eos_id=eos_id,
+                                        pad_id=pad_id, max_len=max_source_length,
+                                        with_layout_labels=with_layout_labels, sims=sims, topk_val=topk_val,
+                                        max_rows=table.max_rows)
+            plan.launch()
+            packed = plan.finish()
+        res = F.ScoreTopK(list(torch.split(sims, table.sizes)) if B else [], sims, topk_idx, topk_val, topk_cnt,
+                          table.sizes)
         return packed, res
 
 

@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 TEXT_CASES = ["c1", "ragged_norm", "ragged_raw", "k20_d1024"]
 
 
-LDG, TMA = 1, 2
+LDG, TMA, FUSED = 1, 2, 3
+ALGOS = [LDG, TMA, FUSED]
 
 
 def run_case(emb, q, k, tile_rows=0, algo=0):
@@ -47,7 +48,7 @@ def check_against_oracle(res, emb, q, k, ref_sims=None):
         np.testing.assert_array_equal(val[b, :kb], own[idx[b, :kb]])
 
 
-@pytest.mark.parametrize("algo", [LDG, TMA])
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("name", TEXT_CASES)
 def test_golden_cases(golden_dir, name, algo):
     z = np.load(os.path.join(golden_dir, "score_topk_%s.npz" % name))
@@ -60,7 +61,7 @@ def test_golden_cases(golden_dir, name, algo):
     check_against_oracle(res, emb, q, k, ref_sims=ref)   # the reference's own frozen outputs
 
 
-@pytest.mark.parametrize("algo,tile_rows", [(LDG, 8), (LDG, 32), (LDG, 128), (TMA, 1), (TMA, 8), (TMA, 16), (TMA, 40)])
+@pytest.mark.parametrize("algo,tile_rows", [(LDG, 8), (LDG, 32), (LDG, 128), (FUSED, 8), (FUSED, 32), (FUSED, 200), (TMA, 1), (TMA, 5), (TMA, 8), (TMA, 16)])
 @pytest.mark.parametrize("normalised", [True, False])
 def test_c2_full(algo, tile_rows, normalised):
     batch = synth.make_text_batch("C2", normalised=normalised)
@@ -68,7 +69,7 @@ def test_c2_full(algo, tile_rows, normalised):
     check_against_oracle(res, batch["text_embeddings"], batch["question_embeddings"], 5)
 
 
-@pytest.mark.parametrize("algo", [LDG, TMA])
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("k", [1, 5, 10, 20, 64])
 def test_k_sweep_with_duplicates(k, algo):
     sizes = [300, 17, 0, 64, 1, 1000]
@@ -84,7 +85,7 @@ def test_dims(d):
     res = run_case(emb, q, 5)
     check_against_oracle(res, emb, q, 5)
     if d in (128, 256, 384, 512, 768, 1024):
-        for algo in (LDG, TMA):
+        for algo in ALGOS:
             res = run_case(emb, q, 5, algo=algo)
             check_against_oracle(res, emb, q, 5)
     else:
@@ -133,12 +134,22 @@ def test_workspace_left_clean_and_repeatable():
     a = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=TMA)
     b = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=TMA)
     c = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=LDG)
+    f1 = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=FUSED)
+    f2 = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=FUSED)   # counters were left zeroed
     assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_idx, c.topk_idx)
+    assert torch.equal(a.topk_idx, f1.topk_idx) and torch.equal(f1.topk_idx, f2.topk_idx)
     assert torch.equal(a.sims, b.sims)          # deterministic: fixed summation order
-    assert torch.equal(a.sims, c.sims)          # both kernels use the same per-lane order and butterfly
+    assert torch.equal(a.sims, c.sims) and torch.equal(a.sims, f1.sims)   # same per-lane order and butterfly everywhere
 
 
-@pytest.mark.parametrize("algo", [LDG, TMA])
+def test_tma_rejects_oversized_tiles():
+    from rag_docvqa_b200 import _lib
+    batch = synth.make_text_batch("C2", docs=4)
+    with pytest.raises(_lib.RdvError):
+        run_case(batch["text_embeddings"], batch["question_embeddings"], 5, tile_rows=40, algo=TMA)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
 def test_c3_slice_large_docs(algo):
     # documents above the selection cache (8192 scores) exercise the L2-resident selection path
     sizes = [20000, 13000, 500]
