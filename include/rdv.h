@@ -94,8 +94,8 @@ typedef struct rdv_tile_desc {
 #define RDV_SCORE_TMA 2        /* persistent, bulk-async-copy (TMA) rings in shared memory; selection in a second kernel */
 #define RDV_SCORE_LDG_FUSED 3  /* LDG kernel with the selection fused in (last block per document): ONE launch */
 
-/* Picks the kernel (AUTO -> TMA when d allows it, else LDG) and the tile height for a batch of
- * total_rows rows. */
+/* Picks the kernel (AUTO -> RDV_SCORE_LDG, the faster one on B200 at every measured size) and the tile
+ * height for a batch of total_rows rows. */
 RDV_API int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows);
 
 RDV_API int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
@@ -171,6 +171,7 @@ RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, i
  * packing of VT5.prepare_inputs_for_vqa (src/VT5.py:141-185).
  *
  * rdv_docstore: CSR view of B documents, all arrays in DEVICE memory (N chunks, W words, T tokens):
+ *   chunk_rec[N]            rdv_chunk_rec: the per-chunk fields below packed so a hit costs one 32-byte load
  *   chunk_off[B+1] i64      first global chunk of each document (== d_row_off of the score kernel)
  *   chunk_word_off[N+1]     first global word of each chunk        word_tok_off[W+1]  first token of each word
  *   tok_ids[T]              token ids (the tokenizer's ids without EOS, src/VT5.py:160)
@@ -194,9 +195,16 @@ RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, i
  *                 and WRITES topk_idx / topk_val / topk_cnt, so a step is rdv_score_f32 + this kernel.
  * Requirements: 1 <= k <= 64.
  * ------------------------------------------------------------------------------------------- */
+typedef struct rdv_chunk_rec {   /* everything the gather needs about one chunk, in one 32-byte load */
+    int32_t word_begin, word_end;   /* = chunk_word_off[c], chunk_word_off[c+1]           */
+    int32_t tok_begin, tok_end;     /* = word_tok_off[word_begin], word_tok_off[word_end] */
+    int32_t page, label, page_start, reserved;
+} rdv_chunk_rec;
+
 typedef struct rdv_docstore {
     int32_t B;
     int32_t reserved;
+    const rdv_chunk_rec* chunk_rec;
     const int64_t* chunk_off;
     const int32_t* chunk_word_off;
     const int32_t* word_tok_off;

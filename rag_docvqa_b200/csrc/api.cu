@@ -35,7 +35,7 @@ int sm_count() {
 
 }  // namespace rdv
 
-extern "C" int rdv_abi_version(void) { return 5; }
+extern "C" int rdv_abi_version(void) { return 6; }
 
 extern "C" const char* rdv_last_error(void) { return rdv::g_error; }
 

@@ -19,6 +19,7 @@ namespace rdv {
 constexpr int kGatherThreads = 256;
 constexpr int kGatherMaxK = 64;
 constexpr int kMaxFresh = 24;     // fresh sub-intervals of one hit after removing better hits' ranges
+constexpr int kSmemSegs = 4;      // word segments per hit kept in shared memory (more spill to the global ws)
 
 struct GatherParams {
     rdv_docstore ds;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
 
     __shared__ int s_chunk[kGatherMaxK];       // global chunk id of hit i
     __shared__ int s_page[kGatherMaxK];
+    __shared__ int s_label[kGatherMaxK];
     __shared__ int s_lo[kGatherMaxK], s_hi[kGatherMaxK];
     __shared__ int s_nseg[kGatherMaxK], s_ntok[kGatherMaxK], s_nwords[kGatherMaxK];
     __shared__ double s_bbox[kGatherMaxK][4];
@@ -43,8 +45,13 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     __shared__ int s_start[kGatherMaxK + 1];   // output token offset of ordered hit r (after its separator)
     __shared__ int s_total;
     __shared__ int s_overflow;
+    __shared__ int s_hit[kGatherMaxK];         // chunk index (within the document) of hit i
+    __shared__ int s_seg[kGatherMaxK][kSmemSegs][2];   // the first segments of every hit (global ws holds all)
+    __shared__ int s_seg_tok[kGatherMaxK][kSmemSegs][2];   // their token ranges [begin, end)
 
     const int64_t c0 = ds.chunk_off[b];
+    const int n_doc = (int)(ds.chunk_off[b + 1] - c0);
+    const int p0 = a.prompt_off[b], plen = a.prompt_off[b + 1] - p0;   // independent of the hits: issue early
     if (a.sims) {
         // fused selection: this block owns document b, so the top-k needs no cross-block traffic at all
         extern __shared__ float4 smem_dyn[];
@@ -52,21 +59,27 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
         SelectArgs sel;
         sel.k = k; sel.cache_floats = a.max_rows < kMaxCacheFloats ? a.max_rows : kMaxCacheFloats;
         sel.topk_idx = a.topk_idx; sel.topk_val = a.topk_val; sel.topk_cnt = a.topk_cnt; sel.doc_done = nullptr;
-        select_topk(sel, b, a.sims + c0, (int)(ds.chunk_off[b + 1] - c0), reinterpret_cast<float*>(smem_dyn), s_red,
-                    BlockSync());
+        sel.smem_idx = s_hit;
+        select_topk(sel, b, a.sims + c0, n_doc, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
         __syncthreads();
+    } else if (tid < k) {
+        s_hit[tid] = a.topk_idx[(size_t)b * k + tid];
     }
-    const int cnt = a.topk_cnt[b];
+    const int cnt = a.sims ? min(k, n_doc) : a.topk_cnt[b];
+    if (!a.sims) __syncthreads();
     int32_t* seg_ws = a.seg_ws + ((size_t)b * k) * (2 * a.max_seg);
     if (tid == 0) s_overflow = 0;
 
     // ---- A: raw page-list interval of every hit -------------------------------------------------
+    rdv_chunk_rec rec = {};
     if (tid < cnt) {
-        const int gc = (int)(c0 + a.topk_idx[(size_t)b * k + tid]);
-        const int start = ds.chunk_page_start[gc];
-        const int nw = ds.chunk_word_off[gc + 1] - ds.chunk_word_off[gc];
+        const int gc = (int)(c0 + s_hit[tid]);
+        rec = ds.chunk_rec[gc];                                 // one 32-byte record: no dependent hops
+        const int start = rec.page_start;
+        const int nw = rec.word_end - rec.word_begin;
         s_chunk[tid] = gc;
-        s_page[tid] = ds.chunk_page[gc];
+        s_page[tid] = rec.page;
+        s_label[tid] = rec.label;
         if (a.include_surroundings == 0) {
             s_lo[tid] = start; s_hi[tid] = start + nw;         // no neighbours: the page length is not needed
         } else {
@@ -81,13 +94,12 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     // ---- B: fresh sub-intervals (minus better hits on the same page) -> global word segments ------
     if (tid < cnt && a.include_surroundings == 0) {
         // ranges of distinct chunks are disjoint in the page word list: the hit is exactly its own words
-        const int gc = s_chunk[tid];
-        const int wb = ds.chunk_word_off[gc], we = ds.chunk_word_off[gc + 1];
-        int* segs = seg_ws + (size_t)tid * (2 * a.max_seg);
-        segs[0] = wb; segs[1] = we;
+        const int wb = rec.word_begin, we = rec.word_end;
+        s_seg[tid][0][0] = wb; s_seg[tid][0][1] = we;
+        s_seg_tok[tid][0][0] = rec.tok_begin; s_seg_tok[tid][0][1] = rec.tok_end;
         s_nseg[tid] = we > wb ? 1 : 0;
         s_nwords[tid] = we - wb;
-        s_ntok[tid] = ds.word_tok_off[we] - ds.word_tok_off[wb];
+        s_ntok[tid] = rec.tok_end - rec.tok_begin;
     } else if (tid < cnt) {
         Interval fresh[kMaxFresh];
         int nf = 1;
@@ -142,8 +154,14 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
                 nwords += x1 - x0;
             }
         }
-        for (int sidx = 0; sidx < nseg; ++sidx)
-            ntok += ds.word_tok_off[segs[2 * sidx + 1]] - ds.word_tok_off[segs[2 * sidx]];
+        for (int sidx = 0; sidx < nseg; ++sidx) {
+            const int tb = ds.word_tok_off[segs[2 * sidx]], te = ds.word_tok_off[segs[2 * sidx + 1]];
+            ntok += te - tb;
+            if (sidx < kSmemSegs) {
+                s_seg[tid][sidx][0] = segs[2 * sidx]; s_seg[tid][sidx][1] = segs[2 * sidx + 1];
+                s_seg_tok[tid][sidx][0] = tb; s_seg_tok[tid][sidx][1] = te;
+            }
+        }
         s_nseg[tid] = nseg; s_ntok[tid] = ntok; s_nwords[tid] = nwords;
         if (overflow) s_overflow = 1;
     }
@@ -151,7 +169,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
 
     // ---- C: bbox of the emitted words (one warp per hit), crop rectangle, labels, pages ---------
     for (int i = warp; i < cnt; i += kGatherThreads / 32) {
-        const int* segs = seg_ws + (size_t)i * (2 * a.max_seg);
+        const int* segs = s_nseg[i] <= kSmemSegs ? &s_seg[i][0][0] : seg_ws + (size_t)i * (2 * a.max_seg);
         double x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
         for (int sidx = 0; sidx < s_nseg[i]; ++sidx) {
             for (int w = segs[2 * sidx] + lane; w < segs[2 * sidx + 1]; w += 32) {
@@ -199,7 +217,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
             const int gc = s_chunk[i];
             a.hit_chunk[o] = (int32_t)(gc - c0);
             a.hit_page[o] = s_page[i];
-            a.hit_label[o] = ds.chunk_label[gc];
+            a.hit_label[o] = s_label[i];
             a.hit_nwords[o] = s_nwords[i];
             double* bb = a.hit_bbox + o * 4;
             bb[0] = s_bbox[i][0]; bb[1] = s_bbox[i][1]; bb[2] = s_bbox[i][2]; bb[3] = s_bbox[i][3];
@@ -220,7 +238,6 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     }
 
     // ---- E: token offsets of the ordered hits ------------------------------------------------------
-    const int p0 = a.prompt_off[b], plen = a.prompt_off[b + 1] - p0;
     if (tid == 0) {
         int pos = plen;
         for (int r = 0; r < cnt; ++r) {
@@ -264,17 +281,24 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
                     id = a.sep_ids[pos - sep_begin]; lb = 0;
                 } else {
                     int o = pos - s_start[r];
-                    const int* segs = seg_ws + (size_t)i * (2 * a.max_seg);
-                    int sidx = 0, wb = segs[0], we = segs[1];
-                    int nt = ds.word_tok_off[we] - ds.word_tok_off[wb];
-                    while (o >= nt) { o -= nt; ++sidx; wb = segs[2 * sidx]; we = segs[2 * sidx + 1];
-                                      nt = ds.word_tok_off[we] - ds.word_tok_off[wb]; }
-                    const int t = ds.word_tok_off[wb] + o;
+                    int t;
+                    if (s_nseg[i] <= kSmemSegs) {                // token ranges of the segments are in shared memory
+                        int sidx = 0, nt = s_seg_tok[i][0][1] - s_seg_tok[i][0][0];
+                        while (o >= nt) { o -= nt; ++sidx; nt = s_seg_tok[i][sidx][1] - s_seg_tok[i][sidx][0]; }
+                        t = s_seg_tok[i][sidx][0] + o;
+                    } else {
+                        const int* segs = seg_ws + (size_t)i * (2 * a.max_seg);
+                        int sidx = 0, wb = segs[0], we = segs[1];
+                        int nt = ds.word_tok_off[we] - ds.word_tok_off[wb];
+                        while (o >= nt) { o -= nt; ++sidx; wb = segs[2 * sidx]; we = segs[2 * sidx + 1];
+                                          nt = ds.word_tok_off[we] - ds.word_tok_off[wb]; }
+                        t = ds.word_tok_off[wb] + o;
+                    }
                     id = ds.tok_ids[t];
                     const double* wbx = ds.word_box + (size_t)ds.tok_word[t] * 4;   // token -> its word's box
                     bx0 = (int64_t)(wbx[0] * 1000.0); bx1 = (int64_t)(wbx[1] * 1000.0);   // f64 -> i64 truncation
                     bx2 = (int64_t)(wbx[2] * 1000.0); bx3 = (int64_t)(wbx[3] * 1000.0);
-                    lb = ds.chunk_label[s_chunk[i]];
+                    lb = s_label[i];
                 }
             }
         } else if (pos == body) {
@@ -297,7 +321,7 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
                 args->k, kGatherMaxK);
     RDV_REQUIRE(args->max_len >= 2 && args->max_seg >= 1 && args->n_sep >= 0 && args->include_surroundings >= 0,
                 RDV_E_INVALID, "gather_vt5_inputs: bad max_len / max_seg / n_sep / include_surroundings");
-    RDV_REQUIRE(ds->chunk_off && ds->chunk_word_off && ds->word_tok_off && ds->tok_ids && ds->word_box &&
+    RDV_REQUIRE(ds->chunk_rec && ds->chunk_off && ds->chunk_word_off && ds->word_tok_off && ds->tok_ids && ds->word_box &&
                 ds->tok_word && ds->chunk_label && ds->chunk_page && ds->chunk_page_start && ds->page_chunks && ds->run_begin &&
                 ds->run_end, RDV_E_INVALID, "gather_vt5_inputs: docstore has a null array");
     RDV_REQUIRE(args->topk_idx && args->topk_cnt && args->prompt_off && args->prompt_ids && args->seg_ws &&

@@ -422,7 +422,9 @@ using namespace rdv;
 extern "C" int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows) {
     RDV_REQUIRE(algo_out && tile_rows, RDV_E_INVALID, "score_plan: null output");
     RDV_REQUIRE(algo >= RDV_SCORE_AUTO && algo <= RDV_SCORE_LDG_FUSED, RDV_E_INVALID, "score_plan: unknown algo %d", algo);
-    if (algo == RDV_SCORE_AUTO) algo = tma_supported(d) ? RDV_SCORE_TMA : RDV_SCORE_LDG;
+    // measured on B200 (profiles/): the LDG streaming kernel leads at every size (C2 3.2 TB/s, C3 7.1 TB/s vs
+    // 2.6 / 3.2 TB/s for the TMA ring), so AUTO picks it; RDV_SCORE_TMA stays selectable
+    if (algo == RDV_SCORE_AUTO) algo = RDV_SCORE_LDG;
     RDV_REQUIRE(algo != RDV_SCORE_TMA || tma_supported(d), RDV_E_INVALID,
                 "score_plan: the TMA kernel supports d in {128,256,384,512,768,1024}, got %d", d);
     *algo_out = algo;
@@ -480,6 +482,7 @@ extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_ti
     p.B = B; p.d = d; p.total_tiles = total_tiles; p.tile_rows = tile_rows; p.sims = d_sims;
     p.sel.k = k; p.sel.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
     p.sel.topk_idx = d_topk_idx; p.sel.topk_val = d_topk_val; p.sel.topk_cnt = d_topk_cnt; p.sel.doc_done = d_doc_done;
+    p.sel.smem_idx = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (algo == RDV_SCORE_LDG_FUSED) {
         p.fused = 1;
@@ -503,5 +506,6 @@ extern "C" int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row
     SelectArgs sel = {};
     sel.k = k; sel.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
     sel.topk_idx = d_topk_idx; sel.topk_val = d_topk_val; sel.topk_cnt = d_topk_cnt; sel.doc_done = nullptr;
+    sel.smem_idx = nullptr;
     return launch_segments(d_scores, d_row_off, B, sel, static_cast<cudaStream_t>(stream));
 }

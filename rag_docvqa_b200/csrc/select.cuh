@@ -14,6 +14,7 @@ struct SelectArgs {
     float* topk_val;        // (B, k)
     int32_t* topk_cnt;      // (B)
     int32_t* doc_done;      // (B) workspace reset to 0 by the selecting block (may be null)
+    int32_t* smem_idx;      // optional shared-memory copy of the winners (k_min entries) for a fused consumer
 };
 
 struct BlockSync {       // whole block
@@ -60,6 +61,7 @@ __device__ void select_topk(const SelectArgs& p, int b, const float* __restrict_
         if (tid == 0) {
             uint32_t idx = key_index(win);
             p.topk_idx[(size_t)b * p.k + r] = (int32_t)idx;
+            if (p.smem_idx) p.smem_idx[r] = (int32_t)idx;
             p.topk_val[(size_t)b * p.k + r] = cached ? cache[idx] : __ldcg(src + idx);
         }
         prev = win;

@@ -37,7 +37,7 @@ class PackedInputs(NamedTuple):
 class DocStore:
     """CSR view of a batch of documents on the device (see `rdv_docstore` in include/rdv.h)."""
 
-    FIELDS = ("chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "tok_word", "word_box", "chunk_label", "chunk_page",
+    FIELDS = ("chunk_rec", "chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "tok_word", "word_box", "chunk_label", "chunk_page",
               "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh")
 
     def __init__(self, arrays: dict, B: int, device):
@@ -124,8 +124,13 @@ class DocStore:
             chunk_page_start[order] = start_sorted
             run_begin[order] = run_starts[run_id]
             run_end[order] = run_ends[run_id]
+        rec = np.zeros((N, 8), dtype=_I32)                       # rdv_chunk_rec
+        if N:
+            rec[:, 0] = chunk_word_off[:-1]; rec[:, 1] = chunk_word_off[1:]
+            rec[:, 2] = word_tok_off[chunk_word_off[:-1]]; rec[:, 3] = word_tok_off[chunk_word_off[1:]]
+            rec[:, 4] = chunk_page; rec[:, 5] = chunk_label; rec[:, 6] = chunk_page_start
         arrays = dict(
-            chunk_off=chunk_off, chunk_word_off=chunk_word_off.astype(_I32), word_tok_off=word_tok_off.astype(_I32),
+            chunk_rec=np.ascontiguousarray(rec), chunk_off=chunk_off, chunk_word_off=chunk_word_off.astype(_I32), word_tok_off=word_tok_off.astype(_I32),
             tok_ids=np.asarray(tok_ids, dtype=_I32),
             tok_word=np.repeat(np.arange(W, dtype=_I32), np.asarray(word_ntok, dtype=np.int64)) if W else np.zeros(0, dtype=_I32),
             word_box=np.ascontiguousarray(word_box),
