@@ -54,7 +54,7 @@ struct MaxSimParams {
     float* out;           // (n)
 };
 
-__global__ void __launch_bounds__(kMsThreads) maxsim_f32_kernel(const MaxSimParams p) {
+__global__ void __launch_bounds__(kMsThreads, 2) maxsim_f32_kernel(const MaxSimParams p) {
     __shared__ __align__(16) float As[2][kMsBK * kMsLd];
     __shared__ __align__(16) float Bs[2][kMsBK * kMsLd];
     __shared__ float s_rowsum[kMsThreads / 32];

@@ -17,6 +17,7 @@ namespace rdv {
 
 constexpr int kPoolThreads = 256;
 constexpr int kPoolMaxL = 4096;
+constexpr int kPoolUnroll = 8;
 
 struct PoolParams {
     const float* embs;       // (n, L, d)
@@ -28,7 +29,7 @@ struct PoolParams {
     float* out_norm;         // (n,) L2 norm of the pooled row before normalisation, or null
 };
 
-__global__ void __launch_bounds__(kPoolThreads) mean_pool_kernel(const PoolParams p) {
+__global__ void __launch_bounds__(kPoolThreads, 4) mean_pool_kernel(const PoolParams p) {
     extern __shared__ float4 s_part[];            // [G][d4] partial sums (G > 1 only)
     __shared__ float s_mask[kPoolMaxL];
     __shared__ float s_red[kPoolThreads / 32];
@@ -69,18 +70,22 @@ __global__ void __launch_bounds__(kPoolThreads) mean_pool_kernel(const PoolParam
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
             int t = g;
-            // 4 independent loads in flight per thread
-            for (; t + 3 * G < p.L; t += 4 * G) {
-                const float m0 = s_mask[t], m1 = s_mask[t + G], m2 = s_mask[t + 2 * G], m3 = s_mask[t + 3 * G];
-                float4 v0, v1, v2, v3;
-                if (m0 != 0.f) v0 = ldg_stream(base + (size_t)t * d4 + c);
-                if (m1 != 0.f) v1 = ldg_stream(base + (size_t)(t + G) * d4 + c);
-                if (m2 != 0.f) v2 = ldg_stream(base + (size_t)(t + 2 * G) * d4 + c);
-                if (m3 != 0.f) v3 = ldg_stream(base + (size_t)(t + 3 * G) * d4 + c);
-                if (m0 != 0.f) { acc.x = fmaf(v0.x, m0, acc.x); acc.y = fmaf(v0.y, m0, acc.y); acc.z = fmaf(v0.z, m0, acc.z); acc.w = fmaf(v0.w, m0, acc.w); }
-                if (m1 != 0.f) { acc.x = fmaf(v1.x, m1, acc.x); acc.y = fmaf(v1.y, m1, acc.y); acc.z = fmaf(v1.z, m1, acc.z); acc.w = fmaf(v1.w, m1, acc.w); }
-                if (m2 != 0.f) { acc.x = fmaf(v2.x, m2, acc.x); acc.y = fmaf(v2.y, m2, acc.y); acc.z = fmaf(v2.z, m2, acc.z); acc.w = fmaf(v2.w, m2, acc.w); }
-                if (m3 != 0.f) { acc.x = fmaf(v3.x, m3, acc.x); acc.y = fmaf(v3.y, m3, acc.y); acc.z = fmaf(v3.z, m3, acc.z); acc.w = fmaf(v3.w, m3, acc.w); }
+            // kPoolUnroll independent 128-bit loads in flight per thread (masked tokens are never requested)
+            for (; t + (kPoolUnroll - 1) * G < p.L; t += kPoolUnroll * G) {
+                float m[kPoolUnroll];
+                float4 v[kPoolUnroll];
+#pragma unroll
+                for (int u = 0; u < kPoolUnroll; ++u) {
+                    m[u] = s_mask[t + u * G];
+                    if (m[u] != 0.f) v[u] = ldg_stream(base + (size_t)(t + u * G) * d4 + c);
+                }
+#pragma unroll
+                for (int u = 0; u < kPoolUnroll; ++u) {
+                    if (m[u] != 0.f) {
+                        acc.x = fmaf(v[u].x, m[u], acc.x); acc.y = fmaf(v[u].y, m[u], acc.y);
+                        acc.z = fmaf(v[u].z, m[u], acc.z); acc.w = fmaf(v[u].w, m[u], acc.w);
+                    }
+                }
             }
             for (; t < p.L; t += G) {
                 const float m = s_mask[t];
