@@ -9,11 +9,14 @@ does (reference src/_modules.py:2155-2180): cosine score of every chunk, per-doc
 of the hits.  Default workload: C2 = BASELINE.json configs[1] (64 questions x docs of <= 20 pages,
 30 chunks/page, 384-d, k=5).
 
-  value     device-resident: the two kernels of the step (score+top-k, gather into the generator's
-            input_ids/boxes/mask) launched back to back through the C ABI, inputs already in HBM.
+  value     device-resident: the two kernels of the step (streaming score; per-document top-k + gather into
+            the generator's input_ids/boxes/mask) launched through the C ABI, inputs already in HBM.
             Successive steps rotate over R distinct resident batches (> 2x the 126 MB L2 in total), so
-            every step streams its embeddings from HBM.
-  roofline  the dominant kernel (score_topk_f32_kernel) timed alone over the same rotation with CUDA
+            every step streams its embeddings from HBM.  The K timed steps are captured once into a CUDA
+            graph (2K kernel nodes) and the timed region is one launch of it; --lanes 2 (default) lets
+            successive, independent batches alternate between two captured streams, --lanes 1 keeps one
+            dependent chain.  Both, and the same steps as plain stream launches, are reported in `stages`.
+  roofline  the dominant kernel (score_ldg_kernel) timed alone over the same rotation with CUDA
             events; achieved = algorithmic bytes per launch / mean launch duration.
   e2e       the drop-in `Retriever.retrieve` (reference signature: pinned HOST embeddings + the
             reference's nested lists + PIL pages in, the reference's 9-tuple out), H2D and D2H inside
@@ -348,6 +351,7 @@ def run_ours(args):
     sizes = host_batch["sizes"]
     step_bytes = score_bytes(sizes, w.dim, w.k)
     R = max(2, min(16, int(np.ceil(2.2 * L2_BYTES / max(1, step_bytes)))))
+    R += R % 2          # even: with two lanes a batch's buffers are only ever touched by one lane
     batches = [synth.make_text_batch(args.workload, device=dev, seed=base_seed, emb_seed=base_seed + 1000 * (r + 1))
                for r in range(R)]
     tables = [F.build_doc_table(b["text_embeddings"], w.dim, dev, algo=args.algo) for b in batches]
@@ -379,40 +383,89 @@ def run_ours(args):
                                       max_rows=t.max_rows) for o, t in zip(outs, tables)]
     torch.cuda.synchronize()
 
-    def launch_score(i):
-        rc = lib.rdv_score_f32(*score_args[i % R])
-        if rc:
-            _lib.check(rc)
+    def make_launchers(stream_ptr):
+        """(score, gather, step) closures launching on the given stream through the C ABI."""
+        s_args = [a[:-1] + (stream_ptr,) for a in score_args]
+        g_args = [a[:-1] + (stream_ptr,) for a in select_args]
 
-    def launch_gather(i):
-        if plans is not None:
-            plans[i % R].launch(stream)
-        else:
-            rc = lib.rdv_topk_segments_f32(*select_args[i % R])
+        def score(i):
+            rc = lib.rdv_score_f32(*s_args[i % R])
             if rc:
                 _lib.check(rc)
 
-    def launch_step(i):
-        launch_score(i)
-        launch_gather(i)
+        def gather(i):
+            if plans is not None:
+                plans[i % R].launch(stream_ptr)
+            else:
+                rc = lib.rdv_topk_segments_f32(*g_args[i % R])
+                if rc:
+                    _lib.check(rc)
 
+        def step(i):
+            score(i)
+            gather(i)
+        return score, gather, step
+
+    launch_score, launch_gather, launch_step = make_launchers(stream)
     launches_per_step = 2
     for i in range(warmup):
         launch_step(i)
     torch.cuda.synchronize()
 
+    # The timed region is ONE CUDA-graph launch holding exactly `steps` steps (2 kernel nodes each), rotating over
+    # the R resident batches: the hot loop is launch-bound (a step is ~13 us of device time, ~8 us of host
+    # enqueue), so it is captured once and replayed.  `lanes` = 1: the steps form one dependent chain.
+    # `lanes` = 2: successive (independent) batches alternate between two captured streams, so the latency-bound
+    # select+gather of batch i overlaps the HBM-bound score of batch i+1, as a serving loop with two streams would.
+    def capture(fn, n, lanes=1):
+        g = torch.cuda.CUDAGraph()
+        main = torch.cuda.Stream(dev)
+        extra = [torch.cuda.Stream(dev) for _ in range(lanes - 1)]
+        fns = [fn(st.cuda_stream) for st in [main] + extra]
+        main.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.graph(g, stream=main):
+            for st in extra:
+                st.wait_stream(main)
+            for i in range(n):
+                fns[i % lanes](i)
+            for st in extra:
+                main.wait_stream(st)
+        return g
+
+    def timed_graph(g, reps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(reps):
+            g.replay()
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1)
+
+    g_seq = capture(lambda sp: make_launchers(sp)[2], args.steps, 1)
+    g_pipe = capture(lambda sp: make_launchers(sp)[2], args.steps, 2)
+    g_score = capture(lambda sp: make_launchers(sp)[0], args.steps, 1)
+    g_gather = capture(lambda sp: make_launchers(sp)[1], args.steps, 1)
+    for g in (g_seq, g_pipe, g_score, g_gather):
+        g.replay()
+    torch.cuda.synchronize()
+
     # ---- value: K steps, device resident --------------------------------------------------------------
     with ClockSampler(local) as clocks:
-        ms_total = timed_loop(launch_step, args.steps, barrier)
+        ms_seq = timed_graph(g_seq, 1)
+        ms_pipe = timed_graph(g_pipe, 1)
         # per-kernel timings over the same rotation (roofline = the dominant kernel alone)
-        ms_score = timed_loop(launch_score, args.steps, barrier) / args.steps
-        ms_gather = timed_loop(launch_gather, args.steps, barrier) / args.steps
+        ms_score = timed_graph(g_score, 1) / args.steps
+        ms_gather = timed_graph(g_gather, 1) / args.steps
+        ms_plain = timed_loop(launch_step, args.steps, barrier)          # the same steps as plain stream launches
+        ms_score_plain = timed_loop(launch_score, args.steps, barrier) / args.steps
         t_end = time.perf_counter() + 0.6          # keep the GPU busy so the sampler sees clocks under load
         while time.perf_counter() < t_end:
-            for i in range(50):
-                launch_step(i)
+            g_pipe.replay()
             torch.cuda.synchronize()
-    ms_total = max_over_ranks(ms_total)
+    ms_seq, ms_pipe, ms_plain = max_over_ranks(ms_seq), max_over_ranks(ms_pipe), max_over_ranks(ms_plain)
+    pipelined = args.lanes == 2
+    ms_total = ms_pipe if pipelined else ms_seq
     ms_per_step = ms_total / args.steps
     qps = w.docs * world / (ms_per_step * 1e-3)
     achieved = step_bytes / (ms_score * 1e-3) / 1e9
@@ -470,9 +523,12 @@ def run_ours(args):
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(w),
-                   "step": "streaming score kernel + %s, one batch of %d questions" % (
+                   "step": "streaming score kernel + %s, one batch of %d questions; the %d steps are one CUDA-graph "
+                           "launch, %s" % (
                        "select+gather kernel (per-document top-k, packed VT5 inputs, max_source_length 512)"
-                       if plans is not None else "per-document top-k kernel", w.docs),
+                       if plans is not None else "per-document top-k kernel", w.docs, args.steps,
+                       "successive batches alternate between 2 captured streams (gather of batch i overlaps the score "
+                       "of batch i+1)" if pipelined else "one dependent chain"),
                    "l2": "inputs larger than L2: %d distinct resident batches rotated (%.0f MB in total)" % (
                        R, R * step_bytes / 1e6),
                    "parallelism": "documents sharded across ranks (dp%d), no data-path collective" % world},
@@ -485,7 +541,9 @@ def run_ours(args):
         "e2e": e2e,
         "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks.summary(),
-        "stages": {"score_ms": ms_score, "select_gather_ms": ms_gather, "step_ms": ms_per_step},
+        "stages": {"score_ms": ms_score, "select_gather_ms": ms_gather, "step_ms": ms_per_step,
+                   "step_ms_graph_one_chain": ms_seq / args.steps, "step_ms_graph_two_lanes": ms_pipe / args.steps,
+                   "step_ms_plain_stream_launches": ms_plain / args.steps, "score_ms_plain_stream_launches": ms_score_plain},
     }
 
     if rank == 0 and world == 1:
@@ -666,6 +724,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 LDG kernel, 2 TMA kernel")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2],
+                    help="captured streams the steps alternate between (1 = one dependent chain)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

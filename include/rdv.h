@@ -182,6 +182,12 @@ RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, i
  *   run_begin[N], run_end[N]  per chunk: the [begin, end) slice of page_chunks holding its page
  *   chunk_page_start[N]     position of the chunk's first word in its page's word list (src/_modules.py:2044)
  *   doc_page_off[B+1], page_wh[P*2]  (optional) page sizes in pixels for the crop rectangles
+ *   tok_rec[T]              (optional) rdv_tok_rec: token id + its word's box as emitted, int(box * 1000)
+ *                           (src/VT5.py:162,174: float64 product truncated toward zero) -- one 32-byte load per
+ *                           output token instead of tok_ids -> tok_word -> word_box; requires |box * 1000| < 2^31
+ *   chunk_bbox[N*4] f64     (optional) bbox of each chunk's own words (src/_modules.py:1102-1132; [0,0,1,1] for an
+ *                           empty chunk): with include_surroundings == 0 a hit IS its chunk, so no pass over
+ *                           the word boxes is needed
  * rdv_gather_args: hits (the score kernel's d_topk_idx / d_topk_cnt, row pitch k), options, prompt ids
  *   (without EOS, src/VT5.py:147-148), separator ids, and the outputs:
  *   out_ids/out_mask/out_labels (B,max_len) i64, out_boxes (B,max_len,4) i64  (out_labels may be NULL)
@@ -201,6 +207,13 @@ typedef struct rdv_chunk_rec {   /* everything the gather needs about one chunk,
     int32_t page, label, page_start, reserved;
 } rdv_chunk_rec;
 
+typedef struct rdv_tok_rec {     /* everything the emission needs about one token, in one 32-byte load */
+    int32_t id;                  /* = tok_ids[t]                                    */
+    int32_t word;                /* = tok_word[t]                                   */
+    int32_t box[4];              /* = (int64)(word_box[word][e] * 1000.0)           */
+    int32_t reserved[2];
+} rdv_tok_rec;
+
 typedef struct rdv_docstore {
     int32_t B;
     int32_t reserved;
@@ -219,6 +232,8 @@ typedef struct rdv_docstore {
     const int32_t* run_end;
     const int32_t* doc_page_off;
     const int32_t* page_wh;
+    const rdv_tok_rec* tok_rec;
+    const double* chunk_bbox;
 } rdv_docstore;
 
 typedef struct rdv_gather_args {

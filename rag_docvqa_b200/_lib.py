@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -26,7 +26,7 @@ class DocStoreStruct(Structure):
     """Mirror of `rdv_docstore` (include/rdv.h)."""
     _fields_ = [("B", c_int32), ("reserved", c_int32)] + [(n, c_void_p) for n in (
         "chunk_rec", "chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "tok_word", "word_box", "chunk_label", "chunk_page",
-        "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh")]
+        "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh", "tok_rec", "chunk_bbox")]
 
 
 class GatherArgsStruct(Structure):

@@ -1,6 +1,7 @@
 // librdv: error plumbing and device queries shared by every entry point.
 #include "rdv_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace rdv {
@@ -19,6 +20,14 @@ int cuda_fail(cudaError_t err, const char* what) {
     return RDV_E_CUDA;
 }
 
+int pdl_mask() {
+    static const int mask = [] {
+        const char* v = getenv("RDV_PDL");
+        return v ? atoi(v) : kPdlStream;
+    }();
+    return mask;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached_sms = 148;
     int dev = 0;
@@ -35,7 +44,7 @@ int sm_count() {
 
 }  // namespace rdv
 
-extern "C" int rdv_abi_version(void) { return 6; }
+extern "C" int rdv_abi_version(void) { return 7; }
 
 extern "C" const char* rdv_last_error(void) { return rdv::g_error; }
 

@@ -49,9 +49,15 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     __shared__ int s_seg[kGatherMaxK][kSmemSegs][2];   // the first segments of every hit (global ws holds all)
     __shared__ int s_seg_tok[kGatherMaxK][kSmemSegs][2];   // their token ranges [begin, end)
 
+    pdl_launch_dependents();   // the next batch's score kernel may be scheduled while this one gathers
+    pdl_wait();                // similarities / hits come from the preceding kernel in the stream
     const int64_t c0 = ds.chunk_off[b];
     const int n_doc = (int)(ds.chunk_off[b + 1] - c0);
     const int p0 = a.prompt_off[b], plen = a.prompt_off[b + 1] - p0;   // independent of the hits: issue early
+    // no neighbours: a hit is exactly its own chunk, so its bbox is the chunk's precomputed bbox and phase C
+    // (a dependent pass over the word boxes) disappears
+    const bool own_bbox = a.include_surroundings == 0 && ds.chunk_bbox != nullptr;
+    const int page0 = (ds.doc_page_off && ds.page_wh) ? ds.doc_page_off[b] : -1;
     if (a.sims) {
         // fused selection: this block owns document b, so the top-k needs no cross-block traffic at all
         extern __shared__ float4 smem_dyn[];
@@ -75,6 +81,11 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     if (tid < cnt) {
         const int gc = (int)(c0 + s_hit[tid]);
         rec = ds.chunk_rec[gc];                                 // one 32-byte record: no dependent hops
+        if (own_bbox) {                                         // independent of rec: both loads in flight together
+            const double2* cb = reinterpret_cast<const double2*>(ds.chunk_bbox + (size_t)gc * 4);
+            const double2 lo2 = cb[0], hi2 = cb[1];
+            s_bbox[tid][0] = lo2.x; s_bbox[tid][1] = lo2.y; s_bbox[tid][2] = hi2.x; s_bbox[tid][3] = hi2.y;
+        }
         const int start = rec.page_start;
         const int nw = rec.word_end - rec.word_begin;
         s_chunk[tid] = gc;
@@ -88,8 +99,9 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
             s_lo[tid] = max(0, start - a.include_surroundings);
             s_hi[tid] = min(page_len, start + nw + a.include_surroundings);
         }
+        if (!a.reorder_chunks) s_order[tid] = tid;
     }
-    __syncthreads();
+    if (a.include_surroundings != 0) __syncthreads();           // phase B reads the other hits' intervals
 
     // ---- B: fresh sub-intervals (minus better hits on the same page) -> global word segments ------
     if (tid < cnt && a.include_surroundings == 0) {
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     __syncthreads();
 
     // ---- C: bbox of the emitted words (one warp per hit), crop rectangle, labels, pages ---------
-    for (int i = warp; i < cnt; i += kGatherThreads / 32) {
+    for (int i = warp; i < cnt && !own_bbox; i += kGatherThreads / 32) {
         const int* segs = s_nseg[i] <= kSmemSegs ? &s_seg[i][0][0] : seg_ws + (size_t)i * (2 * a.max_seg);
         double x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
         for (int sidx = 0; sidx < s_nseg[i]; ++sidx) {
@@ -187,13 +199,12 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
             s_bbox[i][0] = x0; s_bbox[i][1] = y0; s_bbox[i][2] = x1; s_bbox[i][3] = y1;
         }
     }
-    __syncthreads();
+    if (!own_bbox) __syncthreads();
 
     // ---- D: output order (identity, or stable sort by (page, ymin, xmin)) -------------------------
-    if (tid < cnt) {
-        int rank = tid;
-        if (a.reorder_chunks) {
-            rank = 0;
+    if (a.reorder_chunks) {
+        if (tid < cnt) {
+            int rank = 0;
             const int pg = s_page[tid];
             const double ky = s_bbox[tid][1], kx = s_bbox[tid][0];
             for (int j = 0; j < cnt; ++j) {
@@ -204,10 +215,10 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
                 const bool equal = pj == pg && jy == ky && jx == kx;
                 if (less || (equal && j < tid)) ++rank;
             }
+            s_order[rank] = tid;
         }
-        s_order[rank] = tid;
+        __syncthreads();
     }
-    __syncthreads();
 
     // per-hit metadata, in OUTPUT order
     if (tid < k) {
@@ -222,8 +233,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
             double* bb = a.hit_bbox + o * 4;
             bb[0] = s_bbox[i][0]; bb[1] = s_bbox[i][1]; bb[2] = s_bbox[i][2]; bb[3] = s_bbox[i][3];
             int32_t* rc = a.hit_rect + o * 4;
-            if (ds.doc_page_off && ds.page_wh) {
-                const int pidx = ds.doc_page_off[b] + s_page[i];
+            if (page0 >= 0) {
+                const int pidx = page0 + s_page[i];
                 const double W = (double)ds.page_wh[2 * pidx], H = (double)ds.page_wh[2 * pidx + 1];
                 const int rx0 = (int)(bb[0] * W), ry0 = (int)(bb[1] * H);      // int() truncation
                 const int rx1 = (int)(bb[2] * W), ry1 = (int)(bb[3] * H);
@@ -237,8 +248,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
         }
     }
 
-    // ---- E: token offsets of the ordered hits ------------------------------------------------------
-    if (tid == 0) {
+    // ---- E: token offsets of the ordered hits (warp 1, while warp 0 writes the per-hit metadata) --------
+    if (tid == 32) {
         int pos = plen;
         for (int r = 0; r < cnt; ++r) {
             const int i = s_order[r];
@@ -294,10 +305,17 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
                                           nt = ds.word_tok_off[we] - ds.word_tok_off[wb]; }
                         t = ds.word_tok_off[wb] + o;
                     }
-                    id = ds.tok_ids[t];
-                    const double* wbx = ds.word_box + (size_t)ds.tok_word[t] * 4;   // token -> its word's box
-                    bx0 = (int64_t)(wbx[0] * 1000.0); bx1 = (int64_t)(wbx[1] * 1000.0);   // f64 -> i64 truncation
-                    bx2 = (int64_t)(wbx[2] * 1000.0); bx3 = (int64_t)(wbx[3] * 1000.0);
+                    if (ds.tok_rec) {
+                        // one 32-byte record per token: id + its word's box already multiplied by 1000 and truncated
+                        const int4* tr = reinterpret_cast<const int4*>(ds.tok_rec + t);
+                        const int4 r0 = tr[0], r1 = tr[1];
+                        id = r0.x; bx0 = r0.z; bx1 = r0.w; bx2 = r1.x; bx3 = r1.y;
+                    } else {
+                        id = ds.tok_ids[t];
+                        const double* wbx = ds.word_box + (size_t)ds.tok_word[t] * 4;   // token -> its word's box
+                        bx0 = (int64_t)(wbx[0] * 1000.0); bx1 = (int64_t)(wbx[1] * 1000.0);   // f64 -> i64 truncation
+                        bx2 = (int64_t)(wbx[2] * 1000.0); bx3 = (int64_t)(wbx[3] * 1000.0);
+                    }
                     lb = s_label[i];
                 }
             }
@@ -305,7 +323,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
             id = a.eos_id; m = 1; lb = 4;                        // EOS: box 0, label 4
         }
         ids[pos] = id; msk[pos] = m;
-        box[4 * pos] = bx0; box[4 * pos + 1] = bx1; box[4 * pos + 2] = bx2; box[4 * pos + 3] = bx3;
+        longlong2* bo = reinterpret_cast<longlong2*>(box + 4 * (size_t)pos);      // (B, L, 4) int64: 32-byte aligned
+        bo[0] = make_longlong2(bx0, bx1); bo[1] = make_longlong2(bx2, bx3);
         if (lab) lab[pos] = lb;
     }
 }
@@ -329,6 +348,8 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
                 args->hit_chunk && args->hit_page && args->hit_label && args->hit_nwords && args->hit_bbox &&
                 args->hit_rect && (args->n_sep == 0 || args->sep_ids), RDV_E_INVALID,
                 "gather_vt5_inputs: args has a null array");
+    RDV_REQUIRE(aligned16(args->out_boxes) && aligned16(ds->chunk_bbox) && aligned16(ds->tok_rec), RDV_E_ALIGN,
+                "gather_vt5_inputs: out_boxes / chunk_bbox / tok_rec must be 16-byte aligned");
     RDV_REQUIRE(!args->sims || (args->topk_val && args->max_rows >= 0), RDV_E_INVALID,
                 "gather_vt5_inputs: fused selection needs topk_val and max_rows");
     GatherParams P;
@@ -344,7 +365,8 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
         }
         smem = (size_t)(args->max_rows < kMaxCacheFloats ? args->max_rows : kMaxCacheFloats) * sizeof(float) + 16;
     }
-    gather_vt5_kernel<<<ds->B, kGatherThreads, smem, static_cast<cudaStream_t>(stream)>>>(P);
-    RDV_LAUNCH_CHECK("gather_vt5_kernel");
+    cudaError_t le = launch_pdl(kPdlSelect, gather_vt5_kernel, dim3(ds->B), dim3(kGatherThreads), smem,
+                                static_cast<cudaStream_t>(stream), P);
+    if (le != cudaSuccess) return cuda_fail(le, "gather_vt5_kernel");
     return RDV_OK;
 }

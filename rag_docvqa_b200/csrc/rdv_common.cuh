@@ -35,6 +35,39 @@ int sm_count();
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// The per-document batches the reference runs are tens of MB: a kernel is ~5 us of HBM time, so the ~2 us
+// drain + launch gap between two dependent kernels is a third of the step (measured: scripts/probe_stream.cu,
+// 34 MB pure read: 8.1 us per launch back to back, 6.3 us with PDL).  Every kernel launched through
+// launch_pdl() (a) calls pdl_launch_dependents() first, so the next kernel in the stream can be scheduled
+// while this one still executes, and (b) calls pdl_wait() BEFORE its first global-memory access --
+// griddepcontrol.wait returns once the preceding grid has completed and its writes are visible, so stream
+// order is preserved exactly.  Which launches carry the attribute is a measured choice (RDV_PDL bit mask in the
+// environment; scripts/probe_step.py on B200, C2 step score -> select+gather): plain launches 17.1 us with
+// none, 15.1 us with the streaming kernels only (default), 15.7 us with both; inside a CUDA graph 13.2 us with
+// or without the streaming kernels, 15.1 us when the select/gather kernel is launched early as well.
+int pdl_mask();                       // RDV_PDL bit 0: streaming kernels (default), bit 1: selection / gather kernels
+constexpr int kPdlStream = 1, kPdlSelect = 2;
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- ordering keys ----------------------------------------------------------------------------
 // fp32 -> u32 whose unsigned order equals torch.topk's order: NaN (either sign) greatest, -0 == +0.
 __device__ __forceinline__ uint32_t order_key(float v) {

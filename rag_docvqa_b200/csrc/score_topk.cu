@@ -102,17 +102,17 @@ __device__ __forceinline__ float sumsq(const float4 (&q)[VPL]) {
 // =====================================================================================================
 // LDG kernel: one block per tile.  VPL > 0: d == 128 * VPL, everything in registers.  VPL == 0: any d % 4 == 0.
 // =====================================================================================================
-template <int VPL, int ROWS>
-__global__ void __launch_bounds__(kScoreThreads) score_ldg_kernel(const ScoreParams p) {
-    extern __shared__ float4 smem_dyn[];
-    __shared__ unsigned long long s_red[kScoreWarps];
-    __shared__ int s_last;
-
+template <int VPL, int ROWS, int MINB, bool FUSED>
+__global__ void __launch_bounds__(kScoreThreads, MINB) score_ldg_kernel(const ScoreParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d4 = p.d >> 2;
-    float* cache = reinterpret_cast<float*>(smem_dyn);
 
-    if (p.fused && blockIdx.x == 0) write_empty_docs(p, tid, kScoreThreads);
+    pdl_launch_dependents();      // the selection / gather kernel may be scheduled behind this grid's last wave
+    pdl_wait();                   // embeddings, questions and descriptors come from earlier work in the stream
+
+    if constexpr (FUSED) {
+        if (blockIdx.x == 0) write_empty_docs(p, tid, kScoreThreads);
+    }
     if ((int)blockIdx.x >= p.total_tiles) return;
 
     const rdv_tile_desc t = p.tiles[blockIdx.x];          // one broadcast 32-byte load, no search
@@ -181,7 +181,12 @@ __global__ void __launch_bounds__(kScoreThreads) score_ldg_kernel(const ScorePar
             if (lane < ROWS && r + lane < t.rows) out[r + lane] = mine;
         }
     }
-    if (p.fused) publish_rows(p, t.doc, t.rows, t.doc_rows, cache, s_red, &s_last, BlockSync());
+    if constexpr (FUSED) {
+        extern __shared__ float4 smem_dyn[];
+        __shared__ unsigned long long s_red[kScoreWarps];
+        __shared__ int s_last;
+        publish_rows(p, t.doc, t.rows, t.doc_rows, reinterpret_cast<float*>(smem_dyn), s_red, &s_last, BlockSync());
+    }
 }
 
 // =====================================================================================================
@@ -310,20 +315,25 @@ __global__ void __launch_bounds__(kTmaThreads, 1) score_tma_kernel(const ScorePa
 }
 
 // ---- launch plumbing ------------------------------------------------------------------------------
-template <int VPL, int ROWS>
+template <int VPL, int ROWS, int MINB>
 static int launch_ldg(const ScoreParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(score_ldg_kernel<VPL, ROWS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_ldg)");
-        attr_set = true;
+    if (p.fused) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(score_ldg_kernel<VPL, ROWS, MINB, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_ldg)");
+            attr_set = true;
+        }
+        const int grid = p.total_tiles > 0 ? p.total_tiles : 1;
+        const size_t smem = (size_t)p.sel.cache_floats * sizeof(float) + 16;
+        cudaError_t e = launch_pdl(kPdlStream, score_ldg_kernel<VPL, ROWS, MINB, true>, dim3(grid), dim3(kScoreThreads), smem, stream, p);
+        if (e != cudaSuccess) return cuda_fail(e, "score_ldg_kernel (fused)");
+        return RDV_OK;
     }
-    const int grid = p.total_tiles > 0 ? p.total_tiles : (p.fused ? 1 : 0);
-    if (grid == 0) return RDV_OK;
-    const size_t smem = (p.fused ? (size_t)p.sel.cache_floats * sizeof(float) : 0) + 16;
-    score_ldg_kernel<VPL, ROWS><<<grid, kScoreThreads, smem, stream>>>(p);
-    RDV_LAUNCH_CHECK("score_ldg_kernel");
+    if (p.total_tiles == 0) return RDV_OK;
+    cudaError_t e = launch_pdl(kPdlStream, score_ldg_kernel<VPL, ROWS, MINB, false>, dim3(p.total_tiles), dim3(kScoreThreads), 0, stream, p);
+    if (e != cudaSuccess) return cuda_fail(e, "score_ldg_kernel");
     return RDV_OK;
 }
 
@@ -380,14 +390,18 @@ static int launch_stream(const ScoreParams& p, int algo, cudaStream_t s) {
                 return RDV_E_INVALID;
         }
     }
+    // Two shapes per width (measured with scripts/probe_stream.cu on B200).  Small batches (the plan gives them
+    // <= 32-row tiles) are launch/latency-bound: fewer rows in flight per warp, <= 51 registers, 5 blocks per SM
+    // so the whole batch is resident in ~1 wave.  Large batches keep more rows in flight per warp.
+    const bool small = p.tile_rows <= 32 && !p.fused;
     switch (p.d) {
-        case 128:  return launch_ldg<1, 8>(p, s);
-        case 256:  return launch_ldg<2, 4>(p, s);
-        case 384:  return launch_ldg<3, 4>(p, s);
-        case 512:  return launch_ldg<4, 4>(p, s);
-        case 768:  return launch_ldg<6, 2>(p, s);
-        case 1024: return launch_ldg<8, 2>(p, s);
-        default:   return launch_ldg<0, 2>(p, s);
+        case 128:  return small ? launch_ldg<1, 4, 5>(p, s) : launch_ldg<1, 8, 3>(p, s);
+        case 256:  return small ? launch_ldg<2, 2, 5>(p, s) : launch_ldg<2, 4, 3>(p, s);
+        case 384:  return small ? launch_ldg<3, 2, 5>(p, s) : launch_ldg<3, 4, 3>(p, s);
+        case 512:  return small ? launch_ldg<4, 2, 4>(p, s) : launch_ldg<4, 4, 2>(p, s);
+        case 768:  return small ? launch_ldg<6, 1, 4>(p, s) : launch_ldg<6, 2, 2>(p, s);
+        case 1024: return small ? launch_ldg<8, 1, 3>(p, s) : launch_ldg<8, 2, 2>(p, s);
+        default:   return launch_ldg<0, 2, 2>(p, s);
     }
 }
 
@@ -397,6 +411,8 @@ __global__ void __launch_bounds__(kScoreThreads) topk_segments_kernel(const int6
     extern __shared__ float4 smem_dyn[];
     __shared__ unsigned long long s_red[kScoreWarps];
     const int b = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t r0 = row_off[b];
     const int n = (int)(row_off[b + 1] - r0);
     select_topk(sel, b, scores + r0, n, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
@@ -410,8 +426,8 @@ static int launch_segments(const float* scores, const int64_t* row_off, int B, c
         attr_set = true;
     }
     const size_t smem = (size_t)sel.cache_floats * sizeof(float) + 16;
-    topk_segments_kernel<<<B, kScoreThreads, smem, s>>>(row_off, scores, sel);
-    RDV_LAUNCH_CHECK("topk_segments_kernel");
+    cudaError_t e = launch_pdl(kPdlSelect, topk_segments_kernel, dim3(B), dim3(kScoreThreads), smem, s, row_off, scores, sel);
+    if (e != cudaSuccess) return cuda_fail(e, "topk_segments_kernel");
     return RDV_OK;
 }
 

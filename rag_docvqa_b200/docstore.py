@@ -38,7 +38,7 @@ class DocStore:
     """CSR view of a batch of documents on the device (see `rdv_docstore` in include/rdv.h)."""
 
     FIELDS = ("chunk_rec", "chunk_off", "chunk_word_off", "word_tok_off", "tok_ids", "tok_word", "word_box", "chunk_label", "chunk_page",
-              "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh")
+              "chunk_page_start", "page_chunks", "run_begin", "run_end", "doc_page_off", "page_wh", "tok_rec", "chunk_bbox")
 
     def __init__(self, arrays: dict, B: int, device):
         self.B = B
@@ -70,8 +70,10 @@ class DocStore:
 
     @classmethod
     def from_lists(cls, words_text_chunks, words_box_chunks, layout_labels_chunks, page_indices,
-                   tokenize: Callable[[str], Sequence[int]], device, images=None) -> "DocStore":
-        """tokenize(word) -> the word's token ids WITHOUT the trailing EOS (src/VT5.py:160)."""
+                   tokenize: Callable[[str], Sequence[int]], device, images=None, derived: bool = True) -> "DocStore":
+        """tokenize(word) -> the word's token ids WITHOUT the trailing EOS (src/VT5.py:160).
+        derived=False leaves out the optional gather-friendly views (tok_rec, chunk_bbox); the kernel then
+        walks tok_ids -> tok_word -> word_box (tests cover both)."""
         B = len(words_text_chunks)
         sizes = np.array([len(doc) for doc in words_text_chunks], dtype=np.int64)
         chunk_off = np.zeros(B + 1, dtype=np.int64)
@@ -129,10 +131,30 @@ class DocStore:
             rec[:, 0] = chunk_word_off[:-1]; rec[:, 1] = chunk_word_off[1:]
             rec[:, 2] = word_tok_off[chunk_word_off[:-1]]; rec[:, 3] = word_tok_off[chunk_word_off[1:]]
             rec[:, 4] = chunk_page; rec[:, 5] = chunk_label; rec[:, 6] = chunk_page_start
+        tok_ids_a = np.asarray(tok_ids, dtype=_I32)
+        tok_word = np.repeat(np.arange(W, dtype=_I32), np.asarray(word_ntok, dtype=np.int64)) if W else np.zeros(0, dtype=_I32)
+        # derived, gather-friendly views (include/rdv.h: rdv_tok_rec, chunk_bbox)
+        views = {}
+        box1000 = word_box * 1000.0                               # the float64 product of src/VT5.py:162
+        if derived and (W == 0 or bool(np.all(np.abs(box1000) < 2.0 ** 31))):   # NaN/inf/huge boxes: keep the f64 path
+            tok_rec = np.zeros((len(tok_ids_a), 8), dtype=_I32)
+            tok_rec[:, 0] = tok_ids_a
+            tok_rec[:, 1] = tok_word
+            if W:
+                tok_rec[:, 2:6] = box1000.astype(np.int64)[tok_word]      # truncation toward zero, as int()
+            views["tok_rec"] = tok_rec
+        chunk_bbox = np.tile(np.array([0.0, 0.0, 1.0, 1.0]), (N, 1))       # empty chunk: src/_modules.py:1126-1127
+        nonempty = chunk_nwords > 0
+        if W:
+            starts = chunk_word_off[:-1][nonempty]
+            chunk_bbox[nonempty, :2] = np.minimum.reduceat(word_box[:, :2], starts, axis=0)
+            chunk_bbox[nonempty, 2:] = np.maximum.reduceat(word_box[:, 2:], starts, axis=0)
+        if derived:
+            views["chunk_bbox"] = np.ascontiguousarray(chunk_bbox)
         arrays = dict(
+            **views,
             chunk_rec=np.ascontiguousarray(rec), chunk_off=chunk_off, chunk_word_off=chunk_word_off.astype(_I32), word_tok_off=word_tok_off.astype(_I32),
-            tok_ids=np.asarray(tok_ids, dtype=_I32),
-            tok_word=np.repeat(np.arange(W, dtype=_I32), np.asarray(word_ntok, dtype=np.int64)) if W else np.zeros(0, dtype=_I32),
+            tok_ids=tok_ids_a, tok_word=tok_word,
             word_box=np.ascontiguousarray(word_box),
             chunk_label=chunk_label, chunk_page=chunk_page, chunk_page_start=chunk_page_start,
             page_chunks=order.astype(_I32), run_begin=run_begin, run_end=run_end)

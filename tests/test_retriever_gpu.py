@@ -134,7 +134,8 @@ def prompts_for(questions):
             for qs in questions]
 
 
-def test_packed_inputs_match_reference_golden(golden_dir):
+@pytest.mark.parametrize("derived", [True, False])
+def test_packed_inputs_match_reference_golden(golden_dir, derived):
     """tests/golden/vt5_pack.json holds what the reference's flatten + VT5.prepare_inputs_for_vqa built."""
     from rag_docvqa_b200.docstore import DocStore
     from rag_docvqa_b200.retriever import Retriever
@@ -142,7 +143,8 @@ def test_packed_inputs_match_reference_golden(golden_dir):
     with open(os.path.join(golden_dir, "vt5_pack.json")) as f:
         packs = json.load(f)
     table = synth.make_tokens_for_words(words, seed=packs["word_table_seed"])
-    store = DocStore.from_lists(words, boxes, labels, pages, lambda w: table.get(w, [2]), torch.device(DEV), images=images)
+    store = DocStore.from_lists(words, boxes, labels, pages, lambda w: table.get(w, [2]), torch.device(DEV), images=images,
+                                derived=derived)
     prompts = prompts_for(packs["questions"])
     retr = Retriever({**BASE, "chunk_num": packs["k"]})
     for var in packs["variants"]:
@@ -157,8 +159,10 @@ def test_packed_inputs_match_reference_golden(golden_dir):
             assert packed.layout_labels.cpu().tolist() == var["layout_labels"]
 
 
-@pytest.mark.parametrize("s,reorder,sep", [(0, False, False), (3, False, True), (7, True, True), (200, True, False)])
-def test_packed_inputs_vs_oracle_c2_slice(s, reorder, sep):
+@pytest.mark.parametrize("derived", [True, False])
+@pytest.mark.parametrize("s,reorder,sep", [(0, False, False), (0, True, True), (3, False, True), (7, True, True),
+                                           (200, True, False)])
+def test_packed_inputs_vs_oracle_c2_slice(s, reorder, sep, derived):
     from rag_docvqa_b200.docstore import DocStore
     from rag_docvqa_b200.retriever import Retriever
     batch = synth.make_text_batch("C2", with_lists=True, docs=12, seed=55, dup_frac=0.0)
@@ -166,7 +170,7 @@ def test_packed_inputs_vs_oracle_c2_slice(s, reorder, sep):
     pages, images = batch["page_indices"], batch["images"]
     table = synth.make_tokens_for_words(words, seed=9)
     tok = lambda w: table.get(w, [2])
-    store = DocStore.from_lists(words, boxes, labels, pages, tok, torch.device(DEV), images=images)
+    store = DocStore.from_lists(words, boxes, labels, pages, tok, torch.device(DEV), images=images, derived=derived)
     questions = ["what is item %d about ?" % b for b in range(len(words))]
     prompts = prompts_for(questions)
     sep_ids = [2, 9] if sep else []

@@ -72,7 +72,7 @@ def test_c2_full(algo, tile_rows, normalised):
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("k", [1, 5, 10, 20, 64])
 def test_k_sweep_with_duplicates(k, algo):
-    sizes = [300, 17, 0, 64, 1, 1000]
+    sizes = [300, 17, 0, 64, 1, 1000, 3000, 4097, 8000]   # register (<=1024, <=4096), cached and L2 selection paths
     emb, q = synth.make_embeddings(sizes, 384, 31 + k, dup_frac=0.2)
     res = run_case(emb, q, k, algo=algo)
     check_against_oracle(res, emb, q, k)
