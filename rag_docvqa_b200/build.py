@@ -15,6 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librdv.so")
+HOSTLISTS_SRC = os.path.join(CSRC, "hostlists.c")
+HOSTLISTS = os.path.join(HERE, "_hostlists.so")      # CPython helper (host list building), plain gcc
 OBJ_DIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
@@ -67,7 +69,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if res.returncode != 0:
             sys.stderr.write(res.stdout)
             raise RuntimeError("link of librdv.so failed")
+    build_hostlists(force)
     return LIB
+
+
+def build_hostlists(force: bool = False) -> str:
+    """The CPython helper that builds the reference's nested-list outputs (csrc/hostlists.c)."""
+    import sysconfig
+    if force or _stale(HOSTLISTS, [HOSTLISTS_SRC]):
+        cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+        if not cc:
+            raise RuntimeError("no C compiler for _hostlists.so")
+        cmd = [cc, "-O2", "-shared", "-fPIC", "-Wall", "-I", sysconfig.get_paths()["include"], HOSTLISTS_SRC, "-o", HOSTLISTS]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout)
+            raise RuntimeError("build of _hostlists.so failed")
+    return HOSTLISTS
 
 
 if __name__ == "__main__":

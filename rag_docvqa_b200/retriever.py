@@ -27,6 +27,11 @@ import torch
 
 from . import functional as F
 
+try:                                   # C helper for the nested-list view (csrc/hostlists.c); same semantics as
+    from . import _hostlists           # the Python walk below, which stays as the general path and the spec
+except ImportError:                    # pragma: no cover - built by rag_docvqa_b200.build
+    _hostlists = None
+
 _LAYOUT_MAP_4 = {0: "title", 1: "text", 2: "figure", 3: "table"}   # src/_modules.py:308-313, 636-641
 
 
@@ -103,11 +108,15 @@ def _lazy_crop_class():
         behaves exactly like the eager `page.crop(rect)` of reference src/_modules.py:2119."""
 
         def __init__(self, page, rect):
-            super().__init__()
-            self._page, self._rect = page, tuple(int(v) for v in rect)
+            # the fields Image.__init__ sets, written once (this constructor runs once per retrieved chunk)
+            self._im = None
             self._mode = page.mode
-            self._size = (self._rect[2] - self._rect[0], self._rect[3] - self._rect[1])
-            self.info = dict(page.info)
+            self._size = (rect[2] - rect[0], rect[3] - rect[1])
+            self.palette = None
+            self.info = dict(page.info) if page.info else {}
+            self.readonly = 0
+            self._exif = None
+            self._page, self._rect = page, rect
 
         def load(self):
             if self._im is None and self._page is not None:
@@ -125,7 +134,11 @@ def lazy_crop(page, rect):
     global _LazyCrop
     if _LazyCrop is None:
         _LazyCrop = _lazy_crop_class()
-    return _LazyCrop(page, rect)
+    return _LazyCrop(page, tuple(rect))
+
+
+def _eager_crop(page, rect):
+    return page.crop(rect)
 
 
 class Retriever(StatComponent):
@@ -155,6 +168,9 @@ class Retriever(StatComponent):
                    layout_labels_chunks, images, page_indices):
         s = self.include_surroundings
         bs = len(hits)
+        if s == 0 and not self.reorder_chunks and _hostlists is not None:
+            return _hostlists.gather_s0(hits, words_text_chunks, words_box_chunks, layout_labels_chunks, images,
+                                        page_indices, lazy_crop if self.lazy_patches else _eager_crop)
         out_text, out_bbox, out_labels, out_words, out_boxes, out_wlabels, out_patches, out_pages = (
             [], [], [], [], [], [], [], [])
         for b in range(bs):
