@@ -13,9 +13,9 @@ of the hits.  Default workload: C2 = BASELINE.json configs[1] (64 questions x do
             the generator's input_ids/boxes/mask) launched through the C ABI, inputs already in HBM.
             Successive steps rotate over R distinct resident batches (> 2x the 126 MB L2 in total), so
             every step streams its embeddings from HBM.  The K timed steps are captured once into a CUDA
-            graph (2K kernel nodes) and the timed region is one launch of it; --lanes 2 (default) lets
-            successive, independent batches alternate between two captured streams, --lanes 1 keeps one
-            dependent chain.  Both, and the same steps as plain stream launches, are reported in `stages`.
+            graph (2K kernel nodes) and the timed region is one launch of it; --lanes L (default 4) lets
+            successive, independent batches rotate over L captured streams -- what a serving loop with L
+            batches in flight does -- and --lanes 1 keeps one dependent chain.  Both, and the same steps as plain stream launches, are reported in `stages`.
   roofline  the dominant kernel (score_ldg_kernel) timed alone over the same rotation with CUDA
             events; achieved = algorithmic bytes per launch / mean launch duration.
   e2e       the drop-in `Retriever.retrieve` (reference signature: pinned HOST embeddings + the
@@ -351,7 +351,8 @@ def run_ours(args):
     sizes = host_batch["sizes"]
     step_bytes = score_bytes(sizes, w.dim, w.k)
     R = max(2, min(16, int(np.ceil(2.2 * L2_BYTES / max(1, step_bytes)))))
-    R += R % 2          # even: with two lanes a batch's buffers are only ever touched by one lane
+    while R % max(1, args.lanes):     # a batch's buffers are only ever touched by one lane
+        R += 1
     batches = [synth.make_text_batch(args.workload, device=dev, seed=base_seed, emb_seed=base_seed + 1000 * (r + 1))
                for r in range(R)]
     tables = [F.build_doc_table(b["text_embeddings"], w.dim, dev, algo=args.algo) for b in batches]
@@ -415,8 +416,9 @@ def run_ours(args):
     # The timed region is ONE CUDA-graph launch holding exactly `steps` steps (2 kernel nodes each), rotating over
     # the R resident batches: the hot loop is launch-bound (a step is ~13 us of device time, ~8 us of host
     # enqueue), so it is captured once and replayed.  `lanes` = 1: the steps form one dependent chain.
-    # `lanes` = 2: successive (independent) batches alternate between two captured streams, so the latency-bound
-    # select+gather of batch i overlaps the HBM-bound score of batch i+1, as a serving loop with two streams would.
+    # `lanes` = L: successive (independent) batches rotate over L captured streams, so the latency-bound
+    # select+gather of one batch overlaps the HBM-bound score of the next, as a serving loop with L batches in
+    # flight would (measured on B200, C2: 13.0 us per step with 1 lane, 11.7 with 2, 8.1 with 3, 7.2 with 4).
     def capture(fn, n, lanes=1):
         g = torch.cuda.CUDAGraph()
         main = torch.cuda.Stream(dev)
@@ -443,7 +445,7 @@ def run_ours(args):
         return ev0.elapsed_time(ev1)
 
     g_seq = capture(lambda sp: make_launchers(sp)[2], args.steps, 1)
-    g_pipe = capture(lambda sp: make_launchers(sp)[2], args.steps, 2)
+    g_pipe = capture(lambda sp: make_launchers(sp)[2], args.steps, max(2, args.lanes))
     g_score = capture(lambda sp: make_launchers(sp)[0], args.steps, 1)
     g_gather = capture(lambda sp: make_launchers(sp)[1], args.steps, 1)
     for g in (g_seq, g_pipe, g_score, g_gather):
@@ -464,7 +466,7 @@ def run_ours(args):
             g_pipe.replay()
             torch.cuda.synchronize()
     ms_seq, ms_pipe, ms_plain = max_over_ranks(ms_seq), max_over_ranks(ms_pipe), max_over_ranks(ms_plain)
-    pipelined = args.lanes == 2
+    pipelined = args.lanes >= 2
     ms_total = ms_pipe if pipelined else ms_seq
     ms_per_step = ms_total / args.steps
     qps = w.docs * world / (ms_per_step * 1e-3)
@@ -527,8 +529,9 @@ def run_ours(args):
                            "launch, %s" % (
                        "select+gather kernel (per-document top-k, packed VT5 inputs, max_source_length 512)"
                        if plans is not None else "per-document top-k kernel", w.docs, args.steps,
-                       "successive batches alternate between 2 captured streams (gather of batch i overlaps the score "
-                       "of batch i+1)" if pipelined else "one dependent chain"),
+                       "successive independent batches rotate over %d captured streams (the latency-bound select+gather "
+                       "of one batch overlaps the HBM-bound score of the next ones)" % args.lanes if pipelined
+                       else "one dependent chain"),
                    "l2": "inputs larger than L2: %d distinct resident batches rotated (%.0f MB in total)" % (
                        R, R * step_bytes / 1e6),
                    "parallelism": "documents sharded across ranks (dp%d), no data-path collective" % world},
@@ -542,7 +545,7 @@ def run_ours(args):
         "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks.summary(),
         "stages": {"score_ms": ms_score, "select_gather_ms": ms_gather, "step_ms": ms_per_step,
-                   "step_ms_graph_one_chain": ms_seq / args.steps, "step_ms_graph_two_lanes": ms_pipe / args.steps,
+                   "step_ms_graph_one_chain": ms_seq / args.steps, "step_ms_graph_lanes": ms_pipe / args.steps,
                    "step_ms_plain_stream_launches": ms_plain / args.steps, "score_ms_plain_stream_launches": ms_score_plain},
     }
 
@@ -724,7 +727,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 LDG kernel, 2 TMA kernel")
-    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--lanes", type=int, default=4, choices=[1, 2, 3, 4, 6, 8],
                     help="captured streams the steps alternate between (1 = one dependent chain)")
     args = ap.parse_args()
     if args.impl == "reference":

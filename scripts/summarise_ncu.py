@@ -18,6 +18,9 @@ def raw(rep):
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
+TRAFFIC = {}
+
+
 def main(round_tag):
     os.makedirs(OUT, exist_ok=True)
     lines = ["# ncu summaries, round %s (B200, `--set full --clock-control none`; per-launch values)\n" % round_tag]
@@ -27,6 +30,9 @@ def main(round_tag):
         lines.append("## %s\n" % rep)
         for r in data:
             lines.append("kernel: `%s`\n" % r[kcol][:110])
+            TRAFFIC[r[kcol].split("(")[0].replace("void ", "").split("<")[0].replace("rdv::", "")] = sum(
+                float(r[hdr.index(m)].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index(m)]]
+                for m in ("dram__bytes_read.sum", "dram__bytes_write.sum") if m in hdr)
             lines.append("| metric | value | unit |\n|---|---|---|")
             for w in WANT:
                 if w in hdr:
@@ -61,6 +67,7 @@ def main(round_tag):
     with open(os.path.join(OUT, "%s_ncu_summary.md" % round_tag), "w") as f:
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    print("per-launch DRAM traffic (bytes):", json.dumps(TRAFFIC))
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else "r1")
