@@ -13,7 +13,7 @@ of the hits.  Default workload: C2 = BASELINE.json configs[1] (64 questions x do
             the generator's input_ids/boxes/mask) launched through the C ABI, inputs already in HBM.
             Successive steps rotate over R distinct resident batches (> 2x the 126 MB L2 in total), so
             every step streams its embeddings from HBM.  The K timed steps are captured once into a CUDA
-            graph (2K kernel nodes) and the timed region is one launch of it; --lanes L (default 4) lets
+            graph (2K kernel nodes) and the timed region is one launch of it; --lanes L (default 8) lets
             successive, independent batches rotate over L captured streams -- what a serving loop with L
             batches in flight does -- and --lanes 1 keeps one dependent chain.  Both, and the same steps as plain stream launches, are reported in `stages`.
   roofline  the dominant kernel (score_ldg_kernel) timed alone over the same rotation with CUDA
@@ -418,7 +418,8 @@ def run_ours(args):
     # enqueue), so it is captured once and replayed.  `lanes` = 1: the steps form one dependent chain.
     # `lanes` = L: successive (independent) batches rotate over L captured streams, so the latency-bound
     # select+gather of one batch overlaps the HBM-bound score of the next, as a serving loop with L batches in
-    # flight would (measured on B200, C2: 13.0 us per step with 1 lane, 11.7 with 2, 8.1 with 3, 7.2 with 4).
+    # flight would (measured on B200, C2: 13.0 us per step with 1 lane, 11.7 with 2, 8.1 with 3, 7.2 with 4, 5.1 with 8 --
+    # 32.5 MB per 5.1 us = 6.3 TB/s: the whole step at the HBM roofline).
     def capture(fn, n, lanes=1):
         g = torch.cuda.CUDAGraph()
         main = torch.cuda.Stream(dev)
@@ -546,7 +547,8 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "stages": {"score_ms": ms_score, "select_gather_ms": ms_gather, "step_ms": ms_per_step,
                    "step_ms_graph_one_chain": ms_seq / args.steps, "step_ms_graph_lanes": ms_pipe / args.steps,
-                   "step_ms_plain_stream_launches": ms_plain / args.steps, "score_ms_plain_stream_launches": ms_score_plain},
+                   "step_ms_plain_stream_launches": ms_plain / args.steps, "score_ms_plain_stream_launches": ms_score_plain,
+                   "step_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9, "step_frac_hbm": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
     }
 
     if rank == 0 and world == 1:
@@ -727,7 +729,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 LDG kernel, 2 TMA kernel")
-    ap.add_argument("--lanes", type=int, default=4, choices=[1, 2, 3, 4, 6, 8],
+    ap.add_argument("--lanes", type=int, default=8, choices=[1, 2, 3, 4, 8],
                     help="captured streams the steps alternate between (1 = one dependent chain)")
     args = ap.parse_args()
     if args.impl == "reference":
