@@ -269,10 +269,17 @@ def stage_extras(dev, hbm_peak, steps):
     patches, q = synth.make_strip_batch(1, [50], 2048, 768, 3, device=dev)
     flops = 2.0 * 50 * 2048 * 2048 * 768
     for _ in range(2):
-        F.late_interaction(q[0:1], patches[0])
-    ms = timed_loop(lambda i: F.late_interaction(q[0:1], patches[0]), 5, sync) / 5
+        F.late_interaction(q[0:1], patches[0], mode="ffma")
+    ms = timed_loop(lambda i: F.late_interaction(q[0:1], patches[0], mode="ffma"), 5, sync) / 5
     out["maxsim_f32"] = {"shape": "50 strips x 2048 x 768 vs 2048 x 768", "ms": ms, "TFLOPs": flops / ms / 1e9,
                          "bound": "CUDA-core FFMA (fp32 parity mode)", "questions_per_s": 1e3 / ms}
+    # the same contraction at fp32 grade on the tensor pipe: 3 tf32 products per fp32 product (split included)
+    for _ in range(2):
+        F.late_interaction(q[0:1], patches[0], mode="tf32x3")
+    ms = timed_loop(lambda i: F.late_interaction(q[0:1], patches[0], mode="tf32x3"), 10, sync) / 10
+    out["maxsim_tf32x3_tc"] = {"shape": "50 strips x 2048 x 768 vs 2048 x 768", "ms": ms, "fp32_equivalent_TFLOPs": flops / ms / 1e9,
+                               "tf32_TFLOPs_issued": 3 * flops / ms / 1e9, "bound": "tensor (tcgen05 kind::tf32, 3 products per fp32 product)",
+                               "questions_per_s": 1e3 / ms, "includes": "normalise + hi/lo split of Q and P"}
     # the same document through the bf16 tcgen05 mode (normalise + cast included)
     _, tf_peak, _ = measured_peaks()
     for _ in range(2):

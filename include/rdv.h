@@ -307,6 +307,26 @@ RDV_API int rdv_corpus_score_topk_bf16(const void* d_e_bf16, const float* d_e_in
 RDV_API int rdv_maxsim_bf16_tc(const void* d_qn_bf16, const void* d_pn_bf16, int32_t n, int32_t Lq, int32_t Lp,
                                int32_t d, float* d_partial, float* d_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fp32-grade MaxSim on the tensor pipe (3xTF32): the parity mode of late_interaction (src/utils.py:442-458)
+ * at tensor-core speed.  Every fp32 value is split exactly into hi = tf32(x) and lo = x - hi;
+ *     q . p = q_hi.p_hi + q_hi.p_lo + q_lo.p_hi   (+ q_lo.p_lo ~ 2^-22 |q||p|, dropped)
+ * runs as three tcgen05 kind::tf32 MMAs accumulating in fp32 in TMEM (the dominant product in its own
+ * accumulator).  Measured against float64 on B200: every cosine comes out ~d * 2.1e-9 relative low (1.6e-6 at
+ * d = 768, 4.4e-6 at d = 2048: the tensor core's accumulator rounds toward zero at each step), inside the
+ * north_star bar of 1e-5 relative; rdv_maxsim_f32 (~1e-7) is the strict fp32 alternative.
+ *   rdv_rows_split_tf32   x (rows, d) fp32 -> hi, lo (rows, d) fp32; normalise != 0: x is first divided by
+ *                         max(||x||, 1e-12) (F.normalize, src/utils.py:445-446).
+ *   rdv_maxsim_tf32x3_tc  d_q_hi/lo (Lq, d), d_p_hi/lo (n, Lp, d): the NORMALISED, split operands;
+ *                         d_partial: workspace of n * ceil(Lq / rdv_tc_tile_m()) floats; d_out (n).
+ * Requirements: d % 4 == 0.
+ * ------------------------------------------------------------------------------------------- */
+RDV_API int rdv_rows_split_tf32(const float* d_x, int64_t rows, int32_t d, int32_t normalise, float* d_hi, float* d_lo,
+                                void* stream);
+RDV_API int rdv_maxsim_tf32x3_tc(const float* d_q_hi, const float* d_q_lo, const float* d_p_hi, const float* d_p_lo,
+                                 int32_t n, int32_t Lq, int32_t Lp, int32_t d, float* d_partial, float* d_out,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -67,6 +67,9 @@ SIGNATURES = {
                                              c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_maxsim_bf16_tc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                      c_void_p]),
+    "rdv_rows_split_tf32": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "rdv_maxsim_tf32x3_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p, c_void_p, c_void_p]),
     "rdv_gather_vt5_inputs": (c_int32, [POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
 }
 

@@ -51,18 +51,23 @@ def test_mean_pooling_weighted_mask_and_normalise():
     np.testing.assert_allclose(gotn.cpu().numpy(), refn.numpy(), rtol=1e-5, atol=1e-6)
 
 
-def test_late_interaction_golden(golden_dir):
+MAXSIM_MODES = ["ffma", "tf32x3", "auto"]      # CUDA-core fp32, 3xTF32 on the tensor pipe, the shipped default
+
+
+@pytest.mark.parametrize("mode", MAXSIM_MODES)
+def test_late_interaction_golden(golden_dir, mode):
     from rag_docvqa_b200 import functional as F
     z = np.load(os.path.join(golden_dir, "late_interaction.npz"))
     q = torch.from_numpy(z["q"]).to(DEV)
     for b, (pk, sk) in enumerate((("p0", "s0"), ("p1", "s1"))):
-        got = F.late_interaction(q[b:b + 1], torch.from_numpy(z[pk]).to(DEV))
+        got = F.late_interaction(q[b:b + 1], torch.from_numpy(z[pk]).to(DEV), mode=mode)
         np.testing.assert_allclose(got.cpu().numpy(), z[sk], rtol=MAXSIM_RTOL)
 
 
+@pytest.mark.parametrize("mode", MAXSIM_MODES)
 @pytest.mark.parametrize("n,Lq,Lp,d", [(3, 128, 128, 64), (5, 200, 77, 96), (2, 2048, 2048, 768), (7, 1, 300, 768),
-                                       (4, 130, 1, 36), (1, 257, 513, 20)])
-def test_late_interaction_shapes(n, Lq, Lp, d):
+                                       (4, 130, 1, 36), (1, 257, 513, 20), (50, 300, 700, 768), (3, 64, 64, 2048)])
+def test_late_interaction_shapes(n, Lq, Lp, d, mode):
     from rag_docvqa_b200 import functional as F
     g = torch.Generator().manual_seed(n * 1000 + Lq)
     q = torch.randn(1, Lq, d, generator=g)
@@ -70,10 +75,31 @@ def test_late_interaction_shapes(n, Lq, Lp, d):
     p[0, 0] = 0.0                                               # zero token: F.normalize eps path
     ref64 = R.late_interaction_f64(q, p).numpy()
     ref32 = R.late_interaction(q, p).numpy()
-    got = F.late_interaction(q.to(DEV), p.to(DEV)).cpu().numpy()
+    got = F.late_interaction(q.to(DEV), p.to(DEV), mode=mode).cpu().numpy()
     np.testing.assert_allclose(got, ref64, rtol=MAXSIM_RTOL)
-    # no further from the float64 truth than torch's own fp32 result is (x4 slack)
-    assert np.abs(got - ref64).max() <= 4 * max(np.abs(ref32 - ref64).max(), 1e-6 * np.abs(ref64).max())
+    if mode == "ffma":
+        # no further from the float64 truth than torch's own fp32 result is (x4 slack)
+        assert np.abs(got - ref64).max() <= 4 * max(np.abs(ref32 - ref64).max(), 1e-6 * np.abs(ref64).max())
+    else:
+        # 3xTF32: exact products, but the tensor core's accumulator rounds toward zero -> ~d * 2.1e-9 relative low
+        # (stated for sums of positive maxima; with Lp == 1 the terms change sign and cancel, only the 1e-5 bar applies)
+        if Lp >= 64:
+            assert np.abs(got / ref64 - 1).max() <= max(1e-6, d * 3.2e-9)
+
+
+def test_split_tf32_is_exact():
+    """hi + lo == x bit for bit, hi has a 10-bit mantissa, |lo| <= 2^-11 |x| (the premise of the 3xTF32 mode)."""
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(37, 100, generator=g) * torch.logspace(-20, 20, 37).unsqueeze(1)
+    hi, lo = F.split_tf32(x.to(DEV))
+    hi, lo = hi.cpu(), lo.cpu()
+    assert torch.equal(hi + lo, x)
+    assert (hi.view(torch.int32) & 0x1FFF).eq(0).all()
+    assert (lo.abs() <= x.abs() * 2.0 ** -11).all()
+    hn, ln = F.split_tf32(x.to(DEV), normalise=True)
+    ref = torch.nn.functional.normalize(x, p=2, dim=-1)
+    np.testing.assert_allclose((hn.cpu().double() + ln.cpu().double()).numpy(), ref.double().numpy(), rtol=1e-6, atol=1e-30)
 
 
 def test_topk_segments_matches_oracle():
