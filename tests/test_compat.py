@@ -24,7 +24,9 @@ def test_signatures_match_reference_call_sites():
     assert params(VisualRetriever.retrieve) == ["patch_embeddings", "question_embeddings", "patches_flatten_indices",
                                                 "patches_matrix_list", "patches_xyxy", "images"]
     assert params(F.mean_pooling)[:2] == ["embs", "attention_mask"]
-    assert params(F.late_interaction) == ["query", "patches"]
+    assert params(F.late_interaction)[:2] == ["query", "patches"]      # + optional `mode` (default keeps the contract)
+    assert all(p.default is not inspect.Parameter.empty
+               for p in list(inspect.signature(F.late_interaction).parameters.values())[2:])
 
 
 @pytest.mark.skipif(not reference_available(), reason="reference tree not mounted (GPU box)")
