@@ -172,6 +172,8 @@ def run_reference(args):
         return
     if args.workload == "C5":
         return run_reference_corpus(args)
+    if args.workload == "C4":
+        return run_reference_visual(args)
     w = synth.WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -227,6 +229,33 @@ def run_reference_corpus(args):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": "oracle corpus_scores + torch.topk on a 1/64 row slice (%d rows) per step, time x64" % n_cpu},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_reference_visual(args):
+    """CPU arm of the visual path: the oracle's late_interaction (the reference's torch ops) on 5 of the 50 strips
+    of one question per step, time scaled x10."""
+    from oracle import ref_restated as R
+    from rag_docvqa_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    strips, L, d, n_cpu = 50, 2048, 768, 5
+    patches, q = synth.make_strip_batch(1, [n_cpu], L, d, synth_seed(4))
+    for _ in range(max(1, min(args.warmup, 2))):
+        R.late_interaction(q[0:1], patches[0])
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.late_interaction(q[0:1], patches[0])
+    dt = (time.perf_counter() - t0) / steps * (strips / n_cpu)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": 1.0 / dt, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4: questions x %d strips x (%d x %d) tokens, MaxSim late interaction" % (strips, L, d)},
+        "cpu_baseline": {"value": 1.0 / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": "oracle late_interaction on %d of %d strips of one question per step, time x%d" % (n_cpu, strips, strips // n_cpu)},
+        "e2e": {"value": 1.0 / dt, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
@@ -719,6 +748,129 @@ def run_corpus(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# visual path (BASELINE.json configs[3]): MaxSim late interaction of question tokens against page strips
+# ------------------------------------------------------------------------------------------------
+def run_visual(args):
+    """C4: B documents x 50 strips x (2048 x 768) un-pooled encoder tokens, one (2048 x 768) question each
+    (reference src/_modules.py:2191-2205 + src/utils.py:442-458, then torch.topk :2408).  A step = the MaxSim
+    scores of one batch of B questions + the per-document top-k."""
+    from rag_docvqa_b200 import functional as F
+    from rag_docvqa_b200 import synth
+    from rag_docvqa_b200.retriever import VisualRetriever
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _, tf_peak, peak_kind = measured_peaks()
+    B, strips, L, d, k = args.visual_docs, 50, 2048, 768, 5
+    patches, q = synth.make_strip_batch(B, [strips] * B, L, d, synth_seed(4) + 1000 * rank, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def step(i):
+        sims = [F.late_interaction(q[b:b + 1], patches[b]) for b in range(B)]
+        return F.topk_segments(sims, k)
+
+    # the dominant kernel alone: operands already normalised and split
+    qs = [F.split_tf32(q[b], normalise=True) for b in range(B)]
+    ps = [F.split_tf32(patches[b], normalise=True) for b in range(B)]
+    from rag_docvqa_b200 import _lib
+    tiles = (L + 127) // 128
+    partial = torch.empty(strips * tiles, device=dev)
+    out = torch.empty(strips, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def kernel_only(i):
+        b = i % B
+        _lib.check(_lib.lib.rdv_maxsim_tf32x3_tc(qs[b][0].data_ptr(), qs[b][1].data_ptr(), ps[b][0].data_ptr(), ps[b][1].data_ptr(),
+                                                 strips, L, L, d, partial.data_ptr(), out.data_ptr(), stream))
+    warmup = max(3, args.warmup)
+    steps = max(1, min(args.steps, 20))
+    for i in range(warmup):
+        step(i)
+        kernel_only(i)
+    with ClockSampler(local) as clocks:
+        ms_total = timed_loop(step, steps, barrier)
+        ms_kernel = timed_loop(kernel_only, steps * B, barrier) / (steps * B)
+    ms_per_step = max_over_ranks(ms_total) / steps
+    ms_kernel = max_over_ranks(ms_kernel)
+    del qs, ps
+    flops = 2.0 * strips * L * L * d                          # fp32 contraction of one question
+    ceiling = tf_peak / 2 / 3                                  # tf32 = half the bf16 rate; 3 tf32 products per fp32 product
+
+    # e2e: the drop-in VisualRetriever.retrieve with pinned HOST token matrices, PIL pages in, crops + page ids out
+    from PIL import Image
+    pages = [[Image.new("RGB", (212, 275), (b * 7 % 255, g * 5 % 255, 0)) for g in range(strips)] for b in range(B)]
+    flat = [np.arange(strips, dtype=np.int64) for _ in range(B)]
+    mats = [[[[pages[b][g]]] for g in range(strips)] for b in range(B)]
+    xyxy = [[[[0, 0, 212, 275]] for g in range(strips)] for b in range(B)]
+    host_p = [x.cpu().pin_memory() for x in patches]
+    host_q = q.cpu().pin_memory()
+    vr = VisualRetriever({"chunk_num": k, "include_surroundings": 0, "chunk_mode": "horizontal", "device": str(dev)})
+
+    def e2e_step():
+        return vr.retrieve(host_p, host_q, flat, mats, xyxy, pages)
+    e2e_step()
+    barrier()
+    e2e_steps = 3
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = max_over_ranks(time.perf_counter() - t0)
+    h2d = sum(x.numel() * 4 for x in host_p) + host_q.numel() * 4
+    line = {
+        "metric": METRIC, "value": B * world / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32x3 (fp32 operands split exactly into two tf32 parts, fp32 accumulation)", "data": "synthetic",
+        "config": {"workload": "C4: %d questions x %d strips x (%d x %d) tokens, MaxSim late interaction, top-k=%d" % (B, strips, L, d, k),
+                   "step": "per document: F.normalize + tf32 hi/lo split of question and strips, tcgen05 kind::tf32 MaxSim, "
+                           "strip sums; then one segmented top-k kernel for the batch",
+                   "l2": "inputs larger than L2 (%.0f MB of strip tokens per document)" % (strips * L * d * 4 / 1e6),
+                   "parallelism": "documents sharded across ranks (dp%d), no data-path collective" % world},
+        "roofline": {"bound": "tensor", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": ceiling, "unit": "TFLOP/s",
+                     "frac": flops / (ms_kernel * 1e-3) / 1e12 / ceiling, "traffic": None,
+                     "peak_kind": peak_kind + " bf16 burst / 2 (tf32 rate) / 3 (products per fp32 product)",
+                     "kernel": "maxsim_tf32x3_kernel", "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_kernel},
+        "e2e": {"value": B * world * e2e_steps / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": B * (k + 1) * 4, "ms_per_step": e2e_dt / e2e_steps * 1e3,
+                "api": "rag_docvqa_b200.retriever.VisualRetriever.retrieve (reference signature; pinned host token matrices and "
+                       "PIL pages in; crops + page ids out)"},
+        "gpu_launches": steps * (B * 5 + 1),
+        "clocks": clocks.summary(),
+    }
+    if rank == 0 and world == 1:
+        from oracle import ref_restated as R
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        n_cpu = 5
+        qc, pc = q[0:1].cpu(), patches[0][:n_cpu].cpu()
+        best, reps = time_cpu(lambda: R.late_interaction(qc, pc), min(args.cpu_seconds, 10.0), min_reps=1)
+        line["cpu_baseline"] = {"value": 1.0 / (best * strips / n_cpu), "unit": "queries/s", "cores": threads, "kind": "port",
+                                "sample": "oracle late_interaction (torch CPU: F.normalize + bmm + max + sum) on %d of the %d strips "
+                                          "of one question, time scaled x%d, best of %d reps" % (n_cpu, strips, strips // n_cpu, reps)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def synth_seed(config_id):
     from rag_docvqa_b200 import synth
     return synth.SEED_BASE + config_id
@@ -730,7 +882,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C5"])
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--visual-docs", type=int, default=8)
     ap.add_argument("--corpus-rows", type=int, default=10_000_000)
     ap.add_argument("--corpus-queries", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -743,6 +896,8 @@ def main():
         run_reference(args)
     elif args.workload == "C5":
         run_corpus(args)
+    elif args.workload == "C4":
+        run_visual(args)
     else:
         run_ours(args)
 
