@@ -62,6 +62,41 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return d;
 }
 
+// ---- CTA-pair (cta_group::2) forms ---------------------------------------------------------------
+// In a 2-CTA cluster the shared::cluster address of CTA 0's copy of a shared variable is the local shared
+// address with the peer bit (bit 24) cleared.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by BOTH CTAs of the pair; the bytes complete on CTA 0's mbarrier
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(s32(dst)), "l"(map), "r"(s32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// arrives on `bar` (same offset) in both CTAs when all prior MMAs of the issuing thread retire
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(s32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on CTA 0's copy of `bar` from either CTA
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s32(bar) & kPeerBitMask) : "memory");
+}
+// D[256 x N] (128 rows in each CTA's TMEM) += A[256 x K] * B[N x K]^T; each CTA holds its 128 rows of A and its
+// N/2 rows of B in shared memory at the same offsets.  Issued by one thread of CTA 0.
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+
 // kind::tf32 twin of tc_mma_bf16: fp32 operands in shared memory, read as tf32 (low 13 mantissa bits ignored)
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"

@@ -11,6 +11,9 @@
 //   A rows = questions / question tokens  -> TMEM lanes  -> one epilogue THREAD per row, so the per-row
 //     reduction over B rows (top-k / max) is register-resident and needs no cross-thread traffic;
 //   B rows = corpus chunks / strip tokens -> TMEM columns.
+// Two shapes of the same kernel (template NCTA): one CTA per 128 x 256 tile, or a CTA PAIR (cluster of 2,
+// tcgen05 cta_group::2) per 256 x 256 tile -- each CTA keeps its own 128 A rows and half of the B rows in
+// shared memory, CTA 0 issues the MMAs for both, commits are multicast to both CTAs' barriers.
 // Warp roles (320 threads): warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier
 // ring of 48 KB stages), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16,
 // kind::f16 bf16 x bf16 -> fp32), warps 2-9 = epilogue (tcgen05.ld 32x32b.x32; two warps per TMEM lane
@@ -19,14 +22,24 @@
 #include "tc_common.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace rdv {
 namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 4;
-constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kABytes = BM * BK * 2;
 constexpr int kThreads = 320;                // TMA warp + MMA warp + 8 epilogue warps
+// NCTA = 1: one CTA per tile, stage = A (16 KB) + B (32 KB), 4 stages.
+// NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares each B tile: D is 256 x 256, every CTA holds its
+//           own 128 A rows and HALF of the B rows (16 KB), so a stage is 32 KB and 6 fit -- a third less
+//           shared-memory fill and read per SM and a deeper TMA look-ahead.
+template <int NCTA> struct Cfg {
+    static constexpr int kBRows = BN / NCTA;                 // B rows this CTA loads per stage
+    static constexpr int kBBytes = kBRows * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = NCTA == 1 ? 4 : 6;
+};
 constexpr int kTopK = 16;                 // register-resident candidates per question and work item
 constexpr uint32_t kTmemCols = 512;       // 2 accumulators x 256 fp32 columns
 
@@ -47,14 +60,19 @@ struct Params {
     float* partial;         // (n_groups = strips, n_a)
 };
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128*NCTA, N=256
+template <int NCTA> struct IdescBf16 {
+    static constexpr uint32_t value = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
+};
 
 struct Item { int a_tile, group, t0, t1, z; };
-__device__ __forceinline__ Item decode_item(const Params& p, int item) {
+// work item -> (A tile, row chunk).  With CTA pairs an item covers NCTA consecutive A tiles, one per CTA rank.
+template <int NCTA>
+__device__ __forceinline__ Item decode_item(const Params& p, int item, int rank) {
     Item it;
-    it.group = item / p.n_a;
-    it.a_tile = item - it.group * p.n_a;
+    const int n_ap = (p.n_a + NCTA - 1) / NCTA;
+    it.group = item / n_ap;
+    it.a_tile = (item - it.group * n_ap) * NCTA + rank;
     if (p.mode == kCorpus) {
         it.t0 = (int)((long long)it.group * p.tiles_total / p.n_groups);
         it.t1 = (int)((long long)(it.group + 1) * p.tiles_total / p.n_groups);
@@ -65,8 +83,12 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
     return it;
 }
 
+template <int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    using C = Cfg<NCTA>;
+    constexpr int kStages = C::kStages, kStageBytes = C::kStageBytes;
+    constexpr uint32_t kIdesc = IdescBf16<NCTA>::value;
     extern __shared__ __align__(1024) unsigned char smem_unaligned[];
     // 128-byte swizzle atoms repeat every 1024 bytes: the operand ring must start on a 1024-byte boundary
     unsigned char* smem = smem_unaligned + ((1024u - (s32(smem_unaligned) & 1023u)) & 1023u);
@@ -78,19 +100,27 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     float* q_val = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = p.n_a * p.n_groups;
+    const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;                 // CTA within its pair
+    const int n_items = ((p.n_a + NCTA - 1) / NCTA) * p.n_groups;
+    const int first_item = blockIdx.x / NCTA, item_step = gridDim.x / NCTA;  // per pair
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 8 * NCTA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s_tmem_base)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if constexpr (NCTA == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s_tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s_tmem_base)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();      // the peer's barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
@@ -98,15 +128,23 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+            for (int item = first_item; item < n_items; item += item_step) {
+                const Item it = decode_item<NCTA>(p, item, rank);
                 for (int t = it.t0; t < it.t1; ++t) {
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(&s_empty[stage], phase ^ 1);
                         unsigned char* sa = smem + (size_t)stage * kStageBytes;
-                        mbar_expect_tx(&s_full[stage], kStageBytes);
-                        tma_load_3d(sa, &map_a, &s_full[stage], kb * BK, it.a_tile * BM, 0);
-                        tma_load_3d(sa + kABytes, &map_b, &s_full[stage], kb * BK, t * BN, it.z);
+                        if constexpr (NCTA == 1) {
+                            mbar_expect_tx(&s_full[stage], kStageBytes);
+                            tma_load_3d(sa, &map_a, &s_full[stage], kb * BK, it.a_tile * BM, 0);
+                            tma_load_3d(sa + kABytes, &map_b, &s_full[stage], kb * BK, t * BN, it.z);
+                        } else {
+                            // both CTAs load their own A rows and their half of the B rows; all bytes complete on
+                            // CTA 0's barrier, which CTA 0 arms for the pair
+                            if (rank == 0) mbar_expect_tx(&s_full[stage], NCTA * kStageBytes);
+                            tma_load_3d_pair(sa, &map_a, &s_full[stage], kb * BK, it.a_tile * BM, 0);
+                            tma_load_3d_pair(sa + kABytes, &map_b, &s_full[stage], kb * BK, t * BN + rank * C::kBRows, it.z);
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -114,13 +152,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {                                    // CTA 0 issues for the pair
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+            for (int item = first_item; item < n_items; item += item_step) {
+                const Item it = decode_item<NCTA>(p, item, rank);
                 for (int t = it.t0; t < it.t1; ++t) {
-                    mbar_wait(&s_tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+                    mbar_wait(&s_tempty[acc], acc_phase ^ 1);          // epilogue(s) have drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -129,12 +167,17 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const uint32_t a_addr = s32(smem + (size_t)stage * kStageBytes);
                         const uint64_t da = smem_desc(a_addr), db = smem_desc(a_addr + kABytes);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)                 // 32 bytes (>>4 = 2) per K=16 step
-                            tc_mma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
-                        tc_commit(&s_empty[stage]);                       // frees the smem stage when the MMAs retire
+                        for (int k = 0; k < BK / 16; ++k) {               // 32 bytes (>>4 = 2) per K=16 step
+                            if constexpr (NCTA == 1)
+                                tc_mma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                            else
+                                tc_mma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                        }
+                        // frees the smem stage (in both CTAs) when the MMAs retire
+                        if constexpr (NCTA == 1) tc_commit(&s_empty[stage]); else tc_commit_pair(&s_empty[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(&s_tfull[acc]);                             // accumulator complete
+                    if constexpr (NCTA == 1) tc_commit(&s_tfull[acc]); else tc_commit_pair(&s_tfull[acc]);   // accumulator complete
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
@@ -148,17 +191,24 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int row_in_tile = quarter * 32 + lane;
         const int et = (warp - 2) * 32 + lane;                          // 0..255 among epilogue threads
         int acc = 0; uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const Item it = decode_item(p, item);
+        for (int item = first_item; item < n_items; item += item_step) {
+            const Item it = decode_item<NCTA>(p, item, rank);
             float vals[kTopK]; int idxs[kTopK];
 #pragma unroll
             for (int j = 0; j < kTopK; ++j) { vals[j] = -INFINITY; idxs[j] = -1; }
             float runmax = -INFINITY;
+            // inverse norms of the tile's 256 rows, one per epilogue thread; rows past the shard get NaN so they never
+            // compare greater.  The load for tile t+1 is issued before tile t is processed: it was 32 % of the
+            // epilogue's stall samples when it sat in front of the accumulator wait (profiles/).
+            auto load_inv = [&](int t) {
+                const int row = t * BN + et;
+                return row < p.b_rows ? __ldg(p.inv_norm + row) : __int_as_float(0x7fc00000);
+            };
+            float inv_next = (p.mode == kCorpus && it.t0 < it.t1) ? load_inv(it.t0) : 0.f;
             for (int t = it.t0; t < it.t1; ++t) {
                 if (p.mode == kCorpus) {
-                    // stage this tile's inverse norms; rows past the shard get NaN so they never compare greater
-                    const int row = t * BN + et;
-                    s_inv[acc][et] = row < p.b_rows ? p.inv_norm[row] : __int_as_float(0x7fc00000);
+                    s_inv[acc][et] = inv_next;
+                    if (t + 1 < it.t1) inv_next = load_inv(t + 1);
                 }
                 mbar_wait(&s_tfull[acc], acc_phase);
                 tc_fence_after();
@@ -221,14 +271,18 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_tempty[acc]);             // accumulator may be overwritten
+                if (lane == 0) {                                        // accumulator may be overwritten
+                    if constexpr (NCTA == 1) mbar_arrive(&s_tempty[acc]); else mbar_arrive_cta0(&s_tempty[acc]);
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             const int a_row = it.a_tile * BM + row_in_tile;
             if (p.mode == kCorpus) {
-                const size_t o = (((size_t)it.group * 2 + half) * ((size_t)p.n_a * BM) + (size_t)a_row) * kTopK;
+                if (it.a_tile < p.n_a) {                                // an odd tile count leaves the pair's second CTA idle
+                    const size_t o = (((size_t)it.group * 2 + half) * ((size_t)p.n_a * BM) + (size_t)a_row) * kTopK;
 #pragma unroll
-                for (int j = 0; j < kTopK; ++j) { p.part_val[o + j] = vals[j]; p.part_idx[o + j] = idxs[j]; }
+                    for (int j = 0; j < kTopK; ++j) { p.part_val[o + j] = vals[j]; p.part_idx[o + j] = idxs[j]; }
+                }
             } else {
                 // max over the two column halves of the same row, then the sum over the block's 128 rows
                 q_val[et] = runmax;
@@ -238,16 +292,21 @@ tc_score_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 v = warp_sum(v);
                 if (half == 0 && lane == 0) s_sum[warp - 2] = v;
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (et == 0) p.partial[(size_t)it.group * p.n_a + it.a_tile] = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
+                if (et == 0 && it.a_tile < p.n_a)
+                    p.partial[(size_t)it.group * p.n_a + it.a_tile] = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();      // nobody leaves while its peer may still touch its barriers / TMEM
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        if constexpr (NCTA == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
 
@@ -335,20 +394,46 @@ static int make_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows,
     return make_map_bytes(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, rows, z, box_rows);
 }
 
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+template <int NCTA>
+static int launch_n(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
     static bool attr_set = false;
-    const size_t smem = (size_t)kStages * kStageBytes + 1024 + 16 * 256 * 4;
+    const size_t smem = (size_t)Cfg<NCTA>::kStages * Cfg<NCTA>::kStageBytes + 1024 + 16 * 256 * 4;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_score_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_score_kernel)");
         attr_set = true;
     }
-    int grid = sm_count();
-    const int items = p.n_a * p.n_groups;
-    if (grid > items) grid = items;
-    tc_score_kernel<<<grid, kThreads, smem, stream>>>(ma, mb, p);
-    RDV_LAUNCH_CHECK("tc_score_kernel");
+    int grid = sm_count() / NCTA * NCTA;
+    const int items = ((p.n_a + NCTA - 1) / NCTA) * p.n_groups;
+    if (grid > items * NCTA) grid = items * NCTA;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = NCTA > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_score_kernel<NCTA>, ma, mb, p);
+    if (e != cudaSuccess) return cuda_fail(e, "tc_score_kernel");
     return RDV_OK;
+}
+
+// Which shape runs is a measured choice (B200, 1024 questions x 768-d bf16):
+//   short launches (1.25 M rows, 1.5 ms, clocks near max): pairs 1.29 vs 1.23 PFLOP/s; MaxSim 1.46 vs 1.43;
+//   sustained (10 M rows, 13 ms, `sw_power_cap` active):   pairs 72.2 k vs 80.6 k questions/s -- the pair kernel
+//   draws more power per clock (SM clocks settle at 1.19 vs 1.37 GHz), and under the 1 kW cap that decides.
+// So the single-CTA kernel is the default and RDV_TC_CTAS=2 in the environment selects CTA pairs (only when the
+// A tiles pair up: with an odd tile count the pair's second CTA would idle).
+static int tc_ctas(int n_a) {
+    const char* v = getenv("RDV_TC_CTAS");
+    return (v && v[0] == '2' && !(n_a & 1)) ? 2 : 1;
+}
+
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+    return tc_ctas(p.n_a) == 2 ? launch_n<2>(ma, mb, p, stream) : launch_n<1>(ma, mb, p, stream);
 }
 
 }  // namespace tc
@@ -419,7 +504,7 @@ extern "C" int rdv_corpus_score_topk_bf16(const void* d_e_bf16, const float* d_e
     CUtensorMap ma, mb;
     int rc = tc::make_map(&ma, d_q_bf16, d, n_questions, 1, tc::BM);
     if (rc) return rc;
-    rc = tc::make_map(&mb, d_e_bf16, d, n_rows, 1, tc::BN);
+    rc = tc::make_map(&mb, d_e_bf16, d, n_rows, 1, tc::BN / tc::tc_ctas(p.n_a));
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rc = tc::launch(ma, mb, p, s);
@@ -450,7 +535,7 @@ extern "C" int rdv_maxsim_bf16_tc(const void* d_qn_bf16, const void* d_pn_bf16, 
     CUtensorMap ma, mb;
     int rc = tc::make_map(&ma, d_qn_bf16, d, Lq, 1, tc::BM);
     if (rc) return rc;
-    rc = tc::make_map(&mb, d_pn_bf16, d, Lp, n, tc::BN);
+    rc = tc::make_map(&mb, d_pn_bf16, d, Lp, n, tc::BN / tc::tc_ctas(p.n_a));
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rc = tc::launch(ma, mb, p, s);

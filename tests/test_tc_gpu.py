@@ -14,6 +14,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=["1", "2"], autouse=True, ids=["one_cta", "cta_pair"])
+def tc_ctas(request, monkeypatch):
+    """Every test runs with the single-CTA kernel and with CTA pairs (tcgen05 cta_group::2; used when the
+    question tiles pair up).  librdv reads RDV_TC_CTAS at each launch."""
+    monkeypatch.setenv("RDV_TC_CTAS", request.param)
+
+
 def bf16_round(x):
     return x.to(torch.bfloat16).to(torch.float64)
 
@@ -25,7 +32,7 @@ def exact_scores_of_bf16_operands(E, Q):
 
 
 @pytest.mark.parametrize("n,d,Qn,k", [(256, 64, 128, 5), (1000, 128, 37, 10), (5000, 768, 300, 10), (70000, 384, 130, 16),
-                                      (300, 72, 5, 3)])
+                                      (300, 72, 5, 3), (20000, 768, 512, 10), (3000, 256, 1000, 4)])
 def test_corpus_topk_matches_exact_bf16_math(n, d, Qn, k):
     from rag_docvqa_b200.sharded import CorpusShard
     g = torch.Generator().manual_seed(n + d)
