@@ -103,6 +103,19 @@ RDV_API int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles
                                int32_t max_rows, float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
                                int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
 
+/* Host-side staging helpers (no kernel is launched): the per-batch bookkeeping of the caller, in C.
+ *   rdv_count_tiles      number of row tiles a ragged batch cuts into (sum of ceil(rows[b] / tile_rows)); -1 on bad input.
+ *   rdv_build_doc_table  fills HOST buffers h_row_off[B+1] and h_tiles[n_tiles] (n_tiles = rdv_count_tiles) from the
+ *                        B device pointers d_docs[b] (rows[b] x d fp32 each, NULL allowed when rows[b] == 0); the caller
+ *                        uploads them (one pinned copy) and passes the device copies to the score entry points.
+ *   rdv_upload_docs_f32  one cudaMemcpyAsync per document: HOST matrices h_docs[b] (rows[b] x d fp32) -> consecutive rows
+ *                        of the device buffer d_packed (sum rows x d).  Replaces B framework-level copies. */
+RDV_API int64_t rdv_count_tiles(const int64_t* rows, int32_t B, int32_t tile_rows);
+RDV_API int rdv_build_doc_table(const void* const* d_docs, const int64_t* rows, int32_t B, int32_t d, int32_t tile_rows,
+                                int64_t* h_row_off, rdv_tile_desc* h_tiles, int64_t n_tiles, int32_t* max_rows);
+RDV_API int rdv_upload_docs_f32(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, float* d_packed,
+                                void* stream);
+
 /* Scores only (the streaming half of rdv_score_topk_f32): writes d_sims.  Used when the selection runs
  * elsewhere (rdv_topk_segments_f32, or inside rdv_gather_vt5_inputs).  algo: RDV_SCORE_LDG or RDV_SCORE_TMA. */
 RDV_API int rdv_score_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -46,6 +46,10 @@ SIGNATURES = {
     "rdv_last_error": (c_char_p, []),
     "rdv_device_info": (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "rdv_score_plan": (c_int32, [c_int64, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32)]),
+    "rdv_count_tiles": (c_int64, [c_void_p, c_int32, c_int32]),
+    "rdv_build_doc_table": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64,
+                                      POINTER(c_int32)]),
+    "rdv_upload_docs_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "rdv_score_topk_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                      c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_score_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

@@ -20,6 +20,7 @@ Differences from the reference, all within north_star's contract:
 """
 from __future__ import annotations
 
+import gc
 from typing import Any, Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -181,8 +182,16 @@ class Retriever(StatComponent):
 
     def _score_topk(self, text_embeddings, question_embeddings) -> F.ScoreTopK:
         dev = question_embeddings.device if question_embeddings.is_cuda else self.device
+        q = _to_device(question_embeddings, dev)
+        if len(text_embeddings) and not any(e.is_cuda for e in text_embeddings):
+            # host documents: one packed device buffer, the per-document copies issued from C
+            if q.dim() != 2 or q.shape[0] != len(text_embeddings):
+                raise ValueError("question_embeddings must be (B, d) with B == len(text_embeddings)")
+            with torch.cuda.device(dev):
+                table = F.upload_doc_table(text_embeddings, q.shape[1], dev)
+                return F.score_topk_table(table, q, int(self.k))
         emb = [_to_device(e, dev) for e in text_embeddings]
-        return F.score_topk(emb, _to_device(question_embeddings, dev), int(self.k))
+        return F.score_topk(emb, q, int(self.k))
 
     # -- a7/a8/a9: host view of the hits ----------------------------------------------------------------
     def _hit_lists(self, hits: Sequence[Sequence[int]], words_text_chunks, words_box_chunks,
@@ -302,7 +311,26 @@ class Retriever(StatComponent):
                  words_text_chunks: list, words_box_chunks: list, layout_labels_chunks: list,
                  images: list, page_indices: list) -> tuple:
         """Retrieve the top-k chunks: 9-tuple, see reference src/_modules.py:2144-2153, 2180."""
+        # The call builds ~1500 small acyclic containers next to the caller's millions of live word / box objects;
+        # the cyclic collector's generation passes triggered by those allocations were up to 30 % of the call
+        # (scripts/profile_e2e_phases.py).  Nothing created here can be part of a cycle, so collection is paused
+        # for the duration of the call and resumes (with its counters intact) on return.
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._retrieve(text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
+                                  layout_labels_chunks, images, page_indices)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+
+    def _retrieve(self, text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
+                  layout_labels_chunks, images, page_indices) -> tuple:
         inputs_on_host = not question_embeddings.is_cuda
+        if (inputs_on_host and len(text_embeddings) >= 8 and not any(e.is_cuda for e in text_embeddings)
+                and question_embeddings.dim() == 2 and question_embeddings.shape[0] == len(text_embeddings)):
+            return self._retrieve_host_pipelined(text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
+                                                 layout_labels_chunks, images, page_indices)
         res = self._score_topk(text_embeddings, question_embeddings)
         hits = self._hits_to_host(res.topk_idx, res.topk_cnt)
         lists = self._hit_lists(hits, words_text_chunks, words_box_chunks, layout_labels_chunks, images, page_indices)
@@ -312,6 +340,64 @@ class Retriever(StatComponent):
             sims = list(torch.split(flat, res.sizes))
         return (*lists, sims)
 
+    def _retrieve_host_pipelined(self, text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
+                                 layout_labels_chunks, images, page_indices) -> tuple:
+        """Host inputs: the call is bounded by the H2D copy of the embeddings (~0.6 ms for a C2 batch) plus the list
+        building (~1.3 ms).  The batch is cut into a few groups of documents, all enqueued at once; while the DMA
+        engine still copies group g+1 the host already builds the lists of group g.  Same outputs, document order."""
+        dev = self.device
+        B, d, k = len(text_embeddings), question_embeddings.shape[1], int(self.k)
+        lib, check = F._lib_fn, F._lib.check
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            q = F._f32_contig_aligned(question_embeddings.to(dev, non_blocking=True))
+            table = F.upload_doc_table(text_embeddings, d, dev)          # ONE table for the batch
+            sizes = np.asarray(table.sizes, dtype=np.int64)
+            row_off = np.zeros(B + 1, dtype=np.int64)
+            np.cumsum(sizes, out=row_off[1:])
+            tile_off = np.zeros(B + 1, dtype=np.int64)
+            np.cumsum((sizes + table.tile_rows - 1) // table.tile_rows, out=tile_off[1:])
+            total = int(row_off[-1])
+            n_groups = 4 if B >= 32 else 2
+            # groups of ~equal row counts (the PCIe reads dominate)
+            cuts = np.searchsorted(row_off[1:], total * np.arange(1, n_groups) / n_groups, side="left") + 1
+            bounds = sorted(set([0, B] + [int(c) for c in cuts if 0 < c < B]))
+            sims = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+            idx = torch.empty((B, k), dtype=torch.int32, device=dev)
+            val = torch.empty((B, k), dtype=torch.float32, device=dev)
+            cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+            idx_h = torch.empty((B, k), dtype=torch.int32, pin_memory=True)
+            cnt_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+            sims_h = torch.empty((total,), dtype=torch.float32, pin_memory=True)
+            p_tiles, p_row = table.pointers()
+            algo = F._lib.SCORE_LDG if table.algo == F._lib.SCORE_LDG_FUSED else table.algo
+            events = []
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                t_lo, t_hi, r_lo, r_hi = int(tile_off[lo]), int(tile_off[hi]), int(row_off[lo]), int(row_off[hi])
+                if t_hi > t_lo:
+                    check(lib.rdv_score_f32(p_tiles + 32 * t_lo, t_hi - t_lo, table.tile_rows, algo, q.data_ptr(), B, d,
+                                            sims.data_ptr(), stream))
+                check(lib.rdv_topk_segments_f32(sims.data_ptr(), p_row + 8 * lo, hi - lo, k, table.max_rows,
+                                                idx.data_ptr() + 4 * k * lo, val.data_ptr() + 4 * k * lo,
+                                                cnt.data_ptr() + 4 * lo, stream))
+                idx_h[lo:hi].copy_(idx[lo:hi], non_blocking=True)
+                cnt_h[lo:hi].copy_(cnt[lo:hi], non_blocking=True)
+                if r_hi > r_lo:
+                    sims_h[r_lo:r_hi].copy_(sims[r_lo:r_hi], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                events.append(done)
+        outs = [[] for _ in range(8)]
+        idx_np, cnt_np = idx_h.numpy(), cnt_h.numpy()
+        for (lo, hi), done in zip(zip(bounds[:-1], bounds[1:]), events):
+            done.synchronize()
+            hits = [idx_np[b, :cnt_np[b]].tolist() for b in range(lo, hi)]
+            lists = self._hit_lists(hits, words_text_chunks[lo:hi], words_box_chunks[lo:hi], layout_labels_chunks[lo:hi],
+                                    images[lo:hi], page_indices[lo:hi])
+            for o in range(8):
+                outs[o].extend(lists[o])
+        return (*outs, list(torch.split(sims_h, table.sizes)))
+
     def retrieve_packed(self, text_embeddings, question_embeddings, store, prompt_ids, sep_ids=(),
                         eos_id: int = 1, pad_id: int = 0, max_source_length: int = 512,
                         with_layout_labels: bool = False):
@@ -319,12 +405,16 @@ class Retriever(StatComponent):
         input_ids / boxes / attention_mask (what flatten + VT5.prepare_inputs_for_vqa build on the host,
         src/utils.py:233-253, src/VT5.py:141-185) for a pre-tokenised `DocStore`.  No Python lists."""
         dev = question_embeddings.device if question_embeddings.is_cuda else self.device
-        emb = [_to_device(e, dev) for e in text_embeddings]
+        on_host = len(text_embeddings) and not any(e.is_cuda for e in text_embeddings)
+        emb = [] if on_host else [_to_device(e, dev) for e in text_embeddings]
         q = _to_device(question_embeddings, dev)
         k = int(self.k)
         with torch.cuda.device(dev):
             # two launches: streaming score kernel, then ONE block per document selects its top-k and gathers
-            table = F.build_doc_table(emb, q.shape[1], dev)
+            if len(text_embeddings) and not any(e.is_cuda for e in text_embeddings):
+                table = F.upload_doc_table(text_embeddings, q.shape[1], dev)
+            else:
+                table = F.build_doc_table(emb, q.shape[1], dev)
             sims = F.score_table(table, q)
             B = table.B
             topk_idx = torch.empty((B, k), dtype=torch.int32, device=dev)

@@ -40,10 +40,14 @@ def assert_same_lists(out, ref):
     assert [[digest(im) for im in doc] for doc in out[6]] == ref[6]
 
 
-@pytest.mark.parametrize("on_device", [True, False])
+@pytest.mark.parametrize("on_device", [True, False, "pinned"])
 def test_retrieve_matches_reference_golden(golden_dir, on_device):
+    """Device tensors (the reference's case), pageable host tensors (packed upload) and pinned host tensors
+    (zero-copy: the score kernel reads the page-locked rows over PCIe) must give the same 9-tuple."""
     from rag_docvqa_b200.retriever import Retriever
     gold, emb, q, words, boxes, labels, images, pages = load_retrieve_inputs(golden_dir)
+    if on_device == "pinned":
+        emb, q, on_device = [e.pin_memory() for e in emb], q.pin_memory(), False
     emb_in = [e.to(DEV) for e in emb] if on_device else emb
     q_in = q.to(DEV) if on_device else q
     for var in gold["variants"]:
@@ -60,14 +64,19 @@ def test_retrieve_matches_reference_golden(golden_dir, on_device):
             compare.assert_scores_close(s.cpu().numpy(), np.array(var["similarities"][b], dtype=np.float32))
 
 
+@pytest.mark.parametrize("where", ["device", "pinned_host"])
 @pytest.mark.parametrize("s,reorder", [(0, False), (0, True), (2, False), (5, True), (40, False)])
-def test_retrieve_c2_slice_vs_oracle(s, reorder):
+def test_retrieve_c2_slice_vs_oracle(s, reorder, where):
     from rag_docvqa_b200.retriever import Retriever
-    batch = synth.make_text_batch("C2", with_lists=True, docs=10, seed=77, dup_frac=0.0)
+    batch = synth.make_text_batch("C2", with_lists=True, docs=40 if where == "pinned_host" else 10, seed=77, dup_frac=0.0)
     args = (batch["words_text_chunks"], batch["words_box_chunks"], batch["layout_labels_chunks"],
             batch["images"], batch["page_indices"])
     retr = Retriever({**BASE, "chunk_num": 5, "include_surroundings": s, "reorder_chunks": reorder})
-    out = retr.retrieve([e.to(DEV) for e in batch["text_embeddings"]], batch["question_embeddings"].to(DEV), *args)
+    if where == "device":
+        out = retr.retrieve([e.to(DEV) for e in batch["text_embeddings"]], batch["question_embeddings"].to(DEV), *args)
+    else:     # >= 32 documents on the host: the pipelined path (4 groups), zero-copy reads of the pinned rows
+        out = retr.retrieve([e.pin_memory() for e in batch["text_embeddings"]], batch["question_embeddings"].pin_memory(), *args)
+        assert not out[8][0].is_cuda and len(out[8]) == 40
     # the oracle gathers for the SAME hits (index parity is covered in test_score_topk_gpu.py)
     sims = [x.cpu() for x in out[8]]
     hits = [R.topk_lowest_index(x, 5) for x in sims]
