@@ -627,6 +627,46 @@ def run_ours(args):
                     packed_step(i)
                 torch.cuda.synchronize()
                 extras["e2e_packed_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
+                # ... and with the visual input as well: crops of the hits grid-packed and resized to 224 x 224 on the device
+                from rag_docvqa_b200.pagestore import PageStore
+                pstore = PageStore.from_images(host_batch["images"], dev)
+
+                def packed_visual_step(i):
+                    emb_h, q_h = host_sets[i % len(host_sets)]
+                    return retr.retrieve_packed(emb_h, q_h, store, prompts, pages=pstore)
+                packed_visual_step(0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for i in range(e2e_steps):
+                    packed_visual_step(i)
+                torch.cuda.synchronize()
+                extras["e2e_packed_with_visual_input_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
+                # the visual pack kernels alone (hits resident): crop + grid pack + Pillow-exact bicubic resize + normalise
+                pk, rs = retr.retrieve_packed(batches[0]["text_embeddings"], batches[0]["question_embeddings"], store, prompts)
+                vplan = pstore.prepare_pack(pk.hit_page, pk.hit_rect, rs.topk_cnt)
+                for _ in range(3):
+                    vplan.launch()
+                ms_v = timed_loop(lambda i: vplan.launch(), 20, torch.cuda.synchronize) / 20
+                area = int(((pk.hit_rect[..., 2] - pk.hit_rect[..., 0]).clamp(min=0) * (pk.hit_rect[..., 3] - pk.hit_rect[..., 1]).clamp(min=0)).sum().item())
+                extras["visual_pack"] = {"ms": ms_v, "patch_pixels": area, "algorithmic_bytes": area * 3 + w.docs * 224 * 224 * 15,
+                                         "GBps": (area * 3 + w.docs * 224 * 224 * 15) / ms_v / 1e6,
+                                         "cpu_reference_ms": None,
+                                         "what": "64 documents x 5 crops -> grid canvas -> 224 x 224 bicubic (Pillow-exact) -> fp32 pixel_values"}
+                # the same on the host, as the reference does it (PIL crop + concatenate grid + PIL resize), one thread
+                from oracle import ref_restated as R_
+                hr, hp, hc = pk.hit_rect.cpu().numpy(), pk.hit_page.cpu().numpy(), rs.topk_cnt.cpu().numpy()
+                from PIL import Image as _Image
+                t0 = time.perf_counter()
+                for b in range(min(w.docs, 16)):
+                    patches = [host_batch["images"][b][int(hp[b, j])].crop(tuple(int(v) for v in hr[b, j])) for j in range(int(hc[b]))]
+                    if not patches:
+                        continue
+                    gw, gh, pos = R_.grid_layout([p_.size for p_ in patches])
+                    canvas = _Image.new("RGB", (gw, gh))
+                    for p_, xy in zip(patches, pos):
+                        canvas.paste(p_, xy)
+                    canvas.resize((224, 224), resample=_Image.Resampling.BICUBIC)
+                extras["visual_pack"]["cpu_reference_ms"] = (time.perf_counter() - t0) * 1e3 * w.docs / min(w.docs, 16)
         else:
             line["cpu_baseline"] = {"value": w.docs / st_best, "unit": "queries/s", "cores": threads, "kind": "port",
                                     "sample": "oracle score+topk on one full %s batch, best of %d reps" % (w.name, st_reps)}

@@ -286,6 +286,65 @@ RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args*
 
 
 /* ---------------------------------------------------------------------------------------------
+ * Retrieved patches -> the generator's visual input.
+ *
+ * Replaces, for page images resident on the device, the host work that follows retrieval when
+ * page_retrieval == "concat" (every shipped config; src/RAGVT5.py:378): page.crop(rect) per hit
+ * (src/_modules.py:2102-2121), concatenate_patches(patches, mode="grid") (src/utils.py:180-231: strip packing
+ * in hit order on a canvas max-width x int(total area / max width), pastes clipped to the canvas, 5 x 5 blank
+ * image when there is no hit) and the feature extractor's resize to out_size x out_size (src/_modules.py:133;
+ * PIL.Image.resize = Pillow's two-pass 8-bit resampler: horizontal pass rounded to uint8, then vertical
+ * pass; filter 2 = BILINEAR, 3 = BICUBIC), then pixel_values = (u8 * (1/255) - mean) / std as fp32 CHW.
+ * uint8 results are bit-exact against Pillow.
+ *
+ * rdv_pagestore: B documents; page (b, p) is entry doc_page_off[b] + p of page_wh[P*2] (width, height) and
+ *   page_off[P] (int64 byte offset into `pixels` of its RGB rows, tightly packed H x W x 3 uint8; several
+ *   entries may share one image).
+ * rdv_visual_args: hit_page / hit_rect / hit_cnt = the gather kernel's per-hit outputs in output order
+ *   ((B,k) page index within the document, (B,k,4) crop rectangle x0,y0,x1,y1, (B) number of hits);
+ *   workspaces layout (B * (8 + 4k) int32), coeff_h / coeff_v (B * out_size * (ksize_cap + 2) int32),
+ *   temp (B * rows_cap * out_size * 3 bytes); outputs out_u8 (B, S, S, 3), out_px (B, 3, S, S) fp32 or NULL,
+ *   status[B]: 0 ok, 1 = a capacity (ksize_cap_h / ksize_cap_v / rows_cap / 8192-pixel canvas width) is too
+ *   small, 2 = degenerate canvas (zero width or height: the reference raises there).  Capacities for a batch
+ *   whose pages are at most Wmax x Hmax: ksize_cap = 2 * ceil(support * max(extent / out_size, 1)) + 1 with
+ *   support 1 (bilinear) or 2 (bicubic) and extent = Wmax (h) or k * Hmax (v); rows_cap = k * Hmax.
+ * Requirements: 1 <= k <= 64.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rdv_pagestore {
+    int32_t B;
+    int32_t reserved;
+    const int32_t* doc_page_off;
+    const int32_t* page_wh;
+    const int64_t* page_off;
+    const uint8_t* pixels;
+} rdv_pagestore;
+
+typedef struct rdv_visual_args {
+    const int32_t* hit_page;
+    const int32_t* hit_rect;
+    const int32_t* hit_cnt;
+    int32_t k;
+    int32_t out_size;
+    int32_t filter;
+    int32_t ksize_cap_h;
+    int32_t ksize_cap_v;
+    int32_t rows_cap;
+    int32_t max_page_w;          /* widest page of the batch, 1..8192 (sizes the launch and its shared memory) */
+    int32_t reserved;
+    float mean[3];
+    float std[3];
+    int32_t* layout;
+    int32_t* coeff_h;
+    int32_t* coeff_v;
+    uint8_t* temp;
+    uint8_t* out_u8;
+    float* out_px;
+    int32_t* status;
+} rdv_visual_args;
+
+RDV_API int rdv_visual_pack(const rdv_pagestore* ps, const rdv_visual_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * bf16 tensor-core scoring (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
  *
  * rdv_rows_to_bf16      fp32 (rows, d) -> bf16 copy, optionally L2-normalised first (F.normalize,

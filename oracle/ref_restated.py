@@ -378,3 +378,136 @@ def merge_topk(cand_scores: np.ndarray, cand_idx: np.ndarray, k: int):
         out_s[q, :len(order)] = s[order]
         out_i[q, :len(order)] = i[order]
     return out_s, out_i
+
+
+# --------------------------------------------------------------------------------------
+# f1: retrieved patches -> the generator's visual input
+#   crop rectangles (a9) -> concatenate_patches(mode="grid")   reference: src/utils.py:180-231 (used at
+#   src/RAGVT5.py:378 for page_retrieval == "concat", every shipped config) -> the HF feature extractor's
+#   resize to 224 x 224 (src/_modules.py:133), which is PIL.Image.resize (third party: Pillow, pinned by the
+#   reference's requirements.txt; algorithm restated below from Pillow's src/libImaging/Resample.c, 8 bits
+#   per channel path, and checked bit for bit against the installed Pillow in tests/test_oracle_golden.py).
+# --------------------------------------------------------------------------------------
+def grid_layout(sizes: Sequence[Tuple[int, int]]):
+    """Placement of patches of the given (width, height) by concatenate_patches(mode="grid") (src/utils.py:189-231,
+    compute_grid :180-187).  Returns (grid_w, grid_h, [(x, y), ...]); no patches -> the 5 x 5 blank image (:193-195)."""
+    if not sizes:
+        return 5, 5, []
+    total_area = sum(w * h for w, h in sizes)                    # :183
+    grid_w = max(w for w, _ in sizes)                            # :185
+    grid_h = int(total_area / grid_w)                            # :186  (true division, truncation)
+    pos, x_off, y_off, row_h = [], 0, 0, 0
+    for w, h in sizes:                                           # :223-230, original patch order
+        if x_off + w > grid_w:
+            x_off = 0
+            y_off += row_h
+            row_h = 0
+        pos.append((x_off, y_off))
+        x_off += w
+        row_h = max(row_h, h)
+    return grid_w, grid_h, pos
+
+
+def concat_grid(pages: Sequence[np.ndarray], rects: Sequence[Sequence[int]], page_of: Sequence[int]) -> np.ndarray:
+    """uint8 (grid_h, grid_w, 3) image = concatenate_patches([page.crop(rect) ...], mode="grid"): crops that reach
+    outside the page are black there (PIL crop), pastes are clipped to the canvas (PIL paste)."""
+    sizes = [(r[2] - r[0], r[3] - r[1]) for r in rects]
+    gw, gh, pos = grid_layout(sizes)
+    canvas = np.zeros((gh, gw, 3), dtype=np.uint8)
+    for (x0, y0, x1, y1), p, (dx, dy) in zip(rects, page_of, pos):
+        page = pages[p]
+        H, W = page.shape[:2]
+        w, h = x1 - x0, y1 - y0
+        patch = np.zeros((max(h, 0), max(w, 0), 3), dtype=np.uint8)
+        sx0, sy0, sx1, sy1 = max(x0, 0), max(y0, 0), min(x1, W), min(y1, H)
+        if sx1 > sx0 and sy1 > sy0:
+            patch[sy0 - y0:sy1 - y0, sx0 - x0:sx1 - x0] = page[sy0:sy1, sx0:sx1]
+        cw, ch = min(w, gw - dx), min(h, gh - dy)                 # paste clips at the canvas border
+        if cw > 0 and ch > 0:
+            canvas[dy:dy + ch, dx:dx + cw] = patch[:ch, :cw]
+    return canvas
+
+
+PIL_BILINEAR, PIL_BICUBIC = 2, 3            # PIL.Image.Resampling values
+_PRECISION_BITS = 32 - 8 - 2
+
+
+def _pil_filter(kind: int, x: float) -> float:
+    if x < 0.0:
+        x = -x
+    if kind == PIL_BILINEAR:
+        return 1.0 - x if x < 1.0 else 0.0
+    a = -0.5
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_coeffs(in_size: int, out_size: int, kind: int):
+    """precompute_coeffs + normalize_coeffs_8bpc of Pillow's Resample.c for the full-image box:
+    returns (bounds (out, 2) int32 [first, count], kk (out, ksize) int32 fixed-point weights)."""
+    support_f = 1.0 if kind == PIL_BILINEAR else 2.0
+    scale = float(np.float32(in_size) - np.float32(0.0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = support_f * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        xmin = max(xmin, 0)
+        xmax = int(center + support + 0.5)
+        xmax = min(xmax, in_size) - xmin
+        w = [_pil_filter(kind, (x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x in range(xmax):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(-0.5 + v * (1 << _PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def _pil_pass(src: np.ndarray, bounds: np.ndarray, kk: np.ndarray) -> np.ndarray:
+    """One 8-bit resampling pass along axis 1 of src (rows, in, 3) -> (rows, out, 3): 32-bit accumulation from
+    1 << (PRECISION_BITS - 1), arithmetic shift, clip to 0..255 (ImagingResampleHorizontal_8bpc)."""
+    out = np.empty((src.shape[0], bounds.shape[0], 3), dtype=np.uint8)
+    s = src.astype(np.int64)
+    for xx in range(bounds.shape[0]):
+        x0, n = int(bounds[xx, 0]), int(bounds[xx, 1])
+        acc = (s[:, x0:x0 + n, :] * kk[xx, :n].astype(np.int64)[None, :, None]).sum(axis=1) + (1 << (_PRECISION_BITS - 1))
+        out[:, xx, :] = np.clip(acc >> _PRECISION_BITS, 0, 255).astype(np.uint8)
+    return out
+
+
+def pil_resize_u8(img: np.ndarray, out_w: int, out_h: int, kind: int = PIL_BICUBIC) -> np.ndarray:
+    """PIL.Image.resize((out_w, out_h), resample=kind) of an RGB uint8 image (reducing_gap=None): horizontal pass
+    over the rows the vertical pass needs, rounded to uint8, then the vertical pass (ImagingResample)."""
+    in_h, in_w = img.shape[:2]
+    if (in_w, in_h) == (out_w, out_h):
+        return img.copy()
+    bh, kh = pil_coeffs(in_w, out_w, kind)
+    bv, kv = pil_coeffs(in_h, out_h, kind)
+    cur = img
+    if out_w != in_w:
+        first = int(bv[0, 0])
+        last = int(bv[-1, 0] + bv[-1, 1])
+        cur = _pil_pass(img[first:last], bh, kh)
+        bv = bv.copy()
+        bv[:, 0] -= first
+    if out_h != in_h:
+        cur = _pil_pass(cur.transpose(1, 0, 2), bv, kv).transpose(1, 0, 2)
+    return np.ascontiguousarray(cur)
+
+
+def visual_input(pages, rects, page_of, out_size: int = 224, kind: int = PIL_BICUBIC,
+                 mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    """(uint8 (S, S, 3) resized grid image, float32 (3, S, S) pixel_values = (u8 / 255 - mean) / std)."""
+    u8 = pil_resize_u8(concat_grid(pages, rects, page_of), out_size, out_size, kind)
+    px = (u8.astype(np.float32) * np.float32(1.0 / 255.0) - np.asarray(mean, np.float32)) / np.asarray(std, np.float32)
+    return u8, np.ascontiguousarray(px.transpose(2, 0, 1))

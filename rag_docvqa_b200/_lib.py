@@ -6,11 +6,11 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int32, c_int64, c_void_p, POINTER, Structure
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -38,6 +38,20 @@ class GatherArgsStruct(Structure):
                     "seg_ws", "out_ids", "out_boxes", "out_mask", "out_labels", "full_len", "status", "hit_chunk",
                     "hit_page", "hit_label", "hit_nwords", "hit_bbox", "hit_rect", "sims", "topk_val")] + [
                     ("max_rows", c_int32), ("reserved", c_int32)]
+
+
+class PageStoreStruct(Structure):
+    """Mirror of `rdv_pagestore` (include/rdv.h)."""
+    _fields_ = [("B", c_int32), ("reserved", c_int32), ("doc_page_off", c_void_p), ("page_wh", c_void_p),
+                ("page_off", c_void_p), ("pixels", c_void_p)]
+
+
+class VisualArgsStruct(Structure):
+    """Mirror of `rdv_visual_args` (include/rdv.h)."""
+    _fields_ = [("hit_page", c_void_p), ("hit_rect", c_void_p), ("hit_cnt", c_void_p), ("k", c_int32), ("out_size", c_int32),
+                ("filter", c_int32), ("ksize_cap_h", c_int32), ("ksize_cap_v", c_int32), ("rows_cap", c_int32),
+                ("max_page_w", c_int32), ("reserved", c_int32), ("mean", c_float * 3), ("std", c_float * 3), ("layout", c_void_p), ("coeff_h", c_void_p),
+                ("coeff_v", c_void_p), ("temp", c_void_p), ("out_u8", c_void_p), ("out_px", c_void_p), ("status", c_void_p)]
 
 
 # name -> (restype, argtypes); tests/test_abi.py checks this table against include/rdv.h
@@ -74,6 +88,7 @@ SIGNATURES = {
     "rdv_rows_split_tf32": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "rdv_maxsim_tf32x3_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                        c_void_p, c_void_p, c_void_p]),
+    "rdv_visual_pack": (c_int32, [POINTER(PageStoreStruct), POINTER(VisualArgsStruct), c_void_p]),
     "rdv_gather_vt5_inputs": (c_int32, [POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
 }
 

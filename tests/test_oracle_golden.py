@@ -194,3 +194,55 @@ def test_against_live_reference():
     assert torch.equal(R.mean_pooling(e, m), model_utils.mean_pooling(e, m))
     p, qq = synth.make_strip_batch(1, [3], 20, 24, 6)
     assert torch.equal(R.late_interaction(qq[0:1], p[0]), utils.late_interaction(qq[0:1], p[0]))
+
+
+# ---- f1: retrieved patches -> visual input (concatenate_patches grid + Pillow resize) -------------------------
+def _visual_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "visual_pack.npz"))
+    for b in range(int(z["docs"])):
+        pages = [z["page_%d_%d" % (b, p)] for p in range(int(z["n_pages_%d" % b]))]
+        rects = [tuple(int(v) for v in r) for r in z["rects_%d" % b]]
+        yield b, z, pages, rects, [int(p) for p in z["page_of_%d" % b]]
+
+
+def test_concat_grid_and_resize_match_reference_golden(golden_dir):
+    """The frozen outputs of the reference's concatenate_patches(mode="grid") + PIL resize."""
+    for b, z, pages, rects, page_of in _visual_golden(golden_dir):
+        canvas = R.concat_grid(pages, rects, page_of)
+        np.testing.assert_array_equal(canvas, z["canvas_%d" % b])
+        for name, kind in (("bilinear", R.PIL_BILINEAR), ("bicubic", R.PIL_BICUBIC)):
+            np.testing.assert_array_equal(R.pil_resize_u8(canvas, 64, 64, kind), z["resized_%s_%d" % (name, b)])
+
+
+@pytest.mark.parametrize("shape", [(300, 400, 224, 224), (1069, 791, 224, 224), (2500, 816, 224, 224), (100, 60, 224, 224),
+                                   (224, 500, 224, 224), (37, 224, 224, 224), (224, 224, 224, 224), (3, 3, 32, 32),
+                                   (90, 700, 64, 48)])
+def test_pil_resize_restatement_equals_installed_pillow(shape):
+    """Pillow is a third-party dependency of the path (not under /root/reference): the restated Resample.c must
+    equal the installed library bit for bit, down- and up-scaling, both filters."""
+    from PIL import Image
+    h, w, oh, ow = shape
+    img = np.random.RandomState(h * 7 + w).randint(0, 256, (h, w, 3)).astype(np.uint8)
+    for kind, pk in ((R.PIL_BILINEAR, Image.Resampling.BILINEAR), (R.PIL_BICUBIC, Image.Resampling.BICUBIC)):
+        ref = np.asarray(Image.fromarray(img, "RGB").resize((ow, oh), resample=pk))
+        np.testing.assert_array_equal(R.pil_resize_u8(img, ow, oh, kind), ref)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted (GPU box)")
+def test_concat_grid_against_live_reference():
+    from PIL import Image
+    from oracle.ref_import import import_reference
+    _, utils, _ = import_reference()
+    rng = np.random.RandomState(3)
+    for trial in range(20):
+        pages = [rng.randint(0, 256, (rng.randint(50, 200), rng.randint(50, 200), 3)).astype(np.uint8) for _ in range(3)]
+        rects, page_of = [], []
+        for i in range(rng.randint(0, 7)):
+            p = rng.randint(0, 3)
+            H, W = pages[p].shape[:2]
+            x0, y0 = rng.randint(0, W - 1), rng.randint(0, H - 1)
+            rects.append((x0, y0, rng.randint(x0 + 1, W + 1), rng.randint(y0 + 1, H + 1)))
+            page_of.append(p)
+        patches = [Image.fromarray(pages[p], "RGB").crop(r) for r, p in zip(rects, page_of)]
+        ref = np.asarray(utils.concatenate_patches(patches, mode="grid").convert("RGB"))
+        np.testing.assert_array_equal(R.concat_grid(pages, rects, page_of), ref)
