@@ -167,6 +167,18 @@ class DocStore:
             arrays["page_wh"] = np.ascontiguousarray(wh)
         return cls(arrays, B, device)
 
+    # ---- on-disk form: the CSR arrays of a pre-tokenised batch of documents --------
+    def save(self, path: str) -> None:
+        """One .npz with every host array; DocStore.load(path, device) restores an identical store."""
+        np.savez(path, __B=np.int64(self.B), **{k: v for k, v in self.host.items() if v is not None})
+
+    @classmethod
+    def load(cls, path: str, device) -> "DocStore":
+        with np.load(path if path.endswith(".npz") else path + ".npz") as z:
+            arrays = {k: z[k] for k in z.files if k != "__B"}
+            B = int(z["__B"])
+        return cls(arrays, B, device)
+
     # ------------------------------------------------------------------------------------------
     def prepare_gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],
                        include_surroundings: int = 0, reorder_chunks: bool = False, sep_ids: Sequence[int] = (),

@@ -10,13 +10,16 @@ scoring formula is Retriever._get_similarities' (src/_modules.py:1990-1993) appl
              -> ONE all-gather of (Q, k) values + ids over NCCL / NVLink (80 KB per rank at Q=1024, k=10)
              -> merge kernel by (score desc, global id asc) on every rank.
 The same packed ordering is used locally and in the merge, so the sharded answer equals the
-unsharded one bit for bit (tests/test_sharded_gloo.py checks this on CPU with world_size 2 for the
-host logic; tests/test_tc_gpu.py on the GPU).
+unsharded one bit for bit (tests/test_sharded_gloo.py checks the exchange logic on CPU ranks with
+world_size 2, injecting the oracle's merge; tests/test_tc_gpu.py checks the kernels on the GPU).
 """
 from __future__ import annotations
 
+import json
+import os
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -75,9 +78,75 @@ class CorpusShard:
         return F.topk_merge(cand_val, cand_idx, k)
 
 
-def merge_across_ranks(local_val: torch.Tensor, local_idx: torch.Tensor, k: int, group=None):
+# ---- on-disk corpus index ---------------------------------------------------------
+# A directory with  rows.bf16  (N x d bfloat16, row-major, raw),  inv_norm.f32  (N fp32 = 1 / ||row||, raw)  and
+# meta.json.  Every rank memory-maps the files and uploads only ITS row range (shard_bounds), through a pinned
+# staging buffer in fixed-size pieces, so a 15 GB index never exists twice in host memory.
+INDEX_VERSION = 1
+
+
+def save_corpus_index(path: str, rows_bf16: torch.Tensor, inv_norm: Optional[torch.Tensor] = None, chunk_rows: int = 1 << 18) -> None:
+    """Writes a corpus (CPU or CUDA tensor, (N, d) bf16) as an index directory.  `inv_norm` is computed on the device
+    for CUDA inputs when not given; for CPU inputs it is left to load time."""
+    if rows_bf16.dtype != torch.bfloat16 or rows_bf16.dim() != 2:
+        raise ValueError("save_corpus_index: expected an (N, d) bf16 matrix")
+    os.makedirs(path, exist_ok=True)
+    n, d = rows_bf16.shape
+    if inv_norm is None and rows_bf16.is_cuda:
+        inv_norm = F.bf16_inv_norm(rows_bf16.contiguous())
+    with open(os.path.join(path, "rows.bf16"), "wb") as f:
+        for a in range(0, n, chunk_rows):
+            f.write(rows_bf16[a:a + chunk_rows].contiguous().cpu().view(torch.int16).numpy().tobytes())
+    if inv_norm is not None:
+        with open(os.path.join(path, "inv_norm.f32"), "wb") as f:
+            f.write(inv_norm.detach().float().cpu().numpy().tobytes())
+    with open(os.path.join(path, "meta.json"), "w") as f:
+        json.dump({"version": INDEX_VERSION, "rows": int(n), "dim": int(d), "dtype": "bfloat16",
+                   "has_inv_norm": inv_norm is not None}, f)
+
+
+class CorpusIndex:
+    """Read side of an index directory: memory-mapped rows, per-rank loading."""
+
+    def __init__(self, path: str):
+        with open(os.path.join(path, "meta.json")) as f:
+            self.meta = json.load(f)
+        if self.meta.get("version") != INDEX_VERSION or self.meta.get("dtype") != "bfloat16":
+            raise ValueError("unsupported corpus index: %r" % (self.meta,))
+        self.path, self.n, self.d = path, int(self.meta["rows"]), int(self.meta["dim"])
+        self.rows = np.memmap(os.path.join(path, "rows.bf16"), dtype=np.int16, mode="r", shape=(self.n, self.d)) if self.n else \
+            np.zeros((0, self.d), np.int16)
+        self.inv_norm = (np.memmap(os.path.join(path, "inv_norm.f32"), dtype=np.float32, mode="r", shape=(self.n,))
+                         if self.meta.get("has_inv_norm") and self.n else None)
+
+    def load_shard(self, device, rank: int = 0, world: int = 1, chunk_rows: int = 1 << 18) -> CorpusShard:
+        """Rows [lo, hi) of this rank on `device`, global ids starting at lo."""
+        lo, hi = shard_bounds(self.n, world, rank)
+        rows = torch.empty((hi - lo, self.d), dtype=torch.bfloat16, device=device)
+        stage = [torch.empty((min(chunk_rows, max(hi - lo, 1)), self.d), dtype=torch.int16, pin_memory=True) for _ in range(2)]
+        done = [None, None]
+        for i, a in enumerate(range(lo, hi, chunk_rows)):
+            b = min(hi, a + chunk_rows)
+            buf = stage[i & 1]
+            if done[i & 1] is not None:
+                done[i & 1].synchronize()                      # the previous copy out of this staging buffer
+            buf[:b - a].numpy()[...] = self.rows[a:b]
+            rows[a - lo:b - lo].view(torch.int16).copy_(buf[:b - a], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            done[i & 1] = ev
+        inv = None
+        if self.inv_norm is not None:
+            inv = torch.from_numpy(np.ascontiguousarray(self.inv_norm[lo:hi])).to(device)
+        torch.cuda.synchronize(device)
+        return CorpusShard(rows, id_offset=lo, inv_norm=inv)
+
+
+def merge_across_ranks(local_val: torch.Tensor, local_idx: torch.Tensor, k: int, group=None, merge_fn=None):
     """All-gather every rank's (Q, k) candidates and merge on every rank.  With world_size 1 (or no
-    process group) the local result is already final."""
+    process group) the local result is already final.  `merge_fn(cand_val, cand_idx, k)` defaults to the
+    CUDA merge kernel (rdv_topk_merge); there is no host implementation in the product -- the CPU (gloo)
+    test of this exchange logic injects the oracle's merge."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_val, local_idx
@@ -87,28 +156,12 @@ def merge_across_ranks(local_val: torch.Tensor, local_idx: torch.Tensor, k: int,
     dist.all_gather(vals, local_val.contiguous(), group=group)
     dist.all_gather(idxs, local_idx.contiguous(), group=group)
     cand_val, cand_idx = torch.cat(vals, dim=1), torch.cat(idxs, dim=1)
-    return merge_candidates(cand_val, cand_idx, k)
+    return (merge_fn or merge_candidates)(cand_val, cand_idx, k)
 
 
 def merge_candidates(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):
-    """(Q, m) -> (Q, k) by (score desc, id asc).  CUDA tensors go through rdv_topk_merge; the torch
-    path below exists ONLY so the host-side sharding logic can be exercised with the gloo backend on
-    CPU ranks in tests (it is never taken on a GPU rank)."""
-    if cand_val.is_cuda:
-        return F.topk_merge(cand_val, cand_idx, k)
-    return _merge_candidates_host(cand_val, cand_idx, k)
-
-
-def _merge_candidates_host(cand_val, cand_idx, k):
-    big = torch.iinfo(torch.int64).max
-    val = torch.where(cand_idx >= 0, cand_val, torch.full_like(cand_val, float("-inf")))
-    idx = torch.where(cand_idx >= 0, cand_idx, torch.full_like(cand_idx, big))
-    order = torch.argsort(idx, dim=1, stable=True)                      # id asc ...
-    val, idx = torch.gather(val, 1, order), torch.gather(idx, 1, order)
-    order = torch.argsort(val, dim=1, descending=True, stable=True)     # ... then score desc (stable)
-    val, idx = torch.gather(val, 1, order)[:, :k], torch.gather(idx, 1, order)[:, :k]
-    idx = torch.where(idx == big, torch.full_like(idx, -1), idx)
-    return val, idx
+    """(Q, m) -> (Q, k) by (score desc, id asc) on the device (rdv_topk_merge).  CUDA tensors only."""
+    return F.topk_merge(cand_val, cand_idx, k)
 
 
 def search(shard: CorpusShard, questions: torch.Tensor, k: int, group=None):

@@ -1,7 +1,7 @@
-"""N > 1 host logic on CPU ranks (gloo, world_size 2): shard bounds, the all-gather of per-rank
-candidates and the final merge must reproduce the unsharded oracle exactly.  (The per-rank scoring
-kernel is covered on the GPU in tests/test_tc_gpu.py; CUDA tensors take rdv_topk_merge instead of the
-torch merge used here.)"""
+"""N > 1 host logic on CPU ranks (gloo, world_size 2): shard bounds and the all-gather of per-rank candidates,
+merged with the ORACLE's merge (injected: the product has no host merge), must reproduce the unsharded oracle
+exactly.  (The scoring and merge kernels are covered on the GPU in tests/test_tc_gpu.py and
+tests/test_pool_maxsim_merge_gpu.py.)"""
 import os
 import socket
 
@@ -19,6 +19,11 @@ def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _oracle_merge(cand_val, cand_idx, k):
+    v, i = R.merge_topk(cand_val.numpy(), cand_idx.numpy(), k)
+    return torch.from_numpy(v), torch.from_numpy(i)
 
 
 def _worker(rank, world, port, n, d, Qn, k, out_dir):
@@ -39,7 +44,7 @@ def _worker(rank, world, port, n, d, Qn, k, out_dir):
                           torch.gather(scores, 1, torch.from_numpy(np.maximum(loc, 0))),
                           torch.full((Qn, k), float("-inf")))
         idx = torch.where(torch.from_numpy(loc) >= 0, torch.from_numpy(loc) + lo, torch.full((Qn, k), -1))
-        m_val, m_idx = sharded.merge_across_ranks(val, idx, k)
+        m_val, m_idx = sharded.merge_across_ranks(val, idx, k, merge_fn=_oracle_merge)
         full = R.corpus_scores(E, Q)
         ref = np.stack([R.topk_lowest_index(full[q], k) for q in range(Qn)])
         ok = bool(np.array_equal(m_idx.numpy(), ref)) and bool(
@@ -68,10 +73,10 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_host_merge_orders_by_score_then_id():
+def test_product_has_no_host_merge():
     val = torch.tensor([[0.5, 0.9, 0.9, 0.1, 0.9]])
     idx = torch.tensor([[7, 30, 4, 2, -1]])
-    v, i = sharded.merge_candidates(val, idx, 3)
-    assert i.tolist() == [[4, 30, 7]] and torch.equal(v, torch.tensor([[0.9, 0.9, 0.5]]))
-    ref_v, ref_i = R.merge_topk(val.numpy(), idx.numpy(), 3)
-    assert np.array_equal(i.numpy(), ref_i)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sharded.merge_candidates(val, idx, 3)
+    ref_v, ref_i = R.merge_topk(val.numpy(), idx.numpy(), 3)          # the checker's ordering: score desc, id asc
+    assert ref_i.tolist() == [[4, 30, 7]] and ref_v.tolist() == [[np.float32(0.9), np.float32(0.9), np.float32(0.5)]]
