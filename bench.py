@@ -521,7 +521,10 @@ def run_ours(args):
     cfg = {"compute_stats": False, "compute_stats_examples": False, "n_stats_examples": 0, "chunk_num": w.k,
            "device": str(dev)}
     e2e_steps = max(5, min(args.steps, 40))
-    if with_lists:
+    if args.skip_e2e:
+        e2e = {"value": None, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 0,
+               "api": "skipped (--skip-e2e: profiling run, keeps the kernel launch list to the device-resident steps)"}
+    elif with_lists:
         lists = (host_batch["words_text_chunks"], host_batch["words_box_chunks"], host_batch["layout_labels_chunks"],
                  host_batch["images"], host_batch["page_indices"])
         retr = Retriever({**cfg, "retrieval_lazy_patches": True})
@@ -932,10 +935,13 @@ def main():
     ap.add_argument("--corpus-queries", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-input arm")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 LDG kernel, 2 TMA kernel")
     ap.add_argument("--lanes", type=int, default=8, choices=[1, 2, 3, 4, 8],
                     help="captured streams the steps alternate between (1 = one dependent chain)")
     args = ap.parse_args()
+    if args.skip_e2e:
+        args.no_extras = True
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "C5":

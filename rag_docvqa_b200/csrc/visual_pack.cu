@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) visual_resize_h_kernel(const Params 
     }
     const int* ch = a.coeff_h + (size_t)b * S * cap;
     if (k_in_smem)
-        for (int i = tid; i < S * ksz; i += kThreads) { const int xx = i / ksz; s_k[i] = __ldg(ch + (size_t)xx * cap + (i - xx * ksz)); }
+        for (int i = tid; i < S * ksz; i += kThreads) { const int xx = i / ksz; s_k[i] = __ldg(ch + (size_t)xx * cap + (i - xx * ksz)); }   // (a warp-per-row variant measured no faster)
     const int nr = min(R, rows - r_begin);
     for (int i = tid; i < nr * pitch / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_rows)[i] = 0u;      // black canvas
     __syncthreads();
@@ -274,18 +274,32 @@ __global__ void __launch_bounds__(kThreads) visual_resize_v_kernel(const Params 
     const int* k = a.coeff_v + ((size_t)b * S + yy) * cap;
     const int first = bad ? 0 : __ldg(k) - hdr[kHdrRowFirst], cnt = bad ? 0 : __ldg(k + 1);
     const unsigned char* temp = a.temp + (size_t)b * a.rows_cap * S * 3;
-    for (int o = tid; o < S * 3; o += kThreads) {
-        int v = 0;
+    // a thread owns up to kVOut outputs of the row (o, o + 256, ...), so each weight is fetched once per tap for all of them
+    constexpr int kVOut = 4;
+    for (int o0 = tid; o0 < S * 3; o0 += kThreads * kVOut) {
+        int acc[kVOut];
+#pragma unroll
+        for (int u = 0; u < kVOut; ++u) acc[u] = 1 << (kPrecisionBits - 1);
         if (!bad) {
-            int acc = 1 << (kPrecisionBits - 1);
-            for (int t = 0; t < cnt; ++t) acc += (int)__ldg(temp + (size_t)(first + t) * S * 3 + o) * __ldg(k + 2 + t);
-            v = min(max(acc >> kPrecisionBits, 0), 255);
+            const unsigned char* col = temp + (size_t)first * S * 3 + o0;
+            for (int t = 0; t < cnt; ++t) {
+                const int wgt = __ldg(k + 2 + t);
+#pragma unroll
+                for (int u = 0; u < kVOut; ++u)
+                    if (o0 + u * kThreads < S * 3) acc[u] += (int)__ldg(col + (size_t)t * S * 3 + u * kThreads) * wgt;
+            }
         }
-        out[o] = (unsigned char)v;
-        if (a.out_px) {
-            const int xx = o / 3, c = o - xx * 3;
-            const float f = __fdiv_rn(__fsub_rn(__fmul_rn((float)v, 1.0f / 255.0f), a.mean[c]), a.std[c]);
-            a.out_px[(((size_t)b * 3 + c) * S + yy) * S + xx] = f;
+#pragma unroll
+        for (int u = 0; u < kVOut; ++u) {
+            const int o = o0 + u * kThreads;
+            if (o >= S * 3) continue;
+            const int v = bad ? 0 : min(max(acc[u] >> kPrecisionBits, 0), 255);
+            out[o] = (unsigned char)v;
+            if (a.out_px) {
+                const int xx = o / 3, c = o - xx * 3;
+                const float f = __fdiv_rn(__fsub_rn(__fmul_rn((float)v, 1.0f / 255.0f), a.mean[c]), a.std[c]);
+                a.out_px[(((size_t)b * 3 + c) * S + yy) * S + xx] = f;
+            }
         }
     }
 }
