@@ -109,14 +109,11 @@ def _lazy_crop_class():
         behaves exactly like the eager `page.crop(rect)` of reference src/_modules.py:2119."""
 
         def __init__(self, page, rect):
-            # the fields Image.__init__ sets, written once (this constructor runs once per retrieved chunk)
-            self._im = None
+            super().__init__()                     # Pillow's own field set (it differs between Pillow versions)
             self._mode = page.mode
             self._size = (rect[2] - rect[0], rect[3] - rect[1])
-            self.palette = None
-            self.info = dict(page.info) if page.info else {}
-            self.readonly = 0
-            self._exif = None
+            if page.info:
+                self.info = dict(page.info)
             self._page, self._rect = page, rect
 
         def load(self):

@@ -56,7 +56,7 @@ def main(round_tag):
         for r in rows[1:]:
             name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("rdv::", "")
             agg[name].append(float(r[-1].replace(",", "")))
-        lines.append("## launch list (`--metrics gpu__time_duration.sum`, bench.py --steps 20 --warmup 3 --no-extras; cold-cache, serialised: compare SHARES)\n")
+        lines.append("## launch list (`--metrics gpu__time_duration.sum`, bench.py --steps 20 --warmup 3 --skip-e2e; cold-cache, serialised: compare SHARES)\n")
         lines.append("| kernel | launches | mean us | share of my-kernel time |\n|---|---|---|---|")
         total = sum(sum(v) for v in agg.values())
         for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
