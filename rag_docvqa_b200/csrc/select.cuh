@@ -31,9 +31,6 @@ struct SelectArgs {
 struct BlockSync {       // whole block
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
-struct ConsumerSync {    // the 256 consumer threads of the TMA kernel (named barrier 1)
-    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-};
 
 // warp-wide max of u64 keys: redux.sync.max.u32 on the high halves, then on the low halves of the lanes
 // that hold the winning high half.  All-zero (no key) stays zero.

@@ -135,10 +135,6 @@ def lazy_crop(page, rect):
     return _LazyCrop(page, tuple(rect))
 
 
-def _eager_crop(page, rect):
-    return page.crop(rect)
-
-
 _CROP_POOL = None
 
 
