@@ -345,6 +345,48 @@ typedef struct rdv_visual_args {
 RDV_API int rdv_visual_pack(const rdv_pagestore* ps, const rdv_visual_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Retrieved image crops -> Pix2Struct flattened patches (SURVEY.md section 8 row a12, Pix2Struct half).
+ *
+ * Replaces what src/custom_pix2struct_processor.py does with the crops VisualRetriever returns (call site
+ * src/RAGPix2Struct.py:221): per-image normalize (:175-196), extract_flattened_patches_single (:33-95: patch grid from
+ * the patch budget, anti-aliased bilinear resize = torch F.interpolate(antialias=True), patch x patch patches flattened
+ * pixel-major / channel-minor behind (row id, column id)), extract_multi_image_flattened_patches (:97-132: equal budget
+ * per image, row ids continue across images, zero padding) and the attention mask (:225).  The header text that
+ * render_header draws onto the first image (:214) is out of scope: an image is a crop of a page in the store.
+ *
+ * rdv_p2s_img (one per image, HOST-planned and uploaded; `page` indexes the store's page_wh / page_off entries):
+ *   crop rectangle x0,y0,x1,y1 (black outside the page), patch grid rows x cols, `kept` = min(rows*cols, budget),
+ *   out_start = first output row of the image within its document, row_offset = row ids already used by the
+ *   document's earlier images, temp_off = offset (floats) of its horizontally resized rows in `temp`
+ *   ((y1-y0) * cols*patch * 3 floats).
+ * rdv_p2s_args: images[n_images], stats (2 floats per image: workspace), temp, doc_total[n_docs] = output rows used by
+ *   each document, out (n_docs, max_total, 2 + patch*patch*3) fp32, mask (n_docs, max_total) fp32;
+ *   max_rw / max_rwh = largest resized width / resized width*height over the images (launch bounds).
+ * fp32 like the reference; results agree with torch's CPU kernel to float rounding (tests state the tolerance).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rdv_p2s_img {
+    int32_t doc, page;
+    int32_t x0, y0, x1, y1;
+    int32_t rows, cols, kept, out_start, row_offset, reserved;
+    int64_t temp_off;
+} rdv_p2s_img;
+
+typedef struct rdv_p2s_args {
+    const rdv_p2s_img* images;
+    int32_t n_images, n_docs;
+    int32_t max_total, patch;
+    int32_t do_normalize, max_rw;
+    int64_t max_rwh;
+    float* stats;
+    float* temp;
+    const int32_t* doc_total;
+    float* out;
+    float* mask;
+} rdv_p2s_args;
+
+RDV_API int rdv_pix2struct_patches(const rdv_pagestore* ps, const rdv_p2s_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * bf16 tensor-core scoring (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
  *
  * rdv_rows_to_bf16      fp32 (rows, d) -> bf16 copy, optionally L2-normalised first (F.normalize,

@@ -511,3 +511,72 @@ def visual_input(pages, rects, page_of, out_size: int = 224, kind: int = PIL_BIC
     u8 = pil_resize_u8(concat_grid(pages, rects, page_of), out_size, out_size, kind)
     px = (u8.astype(np.float32) * np.float32(1.0 / 255.0) - np.asarray(mean, np.float32)) / np.asarray(std, np.float32)
     return u8, np.ascontiguousarray(px.transpose(2, 0, 1))
+
+
+# --------------------------------------------------------------------------------------
+# a12, Pix2Struct half: retrieved image crops -> flattened patches for the Pix2Struct generator
+#   reference: src/custom_pix2struct_processor.py:33-132 (extract_flattened_patches_single,
+#   extract_multi_image_flattened_patches), :175-196 (per-image normalize), :225 (attention mask);
+#   called from src/RAGPix2Struct.py:221.  Third-party pieces: torch.nn.functional.interpolate(bilinear,
+#   antialias=True) (called directly below) and transformers==4.49.0 torch_extract_patches (unfold + permute,
+#   restated in _extract_patches; the installed transformers 5.x has the same algorithm with a batch dimension).
+#   render_header (:214, text drawn onto the first image) is CPU text rendering and out of scope: callers pass the
+#   images as they are after that step.
+# --------------------------------------------------------------------------------------
+def pix2struct_normalize(image: np.ndarray) -> np.ndarray:
+    """CustomPix2StructImageProcessor.normalize (:175-196): whole-image mean / std, std floored at 1/sqrt(#elements)."""
+    import math
+    if image.dtype == np.uint8:
+        image = image.astype(np.float32)
+    mean = np.mean(image)
+    std = np.std(image)
+    adjusted = max(std, 1.0 / math.sqrt(np.prod(image.shape)))
+    return ((image - mean) / adjusted).astype(np.float32)          # transformers.image_transforms.normalize
+
+
+def _extract_patches(image: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
+    """transformers 4.49 torch_extract_patches: (C, H, W) -> (1, H/ph, W/pw, ph*pw*C), pixel-major / channel-minor."""
+    x = image.unsqueeze(0)
+    p = F.unfold(x, (ph, pw), stride=(ph, pw))
+    p = p.reshape(x.size(0), x.size(1), ph, pw, -1)
+    p = p.permute(0, 4, 2, 3, 1).reshape(x.size(2) // ph, x.size(3) // pw, x.size(1) * ph * pw)
+    return p.unsqueeze(0)
+
+
+def pix2struct_patches_single(image: np.ndarray, max_patches: int, ph: int = 16, pw: int = 16, row_offset: int = 0):
+    """extract_flattened_patches_single(..., pad=False) for an (H, W, C) float image (:33-95)."""
+    import math
+    img = torch.from_numpy(np.ascontiguousarray(image.transpose(2, 0, 1)))                 # channels first (:45)
+    H, W = img.shape[1], img.shape[2]
+    scale = math.sqrt(max_patches * (ph / H) * (pw / W))                                    # :52
+    rows = max(min(math.floor(scale * H / ph), max_patches), 1)                             # :53
+    cols = max(min(math.floor(scale * W / pw), max_patches), 1)                             # :54
+    rh, rw = max(rows * ph, 1), max(cols * pw, 1)
+    img = F.interpolate(img.unsqueeze(0), size=(rh, rw), mode="bilinear", align_corners=False, antialias=True).squeeze(0)
+    patches = _extract_patches(img, ph, pw)
+    r, c, depth = patches.shape[1], patches.shape[2], patches.shape[3]
+    patches = patches.reshape(r * c, depth)
+    row_ids = torch.arange(r).reshape(r, 1).repeat(1, c).reshape(r * c, 1) + 1 + row_offset   # :79-81
+    col_ids = torch.arange(c).reshape(1, c).repeat(r, 1).reshape(r * c, 1) + 1
+    result = torch.cat([row_ids.to(torch.float32), col_ids.to(torch.float32), patches], dim=-1)
+    return result[:max_patches].numpy(), int(row_ids.max().item())                           # :93-95 (pad=False)
+
+
+def pix2struct_patches(images: Sequence[np.ndarray], max_total_patches: int = 2048, ph: int = 16, pw: int = 16,
+                       normalize: bool = True):
+    """extract_multi_image_flattened_patches (:97-132) after the per-image normalize (:220), and the attention mask
+    of preprocess (:225).  images: (H, W, 3) uint8 / float arrays.  Returns ((max_total, 2 + ph*pw*3) f32, (max_total,) f32)."""
+    if len(images) == 0:
+        raise ValueError("No images provided.")                                              # :109
+    per = max_total_patches // len(images)                                                   # :110
+    out, row_offset = [], 0
+    for img in images:
+        x = pix2struct_normalize(img) if normalize else np.asarray(img, dtype=np.float32)
+        p, row_offset = pix2struct_patches_single(x, per, ph, pw, row_offset)
+        out.append(p)
+    cat = np.concatenate(out, axis=0)
+    if cat.shape[0] < max_total_patches:
+        cat = np.concatenate([cat, np.zeros((max_total_patches - cat.shape[0], cat.shape[1]), dtype=cat.dtype)], axis=0)
+    else:
+        cat = cat[:max_total_patches]
+    return cat, (cat.sum(axis=-1) != 0).astype(np.float32)

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Struc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -54,6 +54,13 @@ class VisualArgsStruct(Structure):
                 ("coeff_v", c_void_p), ("temp", c_void_p), ("out_u8", c_void_p), ("out_px", c_void_p), ("status", c_void_p)]
 
 
+class P2SArgsStruct(Structure):
+    """Mirror of `rdv_p2s_args` (include/rdv.h)."""
+    _fields_ = [("images", c_void_p), ("n_images", c_int32), ("n_docs", c_int32), ("max_total", c_int32), ("patch", c_int32),
+                ("do_normalize", c_int32), ("max_rw", c_int32), ("max_rwh", c_int64), ("stats", c_void_p), ("temp", c_void_p),
+                ("doc_total", c_void_p), ("out", c_void_p), ("mask", c_void_p)]
+
+
 # name -> (restype, argtypes); tests/test_abi.py checks this table against include/rdv.h
 SIGNATURES = {
     "rdv_abi_version": (c_int32, []),
@@ -89,6 +96,7 @@ SIGNATURES = {
     "rdv_maxsim_tf32x3_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                        c_void_p, c_void_p, c_void_p]),
     "rdv_visual_pack": (c_int32, [POINTER(PageStoreStruct), POINTER(VisualArgsStruct), c_void_p]),
+    "rdv_pix2struct_patches": (c_int32, [POINTER(PageStoreStruct), POINTER(P2SArgsStruct), c_void_p]),
     "rdv_gather_vt5_inputs": (c_int32, [POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
 }
 

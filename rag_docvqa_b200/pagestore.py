@@ -73,6 +73,7 @@ class PageStore:
         self.struct.page_wh = base + o_wh
         self.struct.page_off = base + o_off
         self.struct.pixels = self.pixels.data_ptr()
+        self.doc_page_off_host = doc_page_off
         self.max_w = int(wh[:, 0].max()) if P else 1
         self.max_h = int(wh[:, 1].max()) if P else 1
         self.n_pages, self.n_unique, self.bytes = P, len(unique), total
@@ -134,3 +135,75 @@ class VisualPlan:
 
     def result(self) -> VisualInputs:
         return VisualInputs(self.t["out_u8"], self.t["out_px"], self.t["status"])
+
+
+# ---- Pix2Struct flattened patches (SURVEY.md section 8 row a12, Pix2Struct half) -------------------------------------
+P2S_IMG_DTYPE = np.dtype([("doc", "<i4"), ("page", "<i4"), ("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"),
+                          ("rows", "<i4"), ("cols", "<i4"), ("kept", "<i4"), ("out_start", "<i4"), ("row_offset", "<i4"),
+                          ("reserved", "<i4"), ("temp_off", "<i8")])      # rdv_p2s_img, 56 bytes
+
+
+class Pix2StructInputs(NamedTuple):
+    flattened_patches: torch.Tensor     # (B, max_total_patches, 2 + patch*patch*3) fp32
+    attention_mask: torch.Tensor        # (B, max_total_patches) fp32
+
+
+def plan_pix2struct(crops: Sequence[Sequence[Sequence[int]]], doc_page_off: np.ndarray, max_total_patches: int, patch: int):
+    """The per-image plan of extract_multi_image_flattened_patches (src/custom_pix2struct_processor.py:97-132, :52-57):
+    patch budget per image, patch grid from the budget (Python float arithmetic, as the reference), output offsets,
+    row-id offsets.  crops[b] = [(page_in_doc, x0, y0, x1, y1), ...]."""
+    recs, doc_total, temp_off = [], [], 0
+    for b, doc in enumerate(crops):
+        if len(doc) == 0:
+            raise ValueError("No images provided.")                                  # :109
+        per = max_total_patches // len(doc)                                           # :110
+        out_start, row_offset = 0, 0
+        for (p, x0, y0, x1, y1) in doc:
+            w, h = int(x1) - int(x0), int(y1) - int(y0)
+            if w <= 0 or h <= 0:
+                raise ValueError("document %d: empty crop %r" % (b, (x0, y0, x1, y1)))
+            scale = math.sqrt(per * (patch / h) * (patch / w))                        # :52
+            rows = max(min(math.floor(scale * h / patch), per), 1)                    # :53
+            cols = max(min(math.floor(scale * w / patch), per), 1)                    # :54
+            kept = min(rows * cols, per)
+            recs.append((b, int(doc_page_off[b]) + int(p), int(x0), int(y0), int(x1), int(y1), rows, cols, kept, out_start,
+                         row_offset, 0, temp_off))
+            out_start += kept
+            row_offset += rows                                                        # int(row_ids.max()) (:95)
+            temp_off += h * cols * patch * 3
+        doc_total.append(out_start)
+    return np.array(recs, dtype=P2S_IMG_DTYPE), np.asarray(doc_total, dtype=np.int32), temp_off
+
+
+def _pack_pix2struct(self, crops, max_total_patches: int = 2048, patch: int = 16, normalize: bool = True) -> Pix2StructInputs:
+    """Crops of the store's pages -> (flattened_patches, attention_mask) on the device (rdv_pix2struct_patches).
+    crops[b] = [(page_in_doc, x0, y0, x1, y1), ...] in the order the reference would pass the images."""
+    dev = self.device
+    if len(crops) != self.B:
+        raise ValueError("pix2struct pack: %d documents of crops, store has %d" % (len(crops), self.B))
+    images, doc_total, temp_floats = plan_pix2struct(crops, self.doc_page_off_host, max_total_patches, patch)
+    depth = 2 + patch * patch * 3
+    blob = torch.empty(images.nbytes + doc_total.nbytes + 16, dtype=torch.uint8, pin_memory=True)
+    raw = blob.numpy()
+    raw[:images.nbytes] = images.view(np.uint8).reshape(-1)
+    o_tot = (images.nbytes + 15) // 16 * 16
+    raw[o_tot:o_tot + doc_total.nbytes] = doc_total.view(np.uint8)
+    small = blob.to(dev, non_blocking=True)
+    t = dict(small=small, stats=torch.empty((max(len(images), 1), 2), dtype=torch.float32, device=dev),
+             temp=torch.empty((max(temp_floats, 1),), dtype=torch.float32, device=dev),
+             out=torch.empty((self.B, max_total_patches, depth), dtype=torch.float32, device=dev),
+             mask=torch.empty((self.B, max_total_patches), dtype=torch.float32, device=dev))
+    a = _lib.P2SArgsStruct()
+    a.images, a.n_images, a.n_docs = small.data_ptr(), len(images), self.B
+    a.max_total, a.patch, a.do_normalize = max_total_patches, patch, 1 if normalize else 0
+    a.max_rw = int((images["cols"] * patch).max()) if len(images) else 0
+    a.max_rwh = int((images["cols"].astype(np.int64) * images["rows"] * patch * patch).max()) if len(images) else 0
+    a.stats, a.temp, a.doc_total = t["stats"].data_ptr(), t["temp"].data_ptr(), small.data_ptr() + o_tot
+    a.out, a.mask = t["out"].data_ptr(), t["mask"].data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.rdv_pix2struct_patches(ctypes.byref(self.struct), ctypes.byref(a), _stream_ptr(dev)))
+    self._p2s_keepalive = t
+    return Pix2StructInputs(t["out"], t["mask"])
+
+
+PageStore.pack_pix2struct = _pack_pix2struct

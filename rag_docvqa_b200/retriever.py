@@ -502,19 +502,19 @@ class VisualRetriever:
         n_cols = len(patches_matrix[0]) if n_rows > 0 else 0
         return _surrounding_cells(patch_coord[0], patch_coord[1], n_rows, n_cols, include_surroundings)
 
-    def _get_top_k(self, similarities, patches_flatten_indices, patches_matrix_list, patches_xyxy, images):
+    def _decode_rects(self, similarities, patches_flatten_indices, patches_matrix_list, patches_xyxy):
+        """Top-k on the device, then the reference's integer decode on the host (src/_modules.py:2399-2448): per
+        document the list of (group, merged rectangle) in sorted order, and the sorted group ids."""
         bs = len(similarities)
-        if bs == 0:
-            return [], []
         # a document without strips still carries a (1,) dummy score (ImageEncoder returns zeros(1,2048,768),
         # src/_modules.py:1663-1664): it must not contribute hits  (src/_modules.py:2403-2406)
         idx, _val, cnt = F.topk_segments([_to_device(s_b, self.device) for s_b in similarities], int(self.k))
         hits = Retriever._hits_to_host(idx, cnt)
-        crops_all, pages_all = [], []
+        rects_all, pages_all = [], []
         for b in range(bs):
             flat = np.asarray(patches_flatten_indices[b])
             if len(flat) == 0:
-                crops_all.append([])
+                rects_all.append([])
                 pages_all.append([])
                 continue
             cells = set()
@@ -529,13 +529,32 @@ class VisualRetriever:
             by_group: Dict[int, list] = {}
             for (g, r, c) in cells:
                 by_group.setdefault(g, []).append(list(patches_xyxy[b][g][r]))
-            crops = []
+            rects = []
             for g in sorted(by_group):
                 for rect in _merge_rectangles(by_group[g]):
-                    crops.append(images[b][g].crop(tuple(rect)))   # src/_modules.py:2381
-            crops_all.append(crops)
+                    rects.append((g, tuple(rect)))
+            rects_all.append(rects)
             pages_all.append(sorted(int(g) for g in by_group))
+        return rects_all, pages_all
+
+    def _get_top_k(self, similarities, patches_flatten_indices, patches_matrix_list, patches_xyxy, images):
+        if len(similarities) == 0:
+            return [], []
+        rects_all, pages_all = self._decode_rects(similarities, patches_flatten_indices, patches_matrix_list, patches_xyxy)
+        crops_all = [[images[b][g].crop(rect) for (g, rect) in rects] for b, rects in enumerate(rects_all)]   # src/_modules.py:2381
         return crops_all, pages_all
+
+    def retrieve_packed(self, patch_embeddings, question_embeddings, patches_flatten_indices, patches_matrix_list,
+                        patches_xyxy, pages, max_total_patches: int = 2048, patch: int = 16, normalize: bool = True):
+        """B200-native fast path of the visual route: MaxSim + top-k on the device, the integer decode on the host, and
+        the retrieved crops turned into the Pix2Struct generator's flattened patches on the device from a `PageStore`
+        (what src/custom_pix2struct_processor.py:97-132, 175-196, 225 build from PIL crops; the header text of
+        render_header is not drawn).  Returns (Pix2StructInputs, page ids); documents without a hit are not allowed,
+        as in the reference (extract_multi_image_flattened_patches raises on an empty list)."""
+        similarities = self._get_similarities(patch_embeddings, question_embeddings)
+        rects_all, pages_all = self._decode_rects(similarities, patches_flatten_indices, patches_matrix_list, patches_xyxy)
+        crops = [[(g,) + tuple(int(round(v)) for v in rect) for (g, rect) in rects] for rects in rects_all]   # PIL crop rounds its box
+        return pages.pack_pix2struct(crops, max_total_patches=max_total_patches, patch=patch, normalize=normalize), pages_all
 
     def retrieve(self, patch_embeddings: List[torch.Tensor], question_embeddings: torch.Tensor,
                  patches_flatten_indices: list, patches_matrix_list: list, patches_xyxy: list,

@@ -246,3 +246,15 @@ def test_concat_grid_against_live_reference():
         patches = [Image.fromarray(pages[p], "RGB").crop(r) for r, p in zip(rects, page_of)]
         ref = np.asarray(utils.concatenate_patches(patches, mode="grid").convert("RGB"))
         np.testing.assert_array_equal(R.concat_grid(pages, rects, page_of), ref)
+
+
+def test_pix2struct_patches_match_reference_golden(golden_dir):
+    """Frozen outputs of the reference's CustomPix2StructImageProcessor.normalize + extract_multi_image_flattened_patches."""
+    z = np.load(os.path.join(golden_dir, "pix2struct_patches.npz"))
+    for b in range(int(z["docs"])):
+        imgs = [z["img_%d_%d" % (b, i)] for i in range(int(z["n_%d" % b]))]
+        flat, mask = R.pix2struct_patches(imgs, 128)
+        np.testing.assert_array_equal(flat, z["flat_%d" % b])
+        np.testing.assert_array_equal(mask, z["mask_%d" % b])
+    with pytest.raises(ValueError):
+        R.pix2struct_patches([], 128)
