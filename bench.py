@@ -906,6 +906,22 @@ def run_visual(args):
         from oracle import ref_restated as R
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
+        if not args.no_extras:
+            # a12, Pix2Struct half: the 5 retrieved strips of every document -> (2048, 770) flattened patches on the device
+            from rag_docvqa_b200.pagestore import PageStore
+            rng = np.random.RandomState(7)
+            strip_pages = [[Image.fromarray(rng.randint(0, 256, (220, 850, 3)).astype(np.uint8), "RGB") for _ in range(k)] for _ in range(B)]
+            pstore = PageStore.from_images(strip_pages, dev)
+            crops = [[(g, 0, 0, 850, 220) for g in range(k)] for _ in range(B)]
+            for _ in range(2):
+                pstore.pack_pix2struct(crops)
+            ms_p = timed_loop(lambda i: pstore.pack_pix2struct(crops), 10, torch.cuda.synchronize) / 10
+            arrs = [np.asarray(im) for im in strip_pages[0]]
+            best_p, _ = time_cpu(lambda: R.pix2struct_patches(arrs, 2048), 2.0, min_reps=2)
+            line["extras"] = {"pix2struct_patches": {
+                "what": "%d documents x %d strips of 850 x 220 -> (2048, 770) flattened patches + mask (plan on the host, "
+                        "4 kernels)" % (B, k), "ms_per_batch": ms_p, "documents_per_s": B / ms_p * 1e3,
+                "cpu_reference_ms_per_document": best_p * 1e3, "cpu_documents_per_s": 1.0 / best_p}}
         n_cpu = 5
         qc, pc = q[0:1].cpu(), patches[0][:n_cpu].cpu()
         best, reps = time_cpu(lambda: R.late_interaction(qc, pc), min(args.cpu_seconds, 10.0), min_reps=1)
