@@ -103,9 +103,14 @@ SIGNATURES = {
 
 def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            "%s not found: build it with `python -m rag_docvqa_b200.build` (needs nvcc). "
-            "rag_docvqa_b200 has no CPU fallback." % LIB_PATH)
+        # a fresh checkout: compile the CUDA sources once (nvcc); without a compiler there is nothing to fall back to
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as exc:
+            raise ImportError(
+                "%s not found and could not be built (%s): run `python -m rag_docvqa_b200.build` (needs nvcc). "
+                "rag_docvqa_b200 has no CPU fallback." % (LIB_PATH, exc))
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError if the .so is stale
