@@ -17,10 +17,11 @@
 //    fused = 0: scores only; the selection runs in topk_segments_kernel / inside the gather kernel, so no
 //    device-scope fence or atomic sits on the streaming path.
 //  * score_tma_kernel (d in {128,256,384,512,768,1024}): persistent, one block per SM owning a contiguous
-//    run of tiles.  A producer warp streams the tiles into per-warp shared-memory rings with 1-D bulk
-//    async copies (cp.async.bulk -> SASS UBLKCP, completion on mbarriers), ~190 KB in flight per SM
-//    independent of occupancy; each of the 8 consumer warps owns its ring (no cross-warp barrier), reads
-//    rows with conflict-free LDS.128 and produces dot and squared norm from the same registers.
+//    run of tiles; every warp owns a private shared-memory ring and ITS OWN mbarriers, requests its tiles with
+//    1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) and consumes them with conflict-free LDS.128 -- no
+//    producer warp and no cross-warp synchronisation.  192 KB in flight per SM independent of occupancy and of
+//    registers.  Measured on B200: 7.05 TB/s at C3 (LDG kernel 7.2), 12.8 us at C2 (LDG 6.9 us: a 32 MB batch
+//    is launch/latency-bound and the ring adds a descriptor -> copy -> wait chain), so AUTO stays on LDG.
 //
 // Selection (select.cuh): k rounds of a block-wide arg-max over packed (score, ~index) u64 keys, which
 // makes "descending score, lowest index first" one integer compare.
@@ -28,7 +29,7 @@
 
 namespace rdv {
 
-constexpr int kTmaThreads = kScoreThreads + 32;   // + 1 producer warp
+constexpr int kTmaThreads = kScoreThreads;        // 8 self-serving warps
 constexpr int kTmaMaxStages = 4;                  // per consumer warp
 constexpr int kTmaRingBytes = 192 * 1024;         // all warps
 
@@ -218,98 +219,104 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Self-service ring: every warp owns S stages and their mbarriers, issues its OWN bulk copies (lane 0) and consumes
+// them; no producer warp, no cross-warp synchronisation.  A warp's tiles are li = warp, warp + 8, ... of the block's
+// contiguous run; the first S are requested before anything is consumed, and a stage is refilled as soon as the
+// warp has read it.  (The round-1 kernel had one producer lane feeding all eight rings: at ~1000 cycles per 12 KB
+// copy it was the limiter -- 2.6 TB/s at C2, 3.2-4.2 TB/s at C3.)
 template <int VPL>
 __global__ void __launch_bounds__(kTmaThreads, 1) score_tma_kernel(const ScoreParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[kScoreWarps][kTmaMaxStages];
-    __shared__ __align__(8) uint64_t s_empty[kScoreWarps][kTmaMaxStages];
+    __shared__ __align__(8) uint64_t s_full[kTmaThreads / 32][kTmaMaxStages];
 
     constexpr int D4 = 32 * VPL;                       // float4 per row
     constexpr uint32_t kRowBytes = D4 * 16;
+    constexpr int NW = kTmaThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.stages;
     const uint32_t stage_bytes = (uint32_t)p.tile_rows * kRowBytes;
 
-    // contiguous run of tiles for this block; local tile li belongs to consumer warp li % 8
+    pdl_launch_dependents();
+    pdl_wait();
+
+    // contiguous run of tiles for this block; local tile li belongs to warp li % NW
     const int G = gridDim.x;
     const int t0 = (int)((long long)blockIdx.x * p.total_tiles / G);
     const int t1 = (int)((long long)(blockIdx.x + 1) * p.total_tiles / G);
     const int ntiles = t1 - t0;
+    const int mine_n = ntiles > warp ? (ntiles - warp + NW - 1) / NW : 0;      // tiles of this warp
 
-    if (tid == 0) {
-        for (int w = 0; w < kScoreWarps; ++w)
-            for (int s = 0; s < S; ++s) { mbar_init(&s_full[w][s], 1); mbar_init(&s_empty[w][s], 1); }
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&s_full[warp][s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
+    unsigned char* ring = smem_raw + (size_t)warp * S * stage_bytes;
 
-    if (warp == kScoreWarps) {
-        // ===== producer warp: descriptors fetched 32 at a time, lane 0 issues the bulk copies =====
-        for (int base = 0; base < ntiles; base += 32) {
-            rdv_tile_desc mine = {};
-            if (base + lane < ntiles) mine = p.tiles[t0 + base + lane];
-            const int cnt = min(32, ntiles - base);
-            for (int j = 0; j < cnt; ++j) {
-                const void* src = reinterpret_cast<const void*>(__shfl_sync(0xffffffffu, (unsigned long long)mine.src, j));
-                const int rows = __shfl_sync(0xffffffffu, mine.rows, j);
-                if (lane == 0) {
-                    const int li = base + j, w = li & (kScoreWarps - 1), u = li >> 3;
-                    const int st = u % S;
-                    const uint32_t ph = (uint32_t)(u / S) & 1u;
-                    mbar_wait(&s_empty[w][st], ph ^ 1);
-                    const uint32_t bytes = (uint32_t)rows * kRowBytes;
-                    mbar_expect_tx(&s_full[w][st], bytes);
-                    bulk_g2s(smem_raw + ((size_t)w * S + st) * stage_bytes, src, bytes, &s_full[w][st]);
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== consumer warps: each owns its ring; no cross-warp synchronisation =====
     int cur_doc = -1;
     float4 qv[VPL];
     float ss_q = 0.f;
-    for (int ubase = 0; warp + 8 * ubase < ntiles; ubase += 32) {
-        // this warp's next 32 tile descriptors, one per lane
-        rdv_tile_desc mine = {};
-        const int my_li = warp + 8 * (ubase + lane);
-        if (my_li < ntiles) mine = p.tiles[t0 + my_li];
-        for (int j = 0; j < 32; ++j) {
-            const int u = ubase + j;
-            if (warp + 8 * u >= ntiles) break;
-            const int doc = __shfl_sync(0xffffffffu, mine.doc, j);
-            const int rows = __shfl_sync(0xffffffffu, mine.rows, j);
-            const long long sims_off = __shfl_sync(0xffffffffu, mine.sims_off, j);
-            if (doc != cur_doc) {                          // question vector: issued before waiting on the copy
-                const float4* Q = reinterpret_cast<const float4*>(p.q) + (size_t)doc * D4;
+    rdv_tile_desc next = {};                             // descriptors: 32 at a time, one per lane, for issue and for use
+    rdv_tile_desc mine = {};
+    int issued = 0;
+    auto issue = [&](int u) {                            // lane 0: request local tile u of this warp into stage u % S
+        const int j = u & 31;
+        const void* src = reinterpret_cast<const void*>(__shfl_sync(0xffffffffu, (unsigned long long)next.src, j));
+        const int rows = __shfl_sync(0xffffffffu, next.rows, j);
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)rows * kRowBytes;
+            uint64_t* bar = &s_full[warp][u % S];
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(ring + (size_t)(u % S) * stage_bytes, src, bytes, bar);
+        }
+    };
+    auto load_descs = [&](int ubase) {                   // descriptors of local tiles ubase .. ubase + 31
+        rdv_tile_desc d = {};
+        const int li = warp + NW * (ubase + lane);
+        if (ubase + lane < mine_n) d = p.tiles[t0 + li];
+        return d;
+    };
+    next = load_descs(0);
+    for (; issued < mine_n && issued < S; ++issued) issue(issued);             // prologue (all within the first 32)
+
+    for (int u = 0; u < mine_n; ++u) {
+        if ((u & 31) == 0) mine = (u == 0) ? next : load_descs(u);
+        const int j = u & 31;
+        const int doc = __shfl_sync(0xffffffffu, mine.doc, j);
+        const int rows = __shfl_sync(0xffffffffu, mine.rows, j);
+        const long long sims_off = __shfl_sync(0xffffffffu, mine.sims_off, j);
+        if (doc != cur_doc) {                              // question vector: issued before waiting on the copy
+            const float4* Q = reinterpret_cast<const float4*>(p.q) + (size_t)doc * D4;
 #pragma unroll
-                for (int i = 0; i < VPL; ++i) qv[i] = __ldg(Q + lane + 32 * i);
-                ss_q = sumsq<VPL>(qv);
-                cur_doc = doc;
-            }
-            const int st = u % S;
-            const uint32_t ph = (uint32_t)(u / S) & 1u;
-            mbar_wait(&s_full[warp][st], ph);
-            const float4* se = reinterpret_cast<const float4*>(smem_raw + ((size_t)warp * S + st) * stage_bytes);
-            float* __restrict__ out = p.sims + sims_off;
-            for (int r = 0; r < rows; r += 2) {
-                const bool two = r + 1 < rows;
-                float4 e0[VPL], e1[VPL];
+            for (int i = 0; i < VPL; ++i) qv[i] = __ldg(Q + lane + 32 * i);
+            ss_q = sumsq<VPL>(qv);
+            cur_doc = doc;
+        }
+        const int st = u % S;
+        mbar_wait(&s_full[warp][st], (uint32_t)(u / S) & 1u);
+        const float4* se = reinterpret_cast<const float4*>(ring + (size_t)st * stage_bytes);
+        float* __restrict__ out = p.sims + sims_off;
+        for (int r = 0; r < rows; r += 2) {
+            const bool two = r + 1 < rows;
+            float4 e0[VPL], e1[VPL];
 #pragma unroll
-                for (int i = 0; i < VPL; ++i) {
-                    e0[i] = se[(size_t)r * D4 + lane + 32 * i];
-                    e1[i] = two ? se[(size_t)(r + 1) * D4 + lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                float d0, s0, d1, s1;
-                fma_row<VPL>(e0, qv, d0, s0);
-                fma_row<VPL>(e1, qv, d1, s1);
-                d0 = warp_sum(d0); s0 = warp_sum(s0); d1 = warp_sum(d1); s1 = warp_sum(s1);
-                if (lane == 0) out[r] = cosine(d0, s0, ss_q);
-                if (lane == 1 && two) out[r + 1] = cosine(d1, s1, ss_q);
+            for (int i = 0; i < VPL; ++i) {
+                e0[i] = se[(size_t)r * D4 + lane + 32 * i];
+                e1[i] = two ? se[(size_t)(r + 1) * D4 + lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[warp][st]);   // the producer may overwrite this stage
+            float d0, s0, d1, s1;
+            fma_row<VPL>(e0, qv, d0, s0);
+            fma_row<VPL>(e1, qv, d1, s1);
+            d0 = warp_sum(d0); s0 = warp_sum(s0); d1 = warp_sum(d1); s1 = warp_sum(s1);
+            if (lane == 0) out[r] = cosine(d0, s0, ss_q);
+            if (lane == 1 && two) out[r + 1] = cosine(d1, s1, ss_q);
+        }
+        __syncwarp();                                      // every lane has consumed the stage
+        if (issued < mine_n) {                             // refill it with this warp's tile u + S
+            if ((issued & 31) == 0) next = load_descs(issued);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before the async-proxy write
+            issue(issued);
+            ++issued;
         }
     }
 }
@@ -337,9 +344,11 @@ static int launch_ldg(const ScoreParams& p, cudaStream_t stream) {
     return RDV_OK;
 }
 
-// rows per stage and stages per warp for the TMA kernel (~12 KB stages, 24 KB per consumer warp)
-static void tma_plan(int d, int* tile_rows, int* stages) {
-    int rows = (12 * 1024) / (d * 4);
+// rows per stage and stages per warp for the TMA kernel: 24 KB per warp, as ONE 24 KB stage for large batches
+// (measured at C3: 7.05 TB/s, vs 6.5 TB/s with two 12 KB stages) and two 12 KB stages for small ones
+static void tma_plan(int d, int* tile_rows, int* stages, int64_t total_rows = 0) {
+    const bool large = total_rows * (int64_t)d * 4 >= (256ll << 20);
+    int rows = ((large ? 24 : 12) * 1024) / (d * 4);
     rows = rows < 1 ? 1 : (rows > 16 ? 16 : rows);
     int s = (kTmaRingBytes / kScoreWarps) / (rows * d * 4);
     s = s > kTmaMaxStages ? kTmaMaxStages : s;
@@ -438,15 +447,15 @@ using namespace rdv;
 extern "C" int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows) {
     RDV_REQUIRE(algo_out && tile_rows, RDV_E_INVALID, "score_plan: null output");
     RDV_REQUIRE(algo >= RDV_SCORE_AUTO && algo <= RDV_SCORE_LDG_FUSED, RDV_E_INVALID, "score_plan: unknown algo %d", algo);
-    // measured on B200 (profiles/): the LDG streaming kernel leads at every size (C2 3.2 TB/s, C3 7.1 TB/s vs
-    // 2.6 / 3.2 TB/s for the TMA ring), so AUTO picks it; RDV_SCORE_TMA stays selectable
+    // measured on B200 (profiles/, scripts/probe_tma.py): the LDG streaming kernel leads at every size (C2 6.9 us vs
+    // 12.8 us, C3 7.2 vs 7.05 TB/s for the self-service TMA ring), so AUTO picks it; RDV_SCORE_TMA stays selectable
     if (algo == RDV_SCORE_AUTO) algo = RDV_SCORE_LDG;
     RDV_REQUIRE(algo != RDV_SCORE_TMA || tma_supported(d), RDV_E_INVALID,
                 "score_plan: the TMA kernel supports d in {128,256,384,512,768,1024}, got %d", d);
     *algo_out = algo;
     if (algo == RDV_SCORE_TMA) {
         int stages = 0;
-        tma_plan(d, tile_rows, &stages);
+        tma_plan(d, tile_rows, &stages, total_rows);
     } else {
         // one block per tile: >= ~8 tiles per SM on small batches so the hardware scheduler balances ragged docs
         const int64_t want_tiles = (int64_t)sm_count() * 8;
