@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
         extern __shared__ float4 smem_dyn[];
         __shared__ unsigned long long s_red[kScoreWarps];
         SelectArgs sel;
-        sel.k = k; sel.cache_floats = a.max_rows < kMaxCacheFloats ? a.max_rows : kMaxCacheFloats;
+        sel.k = k; sel.cache_floats = cache_floats_for(a.max_rows, k, 16 * kScoreThreads);
         sel.topk_idx = a.topk_idx; sel.topk_val = a.topk_val; sel.topk_cnt = a.topk_cnt; sel.doc_done = nullptr;
         sel.smem_idx = s_hit;
-        select_topk(sel, b, a.sims + c0, n_doc, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
+        select_topk<16>(sel, b, a.sims + c0, n_doc, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
         __syncthreads();
     } else if (tid < k) {
         s_hit[tid] = a.topk_idx[(size_t)b * k + tid];
@@ -359,11 +359,11 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
     if (args->sims) {
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(gather_vt5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(gather_vt5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gather_vt5)");
             attr_set = true;
         }
-        smem = (size_t)(args->max_rows < kMaxCacheFloats ? args->max_rows : kMaxCacheFloats) * sizeof(float) + 16;
+        smem = (size_t)(cache_floats_for(args->max_rows, args->k, 16 * kScoreThreads)) * sizeof(float) + 16;
     }
     cudaError_t le = launch_pdl(kPdlSelect, gather_vt5_kernel, dim3(ds->B), dim3(kGatherThreads), smem,
                                 static_cast<cudaStream_t>(stream), P);

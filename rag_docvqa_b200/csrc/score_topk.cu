@@ -74,7 +74,7 @@ __device__ __forceinline__ void publish_rows(const ScoreParams& p, int b, int ro
         __threadfence();
     }
     sync();
-    if (*s_last) select_topk(p.sel, b, p.sims + p.row_off[b], doc_rows, cache, s_red, sync);
+    if (*s_last) select_topk<16>(p.sel, b, p.sims + p.row_off[b], doc_rows, cache, s_red, sync);
 }
 
 template <int VPL>
@@ -328,7 +328,7 @@ static int launch_ldg(const ScoreParams& p, cudaStream_t stream) {
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(score_ldg_kernel<VPL, ROWS, MINB, true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_ldg)");
             attr_set = true;
         }
@@ -424,13 +424,13 @@ __global__ void __launch_bounds__(kScoreThreads) topk_segments_kernel(const int6
     pdl_wait();
     const int64_t r0 = row_off[b];
     const int n = (int)(row_off[b + 1] - r0);
-    select_topk(sel, b, scores + r0, n, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
+    select_topk<40>(sel, b, scores + r0, n, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
 }
 
 static int launch_segments(const float* scores, const int64_t* row_off, int B, const SelectArgs& sel, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(topk_segments)");
         attr_set = true;
     }
@@ -505,7 +505,8 @@ extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_ti
     ScoreParams p = {};
     p.tiles = d_tiles; p.row_off = d_row_off; p.q = d_q;
     p.B = B; p.d = d; p.total_tiles = total_tiles; p.tile_rows = tile_rows; p.sims = d_sims;
-    p.sel.k = k; p.sel.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
+    p.sel.k = k;
+    p.sel.cache_floats = cache_floats_for(max_rows, k, (algo == RDV_SCORE_LDG_FUSED ? 16 : 40) * kScoreThreads);
     p.sel.topk_idx = d_topk_idx; p.sel.topk_val = d_topk_val; p.sel.topk_cnt = d_topk_cnt; p.sel.doc_done = d_doc_done;
     p.sel.smem_idx = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -529,7 +530,7 @@ extern "C" int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row
     RDV_REQUIRE(d_scores || max_rows == 0, RDV_E_INVALID, "topk_segments_f32: null scores");
     RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "topk_segments_f32: k=%d outside [1, 1024]", k);
     SelectArgs sel = {};
-    sel.k = k; sel.cache_floats = max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
+    sel.k = k; sel.cache_floats = cache_floats_for(max_rows, k, 40 * kScoreThreads);
     sel.topk_idx = d_topk_idx; sel.topk_val = d_topk_val; sel.topk_cnt = d_topk_cnt; sel.doc_done = nullptr;
     sel.smem_idx = nullptr;
     return launch_segments(d_scores, d_row_off, B, sel, static_cast<cudaStream_t>(stream));

@@ -4,8 +4,8 @@
 // first, NaN greatest, -0 == +0" is one unsigned compare (rdv_common.cuh).
 //
 // k <= 32 (every reference config: chunk_num 5 / 10 / 20): register-resident, warp-level.  Thread t owns
-// the strided slice {i : i % 256 == t} of the document's scores as keys in registers (n <= 4096) or as a
-// private column of the shared-memory cache (larger n).  Each warp extracts the k best of its 32 slices
+// the strided slice {i : i % 256 == t} of the document's scores as keys in registers (n <= 10240: every
+// reference workload) or as a private column of the shared-memory cache (larger n).  Each warp extracts the k best of its 32 slices
 // with k rounds of a two-instruction warp arg-max (redux.sync on the high and low key halves) -- no
 // block barrier inside the rounds -- then ONE barrier, and warp 0 merges the 8 x k candidates the same way.
 // k > 32: k rounds of a block-wide arg-max (two barriers per round).
@@ -16,7 +16,9 @@ namespace rdv {
 
 constexpr int kScoreThreads = 256;            // 8 compute warps
 constexpr int kScoreWarps = kScoreThreads / 32;
-constexpr int kMaxCacheFloats = 8192;         // selection pass caches up to this many scores in smem (32 KB)
+constexpr int kMaxCacheFloats = 8192;         // selection pass caches up to this many scores in smem (32 KB).  A 64 KB cache was
+                                              // measured: the selection alone 48 -> 37 us at C3, but the step 640 -> 730 us (the larger
+                                              // shared-memory carve-out delays the streaming kernel that follows), so it stays at 32 KB
 constexpr int kSelWarpK = 32;                 // largest k of the warp-level path
 
 struct SelectArgs {
@@ -27,6 +29,13 @@ struct SelectArgs {
     int32_t* doc_done;      // (B) workspace reset to 0 by the selecting block (may be null)
     int32_t* smem_idx;      // optional shared-memory copy of the winners (k_min entries) for a fused consumer
 };
+
+// shared-memory cache (floats) a selection launch needs: none when every document is selected out of registers
+// (k <= kSelWarpK is the common case; larger k always uses the cache)
+__host__ __device__ __forceinline__ int cache_floats_for(int max_rows, int k, int reg_rows) {
+    if (k <= kSelWarpK && max_rows <= reg_rows) return 0;
+    return max_rows < kMaxCacheFloats ? max_rows : kMaxCacheFloats;
+}
 
 struct BlockSync {       // whole block
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -70,7 +79,10 @@ __device__ __forceinline__ unsigned long long warp_topk_regs(const float* __rest
 
 // Selection of the k best (score desc, index asc) among n scores of one document by 256 threads.
 // Ends with the winners written (global + optional smem_idx); the caller synchronises before reading smem_idx.
-template <class Sync>
+// MAXREG: most keys a thread keeps in registers (16 or 40).  40 (n <= 10240, 80 key registers) is for the stand-alone
+// selection kernel; kernels that do other work around the selection (gather, fused score) stay at 16 so that their
+// register count -- and with it the occupancy of the whole kernel -- does not follow the selection's worst case.
+template <int MAXREG, class Sync>
 __device__ void select_topk(const SelectArgs& p, int b, const float* __restrict__ src, int n,
                             float* cache, unsigned long long* s_red, Sync sync) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -82,6 +94,8 @@ __device__ void select_topk(const SelectArgs& p, int b, const float* __restrict_
             mine = warp_topk_regs<4>(src, n, k_min, tid, lane);
         } else if (n <= 16 * kScoreThreads) {
             mine = warp_topk_regs<16>(src, n, k_min, tid, lane);
+        } else if (MAXREG > 16 && n <= MAXREG * kScoreThreads) {
+            mine = warp_topk_regs<(MAXREG > 16 ? MAXREG : 16)>(src, n, k_min, tid, lane);
         } else {
             // private column of the cache (thread t only ever touches i % 256 == t: no barrier needed)
             const bool cached = n <= p.cache_floats;
