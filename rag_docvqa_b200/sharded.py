@@ -151,11 +151,23 @@ def merge_across_ranks(local_val: torch.Tensor, local_idx: torch.Tensor, k: int,
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_val, local_idx
     world = dist.get_world_size(group)
-    vals = [torch.empty_like(local_val) for _ in range(world)]
-    idxs = [torch.empty_like(local_idx) for _ in range(world)]
-    dist.all_gather(vals, local_val.contiguous(), group=group)
-    dist.all_gather(idxs, local_idx.contiguous(), group=group)
-    cand_val, cand_idx = torch.cat(vals, dim=1), torch.cat(idxs, dim=1)
+    Q, kk = local_val.shape
+    if local_val.is_cuda and (Q * kk) % 2 == 0:
+        # ONE collective: values (fp32) and ids (int64) travel in one byte buffer of Q*k*12 bytes per rank
+        nv = Q * kk * 4
+        send = torch.empty(nv + Q * kk * 8, dtype=torch.uint8, device=local_val.device)
+        send[:nv].view(torch.float32).copy_(local_val.reshape(-1))
+        send[nv:].view(torch.int64).copy_(local_idx.reshape(-1))
+        recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=local_val.device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        cand_val = recv[:, :nv].contiguous().view(torch.float32).view(world, Q, kk).permute(1, 0, 2).reshape(Q, world * kk)
+        cand_idx = recv[:, nv:].contiguous().view(torch.int64).view(world, Q, kk).permute(1, 0, 2).reshape(Q, world * kk)
+    else:
+        vals = [torch.empty_like(local_val) for _ in range(world)]
+        idxs = [torch.empty_like(local_idx) for _ in range(world)]
+        dist.all_gather(vals, local_val.contiguous(), group=group)
+        dist.all_gather(idxs, local_idx.contiguous(), group=group)
+        cand_val, cand_idx = torch.cat(vals, dim=1), torch.cat(idxs, dim=1)
     return (merge_fn or merge_candidates)(cand_val, cand_idx, k)
 
 
