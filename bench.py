@@ -618,6 +618,15 @@ def run_ours(args):
                 extras["e2e_eager_pil_crops_queries_per_s"] = w.docs * 2 / (time.perf_counter() - t0)
                 best_c, _ = time_cpu(cpu_retrieve_fn(cpu_batch, w.k, crop=True), 2.0, min_reps=1)
                 extras["cpu_eager_pil_crops_queries_per_s"] = w.docs / best_c
+                # the reference's own situation: the embedder left the embeddings on the GPU (src/RAGVT5.py:230-252)
+                dev_emb, dev_q = batches[0]["text_embeddings"], batches[0]["question_embeddings"]
+                retr.retrieve(dev_emb, dev_q, *lists)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for i in range(e2e_steps):
+                    retr.retrieve(dev_emb, dev_q, *lists)
+                torch.cuda.synchronize()
+                extras["retrieve_device_embeddings_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
                 # B200-native API: host embeddings in, packed generator tensors on the device out
                 def packed_step(i):
                     emb_h, q_h = host_sets[i % len(host_sets)]
