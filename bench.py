@@ -839,8 +839,10 @@ def run_visual(args):
             return float(t.item())
         return x
 
+    vr_step = VisualRetriever({"chunk_num": k, "include_surroundings": 0, "chunk_mode": "horizontal", "device": str(dev)})
+
     def step(i):
-        sims = [F.late_interaction(q[b:b + 1], patches[b]) for b in range(B)]
+        sims = vr_step._get_similarities(patches, q)            # the drop-in's own scoring loop (two side streams)
         return F.topk_segments(sims, k)
 
     # the dominant kernel alone: operands already normalised and split

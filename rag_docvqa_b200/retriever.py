@@ -492,10 +492,29 @@ class VisualRetriever:
         self.device = _device_of(config)
 
     def _get_similarities(self, patch_embeddings: List[torch.Tensor], question_embeddings: torch.Tensor):
+        """MaxSim of question i against the strips of document i (src/_modules.py:2191-2205).  Documents alternate
+        between two side streams: the HBM-bound normalise + split of one document overlaps the tensor-bound
+        contraction of the previous one."""
         dev = question_embeddings.device if question_embeddings.is_cuda else self.device
         q = _to_device(question_embeddings, dev)
-        return [F.late_interaction(q[i].unsqueeze(0), _to_device(patch_embeddings[i], dev))
-                for i in range(len(patch_embeddings))]
+        n_docs = len(patch_embeddings)
+        if n_docs < 2:
+            return [F.late_interaction(q[i].unsqueeze(0), _to_device(patch_embeddings[i], dev)) for i in range(n_docs)]
+        if getattr(self, "_side_streams", None) is None or self._side_streams[0].device != dev:
+            self._side_streams = [torch.cuda.Stream(dev) for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        ready = cur.record_event()
+        sims = []
+        for i in range(n_docs):
+            st = self._side_streams[i & 1]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                s_i = F.late_interaction(q[i].unsqueeze(0), _to_device(patch_embeddings[i], dev))
+            s_i.record_stream(cur)
+            sims.append(s_i)
+        for st in self._side_streams:
+            cur.wait_stream(st)
+        return sims
 
     def _get_surrounding_patches(self, patch_coord, patches_matrix, include_surroundings=0):
         n_rows = len(patches_matrix)
