@@ -20,6 +20,14 @@ int cuda_fail(cudaError_t err, const char* what) {
     return RDV_E_CUDA;
 }
 
+int carveout_pct() {
+    static const int pct = [] {
+        const char* v = getenv("RDV_CARVEOUT");
+        return v ? atoi(v) : -1;
+    }();
+    return pct;
+}
+
 int pdl_mask() {
     static const int mask = [] {
         const char* v = getenv("RDV_PDL");

@@ -46,15 +46,28 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // environment; scripts/probe_step.py on B200, C2 step score -> select+gather): plain launches 17.1 us with
 // none, 15.1 us with the streaming kernels only (default), 15.7 us with both; inside a CUDA graph 13.2 us with
 // or without the streaming kernels, 15.1 us when the select/gather kernel is launched early as well.
+// RDV_CARVEOUT: preferred shared-memory carve-out (percent) of the kernels launched through launch_pdl, -1 = driver
+// default (the default).  Measured on B200 (C2 step, with / without PDL on the select+gather launch): matching carve-outs
+// do not make the early-launched gather pay off inside a graph (13.4 us per step either way, 5.0-5.2 us with 8 lanes);
+// with plain stream launches RDV_CARVEOUT=0 RDV_PDL=3 gives 14.3 us instead of 16.3 us, but costs the 8-lane mode 15 %.
+int carveout_pct();
 int pdl_mask();                       // RDV_PDL bit 0: streaming kernels (default), bit 1: selection / gather kernels
 constexpr int kPdlStream = 1, kPdlSelect = 2;
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+template <class... KArgs>
+static inline void prefer_carveout(void (*kernel)(KArgs...)) {
+    const int pct = carveout_pct();
+    if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args&&... args) {
+    static bool carve_set = false;            // one static per kernel instantiation
+    if (!carve_set) { prefer_carveout(kernel); carve_set = true; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
