@@ -28,6 +28,10 @@ struct GatherParams {
 
 struct Interval { int lo, hi; };
 
+// SURR = false: include_surroundings == 0 (every shipped config).  The neighbour-window code (interval subtraction,
+// page walks, word-box pass) is compiled out, which matters here: a block runs its code exactly once, so the
+// instruction fetch of the un-taken paths' surroundings shows up as `no_instructions` stalls (17 % in profiles/).
+template <bool SURR>
 __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const GatherParams P) {
     const rdv_docstore& ds = P.ds;
     const rdv_gather_args& a = P.a;
@@ -56,7 +60,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     const int p0 = a.prompt_off[b], plen = a.prompt_off[b + 1] - p0;   // independent of the hits: issue early
     // no neighbours: a hit is exactly its own chunk, so its bbox is the chunk's precomputed bbox and phase C
     // (a dependent pass over the word boxes) disappears
-    const bool own_bbox = a.include_surroundings == 0 && ds.chunk_bbox != nullptr;
+    const int surroundings = SURR ? a.include_surroundings : 0;
+    const bool own_bbox = !SURR && ds.chunk_bbox != nullptr;
     const int page0 = (ds.doc_page_off && ds.page_wh) ? ds.doc_page_off[b] : -1;
     if (a.sims) {
         // fused selection: this block owns document b, so the top-k needs no cross-block traffic at all
@@ -91,27 +96,29 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
         s_chunk[tid] = gc;
         s_page[tid] = rec.page;
         s_label[tid] = rec.label;
-        if (a.include_surroundings == 0) {
+        if (!SURR) {
             s_lo[tid] = start; s_hi[tid] = start + nw;         // no neighbours: the page length is not needed
         } else {
             const int last = ds.page_chunks[ds.run_end[gc] - 1];
             const int page_len = ds.chunk_page_start[last] + (ds.chunk_word_off[last + 1] - ds.chunk_word_off[last]);
-            s_lo[tid] = max(0, start - a.include_surroundings);
-            s_hi[tid] = min(page_len, start + nw + a.include_surroundings);
+            s_lo[tid] = max(0, start - surroundings);
+            s_hi[tid] = min(page_len, start + nw + surroundings);
         }
         if (!a.reorder_chunks) s_order[tid] = tid;
     }
-    if (a.include_surroundings != 0) __syncthreads();           // phase B reads the other hits' intervals
+    if (SURR) __syncthreads();                                  // phase B reads the other hits' intervals
 
     // ---- B: fresh sub-intervals (minus better hits on the same page) -> global word segments ------
-    if (tid < cnt && a.include_surroundings == 0) {
-        // ranges of distinct chunks are disjoint in the page word list: the hit is exactly its own words
-        const int wb = rec.word_begin, we = rec.word_end;
-        s_seg[tid][0][0] = wb; s_seg[tid][0][1] = we;
-        s_seg_tok[tid][0][0] = rec.tok_begin; s_seg_tok[tid][0][1] = rec.tok_end;
-        s_nseg[tid] = we > wb ? 1 : 0;
-        s_nwords[tid] = we - wb;
-        s_ntok[tid] = rec.tok_end - rec.tok_begin;
+    if constexpr (!SURR) {
+        if (tid < cnt) {
+            // ranges of distinct chunks are disjoint in the page word list: the hit is exactly its own words
+            const int wb = rec.word_begin, we = rec.word_end;
+            s_seg[tid][0][0] = wb; s_seg[tid][0][1] = we;
+            s_seg_tok[tid][0][0] = rec.tok_begin; s_seg_tok[tid][0][1] = rec.tok_end;
+            s_nseg[tid] = we > wb ? 1 : 0;
+            s_nwords[tid] = we - wb;
+            s_ntok[tid] = rec.tok_end - rec.tok_begin;
+        }
     } else if (tid < cnt) {
         Interval fresh[kMaxFresh];
         int nf = 1;
@@ -359,14 +366,17 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
     if (args->sims) {
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(gather_vt5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(gather_vt5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(gather_vt5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gather_vt5)");
             attr_set = true;
         }
         smem = (size_t)(cache_floats_for(args->max_rows, args->k, 16 * kScoreThreads)) * sizeof(float) + 16;
     }
-    cudaError_t le = launch_pdl(kPdlSelect, gather_vt5_kernel, dim3(ds->B), dim3(kGatherThreads), smem,
-                                static_cast<cudaStream_t>(stream), P);
+    cudaError_t le = args->include_surroundings != 0
+        ? launch_pdl(kPdlSelect, gather_vt5_kernel<true>, dim3(ds->B), dim3(kGatherThreads), smem, static_cast<cudaStream_t>(stream), P)
+        : launch_pdl(kPdlSelect, gather_vt5_kernel<false>, dim3(ds->B), dim3(kGatherThreads), smem, static_cast<cudaStream_t>(stream), P);
     if (le != cudaSuccess) return cuda_fail(le, "gather_vt5_kernel");
     return RDV_OK;
 }
