@@ -108,3 +108,24 @@ def test_lazy_crop_behaves_like_an_eager_crop():
     assert lazy_crop(page, rect).convert("L").tobytes() == ref.convert("L").tobytes()
     assert lazy_crop(page, rect).copy().tobytes() == ref.tobytes()
     assert lazy_crop(page, (0, 0, 0, 0)).size == (0, 0)
+
+
+def test_pix2struct_plan_matches_the_reference_arithmetic():
+    """Host half of rdv_pix2struct_patches: patch grids, output offsets and row-id offsets of
+    extract_multi_image_flattened_patches (src/custom_pix2struct_processor.py:52-57, 97-132), checked against the
+    oracle's run of the same images."""
+    from oracle import ref_restated as R
+    from rag_docvqa_b200.pagestore import plan_pix2struct
+    rng = np.random.RandomState(12)
+    for max_total in (2048, 300, 64):
+        sizes = [(int(rng.randint(8, 400)), int(rng.randint(8, 900))) for _ in range(rng.randint(1, 7))]     # (h, w)
+        crops = [[(i, 0, 0, w, h) for i, (h, w) in enumerate(sizes)]]
+        images, doc_total, temp = plan_pix2struct(crops, np.array([0, len(sizes)], dtype=np.int32), max_total, 16)
+        per, row_offset, out_start = max_total // len(sizes), 0, 0
+        for rec, (h, w) in zip(images, sizes):
+            flat, nxt = R.pix2struct_patches_single(np.zeros((h, w, 3), np.float32), per, 16, 16, row_offset)
+            assert rec["kept"] == flat.shape[0] and rec["out_start"] == out_start and rec["row_offset"] == row_offset
+            assert rec["rows"] == nxt - row_offset and rec["rows"] * rec["cols"] >= rec["kept"]
+            out_start += flat.shape[0]
+            row_offset = nxt
+        assert doc_total.tolist() == [out_start] and out_start <= max_total
