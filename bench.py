@@ -415,9 +415,11 @@ def run_ours(args):
     plans = None
     if with_lists:
         table = synth.make_tokens_for_words(host_batch["words_text_chunks"], seed=3)
+        t_store = time.perf_counter()
         store = DocStore.from_lists(host_batch["words_text_chunks"], host_batch["words_box_chunks"],
                                     host_batch["layout_labels_chunks"], host_batch["page_indices"],
                                     lambda wd: table.get(wd, [2]), dev, images=host_batch["images"])
+        docstore_build_s = time.perf_counter() - t_store
         prompts = prompts_for(w.docs)
         plans = [store.prepare_gather(o["idx"], o["cnt"], prompts, max_len=512, sims=o["sims"], topk_val=o["val"],
                                       max_rows=t.max_rows) for o, t in zip(outs, tables)]
@@ -639,6 +641,10 @@ def run_ours(args):
                     packed_step(i)
                 torch.cuda.synchronize()
                 extras["e2e_packed_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
+                # the packed path needs the documents pre-tokenised (DocStore): a per-DOCUMENT cost paid at ingest, not per
+                # question -- it walks every word of every chunk on the host
+                extras["docstore_build_s_per_batch_of_documents"] = docstore_build_s
+                extras["docstore_words"] = store.n_words
                 # ... and with the visual input as well: crops of the hits grid-packed and resized to 224 x 224 on the device
                 from rag_docvqa_b200.pagestore import PageStore
                 pstore = PageStore.from_images(host_batch["images"], dev)
