@@ -17,6 +17,11 @@ import torch
 from . import _lib
 from .functional import _stream_ptr
 
+try:                                   # C helper for the per-word walk (csrc/hostlists.c); the Python walk below is the
+    from . import _hostlists           # same algorithm and stays as the specification
+except ImportError:                    # pragma: no cover - built by rag_docvqa_b200.build
+    _hostlists = None
+
 _I32 = np.int32
 
 
@@ -74,6 +79,14 @@ class DocStore:
         """tokenize(word) -> the word's token ids WITHOUT the trailing EOS (src/VT5.py:160).
         derived=False leaves out the optional gather-friendly views (tok_rec, chunk_bbox); the kernel then
         walks tok_ids -> tok_word -> word_box (tests cover both)."""
+        arrays, B = cls.arrays_from_lists(words_text_chunks, words_box_chunks, layout_labels_chunks, page_indices, tokenize,
+                                          images=images, derived=derived)
+        return cls(arrays, B, device)
+
+    @staticmethod
+    def arrays_from_lists(words_text_chunks, words_box_chunks, layout_labels_chunks, page_indices, tokenize,
+                          images=None, derived: bool = True):
+        """The host half of from_lists: nested lists -> CSR arrays (no device needed)."""
         B = len(words_text_chunks)
         sizes = np.array([len(doc) for doc in words_text_chunks], dtype=np.int64)
         chunk_off = np.zeros(B + 1, dtype=np.int64)
@@ -82,24 +95,41 @@ class DocStore:
         chunk_nwords = np.zeros(N, dtype=np.int64)
         chunk_label = np.zeros(N, dtype=_I32)
         chunk_page = np.zeros(N, dtype=_I32)
-        tok_cache = {}
-        word_ntok, tok_ids, boxes = [], [], []
         g = 0
         for b in range(B):
+            labels_b, pages_b = layout_labels_chunks[b], page_indices[b]
             for c in range(int(sizes[b])):
-                words = words_text_chunks[b][c]
-                chunk_nwords[g] = len(words)
-                chunk_label[g] = layout_labels_chunks[b][c]
-                chunk_page[g] = page_indices[b][c]
-                for w in words:
-                    toks = tok_cache.get(w)
-                    if toks is None:
-                        toks = tok_cache[w] = [int(t) for t in tokenize(w)]
-                    word_ntok.append(len(toks))
-                    tok_ids.extend(toks)
-                if len(words):
-                    boxes.extend(words_box_chunks[b][c])
+                chunk_label[g] = labels_b[c]
+                chunk_page[g] = pages_b[c]
                 g += 1
+        tok_cache = {}
+        if _hostlists is not None:
+            # the walk over every word (2 M for a C2 batch) in C: csrc/hostlists.c flatten_docs
+            raw_nw, raw_nt, raw_ids, raw_boxes = _hostlists.flatten_docs(words_text_chunks, words_box_chunks, tokenize, tok_cache)
+            chunk_nwords = np.frombuffer(raw_nw, dtype=np.int64)
+            word_ntok = np.frombuffer(raw_nt, dtype=_I32)
+            tok_ids = np.frombuffer(raw_ids, dtype=_I32)
+            boxes = np.frombuffer(raw_boxes, dtype=np.float64)
+            if len(chunk_nwords) != N:
+                raise ValueError("words_text_chunks: %d chunks, expected %d" % (len(chunk_nwords), N))
+        else:
+            word_ntok, tok_ids, boxes = [], [], []
+            g = 0
+            for b in range(B):
+                for c in range(int(sizes[b])):
+                    words = words_text_chunks[b][c]
+                    chunk_nwords[g] = len(words)
+                    for w in words:
+                        toks = tok_cache.get(w)
+                        if toks is None:
+                            toks = tok_cache[w] = tuple(int(t) for t in tokenize(w))
+                        word_ntok.append(len(toks))
+                        tok_ids.extend(toks)
+                    if len(words):
+                        if len(words_box_chunks[b][c]) != len(words):
+                            raise ValueError("document %d chunk %d: %d words but %d boxes" % (b, c, len(words), len(words_box_chunks[b][c])))
+                        boxes.extend(words_box_chunks[b][c])
+                    g += 1
         chunk_word_off = np.zeros(N + 1, dtype=np.int64)
         np.cumsum(chunk_nwords, out=chunk_word_off[1:])
         W = int(chunk_word_off[-1])
@@ -165,7 +195,7 @@ class DocStore:
             wh = np.array([[im.width, im.height] for pages in images for im in pages], dtype=_I32).reshape(-1, 2)
             arrays["doc_page_off"] = doc_page_off.astype(_I32)
             arrays["page_wh"] = np.ascontiguousarray(wh)
-        return cls(arrays, B, device)
+        return arrays, B
 
     # ---- on-disk form: the CSR arrays of a pre-tokenised batch of documents --------
     def save(self, path: str) -> None:

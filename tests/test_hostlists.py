@@ -129,3 +129,29 @@ def test_pix2struct_plan_matches_the_reference_arithmetic():
             out_start += flat.shape[0]
             row_offset = nxt
         assert doc_total.tolist() == [out_start] and out_start <= max_total
+
+
+def test_docstore_arrays_c_walk_equals_python_walk():
+    """DocStore.arrays_from_lists: the per-word walk in C (flatten_docs) and in Python give identical CSR arrays."""
+    from rag_docvqa_b200 import docstore
+    b = synth.make_text_batch("C2", with_lists=True, docs=6, seed=19, share_image_pool=4)
+    words = b["words_text_chunks"]
+    words[1][3] = []                                             # an empty chunk
+    b["words_box_chunks"][1][3] = []
+    table = synth.make_tokens_for_words(words, seed=3)
+    args = (words, b["words_box_chunks"], b["layout_labels_chunks"], b["page_indices"], lambda w: table.get(w, [2]))
+    assert docstore._hostlists is not None
+    a_c, B_c = docstore.DocStore.arrays_from_lists(*args, images=b["images"])
+    saved, docstore._hostlists = docstore._hostlists, None
+    try:
+        a_py, B_py = docstore.DocStore.arrays_from_lists(*args, images=b["images"])
+    finally:
+        docstore._hostlists = saved
+    assert B_c == B_py == 6 and sorted(a_c) == sorted(a_py)
+    for k in a_c:
+        assert np.array_equal(a_c[k], a_py[k]), k
+    bad_boxes = [list(d) for d in b["words_box_chunks"]]
+    bad_boxes[0] = list(bad_boxes[0])
+    bad_boxes[0][0] = bad_boxes[0][0][:-1]                      # one box short
+    with pytest.raises(ValueError):
+        docstore.DocStore.arrays_from_lists(words, bad_boxes, b["layout_labels_chunks"], b["page_indices"], lambda w: [2])
