@@ -20,11 +20,11 @@
 //    run of tiles; every warp owns a private shared-memory ring and ITS OWN mbarriers, requests its tiles with
 //    1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) and consumes them with conflict-free LDS.128 -- no
 //    producer warp and no cross-warp synchronisation.  192 KB in flight per SM independent of occupancy and of
-//    registers.  Measured on B200: 7.05 TB/s at C3 (LDG kernel 7.2), 12.8 us at C2 (LDG 6.9 us: a 32 MB batch
+//    registers.  Measured on B200: 7.1 TB/s at C3 (595 us per batch; LDG kernel 593 us), 12.8 us at C2 (LDG 6.9 us: a 32 MB batch
 //    is launch/latency-bound and the ring adds a descriptor -> copy -> wait chain), so AUTO stays on LDG.
 //
-// Selection (select.cuh): k rounds of a block-wide arg-max over packed (score, ~index) u64 keys, which
-// makes "descending score, lowest index first" one integer compare.
+// Selection (select.cuh): packed (score, ~index) u64 keys make "descending score, lowest index first" one integer
+// compare; register-resident, warp-level extraction (redux.sync) for k <= 32, block-wide rounds above.
 #include "select.cuh"
 
 namespace rdv {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) score_ldg_kernel(const Sc
 }
 
 // =====================================================================================================
-// TMA kernel: persistent, producer warp + shared-memory ring of bulk async copies.
+// TMA kernel: persistent, per-warp self-service rings of bulk async copies.
 // =====================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
