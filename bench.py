@@ -962,7 +962,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--visual-docs", type=int, default=8)
     ap.add_argument("--corpus-rows", type=int, default=10_000_000)
     ap.add_argument("--corpus-queries", type=int, default=1024)
