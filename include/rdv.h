@@ -212,6 +212,10 @@ RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, i
  *   sims / topk_val / max_rows   optional fused selection: when `sims` is non-NULL the kernel first selects the
  *                 top-k of sims[chunk_off[b] .. chunk_off[b+1]) itself (same ordering as rdv_score_topk_f32)
  *                 and WRITES topk_idx / topk_val / topk_cnt, so a step is rdv_score_f32 + this kernel.
+ *   emit_order (B,k) / emit_cnt[B]   optional (NULL = everything, in retrieve()'s order): the reranker's index list
+ *                 (rdv_rerank_order; src/_modules.py:1592-1595).  Output position r then holds the hit that retrieve()
+ *                 -- after reorder_chunks -- would have put at position emit_order[b][r], and only emit_cnt[b] hits
+ *                 are emitted; every hit keeps the words it was retrieved with (dedup against better hits).
  * Requirements: 1 <= k <= 64.
  * ------------------------------------------------------------------------------------------- */
 typedef struct rdv_chunk_rec {   /* everything the gather needs about one chunk, in one 32-byte load */
@@ -280,9 +284,37 @@ typedef struct rdv_gather_args {
     float* topk_val;
     int32_t max_rows;
     int32_t reserved;
+    const int32_t* emit_order;
+    const int32_t* emit_cnt;
 } rdv_gather_args;
 
 RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args* args, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * What consumes the hits before generation.
+ *
+ * rdv_rerank_order: Reranker.rerank after the cross-encoder call (src/_modules.py:1579-1595).  d_scores (B,k) float32
+ *   (scores_f64 = 0: CrossEncoder.predict) or float64 (scores_f64 = 1: FlagLLMReranker.compute_score), d_cnt[B]
+ *   candidates per document (NULL = k).  np.argsort(scores)[::-1] (equal scores: higher index first, NaN first), keep
+ *   scores >= filter_thresh (compared in float64), more than max_num -> the first max_num, fewer than min_num ->
+ *   the first min_num of the unfiltered order.  d_order (B,k) int32, -1 padded; d_out_cnt[B]; d_out_scores (B,k)
+ *   optional, the scores in the new order (same type as d_scores).  1 <= k <= 64.
+ * rdv_page_vote: major_page_indices of RAGVT5.forward (src/RAGVT5.py:455-475).  d_hit_page (B,k) / d_hit_cnt[B]:
+ *   top_k_page_indices; d_sims / d_row_off[B+1]: every similarity of the batch (the score kernel's output).
+ *   weighted = 0 (majorpage): every hit weighs 1 / n_b.  weighted = 1 (weightmajorpage): hit j weighs
+ *   sims[b][j] / sum(sims[b]) -- the similarity of CHUNK j, as the reference's zip pairs them -- with the sum
+ *   taken sequentially in chunk order.  legacy_promotion = 1: numpy 1.x scalar promotion (the reference pins
+ *   1.26.4): sum and per-page accumulation in float64; 0: NEP 50 (numpy >= 2): float32.  Ties between pages go to
+ *   the first page in CPython's iteration order of set(pages) (Objects/setobject.c, reproduced slot for slot);
+ *   no hits -> page 0.  d_major[B] int32; d_major_weight[B] float64 optional (the winning page's weight).
+ * ------------------------------------------------------------------------------------------- */
+RDV_API int rdv_rerank_order(const void* d_scores, int32_t scores_f64, const int32_t* d_cnt, int32_t B, int32_t k,
+                             double filter_thresh, int32_t max_num, int32_t min_num, int32_t* d_order,
+                             int32_t* d_out_cnt, void* d_out_scores, void* stream);
+RDV_API int rdv_page_vote(const int32_t* d_hit_page, const int32_t* d_hit_cnt, const float* d_sims,
+                          const int64_t* d_row_off, int32_t B, int32_t k, int32_t weighted, int32_t legacy_promotion,
+                          int32_t* d_major, double* d_major_weight, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -76,3 +76,24 @@ def recall_at_k(got_idx, ref_idx) -> float:
         hits += len(r & set(int(x) for x in g if x >= 0))
         total += len(r)
     return hits / max(1, total)
+
+
+def assert_order_matches_modulo_ties(got, ref, scores):
+    """Reranker index lists: same length, distinct entries, and the same score at every rank (equal scores may
+    resolve differently: the reference's order of ties depends on which numpy sort kernel the CPU dispatches to)."""
+    assert len(got) == len(ref) and len(set(got)) == len(got)
+    assert [float(scores[i]) for i in got] == [float(scores[i]) for i in ref], (got, ref)
+
+
+def load_postproc_golden(golden_dir):
+    """tests/golden/postproc.json (oracle/make_golden_postproc.py) with the packed arrays decoded."""
+    import base64
+    import json
+    import os
+    with open(os.path.join(golden_dir, "postproc.json")) as f:
+        g = json.load(f)
+    for c in g["page_vote"]:
+        c["sims"] = [np.frombuffer(base64.b64decode(x), dtype=np.float32) for x in c["sims_f32_b64"]]
+    for c in g["rerank"]:
+        c["scores_np"] = np.asarray(c["scores"], dtype=np.float32 if c["dtype"] == "f32" else np.float64)
+    return g

@@ -580,3 +580,114 @@ def pix2struct_patches(images: Sequence[np.ndarray], max_total_patches: int = 20
     else:
         cat = cat[:max_total_patches]
     return cat, (cat.sum(axis=-1) != 0).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# f3: what consumes the top-k -- reranker post-processing and the page vote
+#     reference: src/_modules.py:1562-1610 (Reranker.rerank / batch_rerank), src/RAGVT5.py:455-477 (majorpage /
+#     weightmajorpage).  The cross-encoder itself is a model and out of scope: its scores are the input here.
+# --------------------------------------------------------------------------------------
+def rerank_order(scores, filter_thresh: float = 0.4, max_chunk_num: int = 5, min_chunk_num: int = 1) -> List[int]:
+    """The index list Reranker.rerank applies to the candidates and to every extra argument (:1579-1595).
+    `np.argsort(scores)[::-1]`: the order of EQUAL scores is unspecified in the reference -- numpy's default sort is
+    an insertion sort (stable) up to 16 elements on its scalar path, so ties come out higher index first after the
+    reversal, but the AVX-512 / AVX2 argsort numpy dispatches to on recent CPUs (>= 1.25 / 2.0) orders ties
+    arbitrarily (seen in tests/golden/postproc.json, made with numpy 2.3).  Stated rule here and in the CUDA kernel:
+    ties -> HIGHER index first (kind="stable" reversed); the comparator accepts the reference's order modulo ties.
+    NaN sorts last ascending = first after the reversal, never passes the threshold, and can only return through
+    the `min_chunk_num` fallback.  The threshold comparison is numpy-scalar >= Python float: float64 under the
+    reference's pinned numpy 1.26.4 (legacy promotion); for the shipped 0.4 a float32 comparison agrees
+    (float32(0.4) > 0.4 and no float32 lies between)."""
+    scores = np.asarray(scores)
+    sorted_indices = np.argsort(scores, kind="stable")[::-1]                                   # :1582
+    thresh = float(filter_thresh)
+    filtered = [int(i) for i in sorted_indices if float(scores[i]) >= thresh]                  # :1585
+    if len(filtered) > max_chunk_num:                                                          # :1586-1587
+        filtered = filtered[:max_chunk_num]
+    elif len(filtered) < min_chunk_num:                                                        # :1588-1589
+        filtered = [int(i) for i in sorted_indices[:min_chunk_num]]
+    return filtered
+
+
+def rerank(scores, candidates, *args, filter_thresh: float = 0.4, max_chunk_num: int = 5, min_chunk_num: int = 1):
+    """Reranker.rerank after the cross-encoder call (:1592-1595): candidates and every argument permuted alike."""
+    order = rerank_order(scores, filter_thresh, max_chunk_num, min_chunk_num)
+    return ([candidates[i] for i in order], *[[arg[i] for i in order] for arg in args])
+
+
+def int_set_order(values: Sequence[int]) -> List[int]:
+    """Iteration order of `set(values)` for non-negative ints, i.e. of `list(set(page_indices_b))`
+    (src/RAGVT5.py:466) -- the order `max(page_weights, key=...)` breaks ties in (:474).  CPython's
+    Objects/setobject.c (3.7 .. 3.12, same algorithm): open addressing, hash(i) = i, 9 linear probes then the
+    perturbed jump, table grown to 4 x used when fill * 5 >= mask * 3, entries re-inserted in slot order."""
+    LINEAR_PROBES, PERTURB_SHIFT = 9, 5
+
+    def insert(table, mask, v):
+        perturb = v
+        i = v & mask
+        while True:
+            probes = LINEAR_PROBES if i + LINEAR_PROBES <= mask else 0
+            for j in range(i, i + probes + 1):
+                if table[j] is None:
+                    table[j] = v
+                    return True
+                if table[j] == v:
+                    return False
+            perturb >>= PERTURB_SHIFT
+            i = (i * 5 + 1 + perturb) & mask
+
+    mask, table, used = 7, [None] * 8, 0
+    for v in values:
+        v = int(v)
+        if v < 0:
+            raise ValueError("page indices are non-negative")
+        if insert(table, mask, v):
+            used += 1
+            if used * 5 >= mask * 3:
+                size = 8
+                while size <= used * 4:
+                    size <<= 1
+                old, table, mask = table, [None] * size, size - 1
+                for e in old:
+                    if e is not None:
+                        insert(table, mask, e)
+    return [e for e in table if e is not None]
+
+
+def page_vote(page_indices_b: Sequence[int], similarities_b: Optional[np.ndarray], n_chunks: int, weighted: bool,
+              legacy_promotion: bool = True) -> int:
+    """major_page_indices[b] of RAGVT5.forward (src/RAGVT5.py:455-475) for one document.
+    majorpage: weights = ones(len(similarities[b])) / n  (float64).  weightmajorpage: weights = similarities[b]
+    (float32, ALL n_b chunks in chunk order) / sum(w); `zip(page_indices_b, weights_b)` then pairs hit j with the
+    weight of CHUNK j (not of the hit) -- reproduced as written.  `sum(w)` and `page_weights[page] += weight` start
+    from the Python int 0: with the reference's pinned numpy 1.26.4 int + float32 promotes to float64 (legacy_promotion,
+    the default); numpy >= 2 (NEP 50) stays in float32.  The division is float32 in both (array / scalar)."""
+    n_hits = len(page_indices_b)
+    if weighted:
+        w32 = np.asarray(similarities_b, dtype=np.float32)
+        if legacy_promotion:
+            total = np.float64(0.0)
+            for x in w32:
+                total = total + np.float64(x)
+            weights = w32 / np.float32(total)
+            acc_t = np.float64
+        else:
+            total = np.float32(0.0)
+            for x in w32:
+                total = np.float32(total + x)
+            weights = w32 / total
+            acc_t = np.float32
+    else:
+        weights = np.ones(n_chunks) / float(n_chunks) if n_chunks else np.ones(0)
+        acc_t = np.float64
+    order = int_set_order(page_indices_b)
+    acc = {p: acc_t(0) for p in order}
+    for page, weight in zip(page_indices_b, weights[:n_hits]):
+        acc[page] = acc_t(acc[page] + acc_t(weight))
+    if not acc:
+        return 0                                                                               # :471-473
+    best = order[0]
+    for p in order[1:]:
+        if acc[p] > acc[best]:                                                                 # max(): first maximum
+            best = p
+    return best

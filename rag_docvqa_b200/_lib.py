@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Struc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -37,7 +37,7 @@ class GatherArgsStruct(Structure):
                 ("max_seg", c_int32)] + [(n, c_void_p) for n in (
                     "seg_ws", "out_ids", "out_boxes", "out_mask", "out_labels", "full_len", "status", "hit_chunk",
                     "hit_page", "hit_label", "hit_nwords", "hit_bbox", "hit_rect", "sims", "topk_val")] + [
-                    ("max_rows", c_int32), ("reserved", c_int32)]
+                    ("max_rows", c_int32), ("reserved", c_int32), ("emit_order", c_void_p), ("emit_cnt", c_void_p)]
 
 
 class PageStoreStruct(Structure):
@@ -97,6 +97,10 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p]),
     "rdv_visual_pack": (c_int32, [POINTER(PageStoreStruct), POINTER(VisualArgsStruct), c_void_p]),
     "rdv_pix2struct_patches": (c_int32, [POINTER(PageStoreStruct), POINTER(P2SArgsStruct), c_void_p]),
+    "rdv_rerank_order": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, ctypes.c_double, c_int32, c_int32,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_page_vote": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                c_void_p, c_void_p]),
     "rdv_gather_vt5_inputs": (c_int32, [POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
 }
 

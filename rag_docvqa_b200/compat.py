@@ -30,7 +30,28 @@ def _make_replacements():
         "VisualRetriever": retriever.VisualRetriever,
         "mean_pooling": _mean_pooling_dispatch(functional),
         "late_interaction": _late_interaction_dispatch(functional),
+        "Reranker": _reranker_class(),
     }
+
+
+def _reranker_class():
+    from . import postproc
+
+    class Reranker(postproc.Reranker):
+        """reference constructor (src/_modules.py:1541-1556): without a cross-encoder argument the REFERENCE's own
+        CrossEncoder / FlagLLMReranker model class is built (the models stay the reference's); everything after its
+        forward() runs through rdv_rerank_order."""
+
+        def __init__(self, config: dict, cross_encoder=None):
+            if cross_encoder is None:
+                ref = sys.modules.get("src._modules")
+                if ref is None:
+                    raise ValueError("Reranker: no cross-encoder given and src._modules is not imported")
+                cls = ref.FlagLLMReranker if "gemma" in config.get("reranker_weights", "") else ref.CrossEncoder
+                cross_encoder = cls(config)
+            super().__init__(config, cross_encoder)
+
+    return Reranker
 
 
 def _mean_pooling_dispatch(functional):
@@ -48,7 +69,7 @@ def _late_interaction_dispatch(functional):
 
 
 def install(modules=None) -> list:
-    """Rebinds the four names in every loaded `src.*` module of the reference that defines or imported
+    """Rebinds the five names in every loaded `src.*` module of the reference that defines or imported
     them.  Returns the list of (module, name) pairs patched.  Idempotent; undo with uninstall()."""
     repl = replacements()
     done = []

@@ -227,10 +227,25 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
         __syncthreads();
     }
 
+    // ---- D': the reranker's index list (src/_modules.py:1592-1595) applies to retrieve()'s OUTPUT order: positions of
+    // the order above are permuted / dropped; the words of every hit (dedup against better hits) stay as retrieved
+    int n_out = cnt;
+    if (a.emit_order) {
+        n_out = min(a.emit_cnt[b], cnt);
+        int v = 0;
+        if (tid < n_out) {
+            const int r = a.emit_order[(size_t)b * k + tid];
+            v = s_order[min(max(r, 0), cnt - 1)];
+        }
+        __syncthreads();
+        if (tid < n_out) s_order[tid] = v;
+        __syncthreads();
+    }
+
     // per-hit metadata, in OUTPUT order
     if (tid < k) {
         const size_t o = (size_t)b * k + tid;
-        if (tid < cnt) {
+        if (tid < n_out) {
             const int i = s_order[tid];
             const int gc = s_chunk[i];
             a.hit_chunk[o] = (int32_t)(gc - c0);
@@ -258,13 +273,13 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
     // ---- E: token offsets of the ordered hits (warp 1, while warp 0 writes the per-hit metadata) --------
     if (tid == 32) {
         int pos = plen;
-        for (int r = 0; r < cnt; ++r) {
+        for (int r = 0; r < n_out; ++r) {
             const int i = s_order[r];
             if (r > 0 && s_nwords[i] > 0) pos += a.n_sep;       // flatten(): separator before non-empty sublists
             s_start[r] = pos;
             pos += s_ntok[i];
         }
-        s_start[cnt] = pos;
+        s_start[n_out] = pos;
         s_total = pos;
         a.full_len[b] = pos + 1;                                // + EOS, before truncation (src/VT5.py:170)
         a.status[b] = s_overflow;
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_vt5_kernel(const Gather
             } else {
                 // ordered hit r with s_start[r] - sep <= pos < s_start[r+1]-sep(next)
                 int r = 0;
-                while (r + 1 < cnt) {
+                while (r + 1 < n_out) {
                     const int nxt = s_order[r + 1];
                     const int nxt_begin = s_start[r + 1] - ((s_nwords[nxt] > 0) ? a.n_sep : 0);
                     if (pos < nxt_begin) break;
@@ -353,7 +368,7 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
     RDV_REQUIRE(args->topk_idx && args->topk_cnt && args->prompt_off && args->prompt_ids && args->seg_ws &&
                 args->out_ids && args->out_boxes && args->out_mask && args->full_len && args->status &&
                 args->hit_chunk && args->hit_page && args->hit_label && args->hit_nwords && args->hit_bbox &&
-                args->hit_rect && (args->n_sep == 0 || args->sep_ids), RDV_E_INVALID,
+                args->hit_rect && (args->n_sep == 0 || args->sep_ids) && (!args->emit_order || args->emit_cnt), RDV_E_INVALID,
                 "gather_vt5_inputs: args has a null array");
     RDV_REQUIRE(aligned16(args->out_boxes) && aligned16(ds->chunk_bbox) && aligned16(ds->tok_rec), RDV_E_ALIGN,
                 "gather_vt5_inputs: out_boxes / chunk_bbox / tok_rec must be 16-byte aligned");

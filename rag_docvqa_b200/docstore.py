@@ -214,7 +214,8 @@ class DocStore:
                        include_surroundings: int = 0, reorder_chunks: bool = False, sep_ids: Sequence[int] = (),
                        eos_id: int = 1, pad_id: int = 0, max_len: int = 512, with_layout_labels: bool = False,
                        max_seg: int = 32, sims: Optional[torch.Tensor] = None, topk_val: Optional[torch.Tensor] = None,
-                       max_rows: int = 0) -> "GatherPlan":
+                       max_rows: int = 0, emit_order: Optional[torch.Tensor] = None,
+                       emit_cnt: Optional[torch.Tensor] = None) -> "GatherPlan":
         """Allocates the outputs and fills the argument block of rdv_gather_vt5_inputs (no launch).
         With `sims` (all similarities of the batch, chunk order) the kernel selects the top-k itself and
         writes topk_idx / topk_val / topk_cnt: a step is then score kernel + this kernel."""
@@ -268,7 +269,10 @@ class DocStore:
                 raise ValueError("fused selection needs topk_val")
             t["sims"], t["topk_val"] = sims, topk_val
             a.sims = sims.data_ptr(); a.topk_val = topk_val.data_ptr(); a.max_rows = int(max_rows)
-        return GatherPlan(self, a, t, max_len, max_seg)
+        plan = GatherPlan(self, a, t, max_len, max_seg)
+        if emit_order is not None:
+            plan.set_emit_order(emit_order, emit_cnt)
+        return plan
 
     def gather(self, topk_idx: torch.Tensor, topk_cnt: torch.Tensor, prompt_ids: Sequence[Sequence[int]],
                **options) -> PackedInputs:
@@ -286,6 +290,22 @@ class GatherPlan:
         self.store, self.args, self.t, self.max_len, self.max_seg = store, args, tensors, max_len, max_seg
         self._ds_ref = ctypes.byref(store.struct)
         self._args_ref = ctypes.byref(args)
+
+    def set_emit_order(self, order: Optional[torch.Tensor], cnt: Optional[torch.Tensor]) -> None:
+        """The reranker's index list (postproc.rerank_order): (B, k) int32 positions of retrieve()'s output order and
+        the number kept per document; None = everything in retrieval order.  The next launch() rebuilds the packed
+        tensors and the hit_* arrays IN PLACE in that order."""
+        if order is None:
+            self.t.pop("emit_order", None); self.t.pop("emit_cnt", None)
+            self.args.emit_order = None; self.args.emit_cnt = None
+            return
+        B, k = self.t["topk_idx"].shape
+        if cnt is None or tuple(order.shape) != (B, k) or tuple(cnt.shape) != (B,):
+            raise ValueError("emit_order must be (B, k) with emit_cnt (B,)")
+        if order.dtype != torch.int32 or cnt.dtype != torch.int32 or not order.is_cuda or not cnt.is_cuda:
+            raise ValueError("emit_order / emit_cnt must be int32 CUDA tensors")
+        self.t["emit_order"], self.t["emit_cnt"] = order.contiguous(), cnt.contiguous()
+        self.args.emit_order = self.t["emit_order"].data_ptr(); self.args.emit_cnt = self.t["emit_cnt"].data_ptr()
 
     def launch(self, stream: Optional[int] = None) -> None:
         dev = self.store.device

@@ -394,13 +394,14 @@ class Retriever(StatComponent):
     def retrieve_packed(self, text_embeddings, question_embeddings, store, prompt_ids, sep_ids=(),
                         eos_id: int = 1, pad_id: int = 0, max_source_length: int = 512,
                         with_layout_labels: bool = False, pages=None, image_size: int = 224, resample: int = 3,
-                        image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5)):
+                        image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), return_plan: bool = False):
         """B200-native fast path: score -> top-k -> device gather straight into the generator's
         input_ids / boxes / attention_mask (what flatten + VT5.prepare_inputs_for_vqa build on the host,
         src/utils.py:233-253, src/VT5.py:141-185) for a pre-tokenised `DocStore`.  No Python lists.
         With `pages` (a PageStore) the retrieved patches are also cropped, grid-packed and resized on the device
         (page.crop + concatenate_patches(mode="grid") + the feature extractor's resize, src/_modules.py:2102-2121,
-        src/utils.py:180-231, src/_modules.py:133); returns (packed, res, visual) in that case."""
+        src/utils.py:180-231, src/_modules.py:133); returns (packed, res, visual) in that case.  `return_plan` appends
+        the GatherPlan, which postproc.Reranker.rerank_packed re-launches in the reranked order."""
         dev = question_embeddings.device if question_embeddings.is_cuda else self.device
         on_host = len(text_embeddings) and not any(e.is_cuda for e in text_embeddings)
         emb = [] if on_host else [_to_device(e, dev) for e in text_embeddings]
@@ -430,7 +431,8 @@ class Retriever(StatComponent):
             packed = plan.finish()
         res = F.ScoreTopK(list(torch.split(sims, table.sizes)) if B else [], sims, topk_idx, topk_val, topk_cnt,
                           table.sizes)
-        return (packed, res) if pages is None else (packed, res, visual)
+        out = (packed, res) if pages is None else (packed, res, visual)
+        return out + (plan,) if return_plan else out
 
 
 # ====================================================================================================

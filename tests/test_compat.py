@@ -40,6 +40,10 @@ def test_signatures_equal_live_reference_and_install_rebinds():
     assert params(Retriever._get_top_k) == params(modules.Retriever._get_top_k)
     assert params(VisualRetriever.retrieve) == params(modules.VisualRetriever.retrieve)
     assert params(VisualRetriever._get_top_k) == params(modules.VisualRetriever._get_top_k)
+    from rag_docvqa_b200.postproc import Reranker
+    assert params(Reranker.rerank) == params(modules.Reranker.rerank)                  # src/_modules.py:1558-1563
+    assert params(Reranker.batch_rerank) == params(modules.Reranker.batch_rerank)      # :1597-1602
+    assert params(Reranker.__init__) == params(modules.Reranker.__init__)              # :1541-1545
     ref_retriever = modules.Retriever
     try:
         done = compat.install()
