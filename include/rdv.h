@@ -318,6 +318,26 @@ RDV_API int rdv_page_vote(const int32_t* d_hit_page, const int32_t* d_hit_cnt, c
 
 
 /* ---------------------------------------------------------------------------------------------
+ * Chunker: OCR words -> layout boxes.
+ *
+ * rdv_layout_assign: containment_ratio(word, layout box) > 0.5 (src/utils.py:328-341) for every word x layout box of
+ *   every page (src/_modules.py:1023-1033).  P pages, W words, G layout boxes, all arrays in device memory:
+ *   d_word_box (W,4) f64 / d_page_word_off[P+1]; d_lay_box (G,4) f64, d_lay_label[G] / d_page_lay_off[P+1], the boxes
+ *   of a page in the order the reference visits them (sorted by (xmin, ymin), :1006-1018).  Words are processed in
+ *   groups of 32 consecutive words of one page: d_page_group_off[P+1] (prefix sums of ceil(words / 32)),
+ *   d_group_page[n_groups] (page of each group).  Outputs: d_bits -- for layout box g a row of ceil(words of its
+ *   page / 32) uint32 starting at d_bits_off[g] (bit l of word j = word 32*j + l of the page is inside);
+ *   d_word_label[W] -- the label of the last containing box in visiting order, else default_label (:1003, :1030).
+ *   float64, every operation rounded individually in the reference's order: the decision is bit-exact against Python
+ *   floats (boxes given as ints are exact below 2^26).
+ * ------------------------------------------------------------------------------------------- */
+RDV_API int rdv_layout_assign(const double* d_word_box, const int32_t* d_page_word_off, const double* d_lay_box,
+                              const int32_t* d_lay_label, const int32_t* d_page_lay_off, const int32_t* d_group_page,
+                              const int32_t* d_page_group_off, int32_t n_groups, int32_t default_label,
+                              const int64_t* d_bits_off, uint32_t* d_bits, int32_t* d_word_label, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
  * Retrieved patches -> the generator's visual input.
  *
  * Replaces, for page images resident on the device, the host work that follows retrieval when

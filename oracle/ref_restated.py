@@ -691,3 +691,126 @@ def page_vote(page_indices_b: Sequence[int], similarities_b: Optional[np.ndarray
         if acc[p] > acc[best]:                                                                 # max(): first maximum
             best = p
     return best
+
+
+# --------------------------------------------------------------------------------------
+# f4: Chunker -- words -> layout boxes -> chunks
+#     reference: src/utils.py:328-341 (containment_ratio), src/_modules.py:872-1100 (Chunker.get_chunks)
+# --------------------------------------------------------------------------------------
+def containment_ratio(small_box, large_box) -> float:                                         # src/utils.py:328-341
+    x1 = max(small_box[0], large_box[0]); y1 = max(small_box[1], large_box[1])
+    x2 = min(small_box[2], large_box[2]); y2 = min(small_box[3], large_box[3])
+    inter_area = max(0, x2 - x1) * max(0, y2 - y1)
+    small_area = (small_box[2] - small_box[0]) * (small_box[3] - small_box[1])
+    return inter_area / small_area if small_area > 0 else 0
+
+
+class ChunkStats:
+    """The four counters Chunker keeps (src/_modules.py:855-866) as plain dicts; zero entries stay, as with the
+    reference's subtract-then-add bookkeeping."""
+    def __init__(self):
+        self.chunk_size_dist, self.n_chunks_per_page_dist = {}, {}
+        self.n_chunks_per_doc_dist, self.n_chunks_per_layout_dist = {}, {}
+
+    @staticmethod
+    def add(d, key, value=1):
+        d[key] = d.get(key, 0) + value
+
+    def as_dict(self):
+        return {k: {str(a): b for a, b in getattr(self, k).items()} for k in
+                ("chunk_size_dist", "n_chunks_per_page_dist", "n_chunks_per_doc_dist", "n_chunks_per_layout_dist")}
+
+
+def make_chunks(words, boxes, tag, words_lst, boxes_lst, tag_lst, chunk_size, overlap, tol, stats: ChunkStats) -> int:
+    """The closure of get_chunks (:906-938): windows of chunk_size words every chunk_size - overlap words; a window is
+    folded into the previous chunk when the sizes -- by the reference's own arithmetic, prev + len(window) - overlap,
+    which can go below the true length -- stay within chunk_size * (1 + tol)."""
+    prev, made = 0, 0
+    for i in range(0, len(words), chunk_size - overlap):
+        cw, cb = words[i:i + chunk_size], boxes[i:i + chunk_size]
+        size = len(cw)
+        if i > 0 and tag == tag_lst[-1] and prev + (size - overlap) <= chunk_size * (1 + tol):
+            size = prev + size - overlap
+            words_lst[-1].extend(cw[overlap:]); boxes_lst[-1].extend(cb[overlap:])
+            stats.add(stats.chunk_size_dist, prev, -1); stats.add(stats.chunk_size_dist, size)
+        else:
+            tag_lst.append(tag); words_lst.append(cw); boxes_lst.append(cb)
+            stats.add(stats.chunk_size_dist, len(cw))
+            made += 1
+        prev = size
+    return made
+
+
+def get_chunks(words, boxes, layout_info=None, chunk_size: int = 60, overlap: int = 10, tol: float = 0.2,
+               page_retrieval: str = "concat", default_label: int = 1, cluster_layouts: bool = False):
+    """Chunker.get_chunks (:872-1100).  Returns the reference's 5-tuple and the counters."""
+    from collections import Counter
+    stats = ChunkStats()
+    bs = len(words)
+    lay_boxes = lay_labels = lay_clusters = None
+    if layout_info != [[]] and layout_info is not None:                                       # :892-898
+        lay_boxes = [[pg["boxes"] for pg in layout_info[b]] for b in range(bs)]
+        lay_labels = [[pg["labels"] for pg in layout_info[b]] for b in range(bs)]
+        if "clusters" in layout_info[0][0].keys() and cluster_layouts:
+            lay_clusters = [[pg["clusters"] for pg in layout_info[b]] for b in range(bs)]
+    out_labels, out_pages, out_words, out_boxes, out_word_labels = [], [], [], [], []
+    for b in range(bs):
+        d_labels, d_pages, d_words, d_boxes, d_word_labels, d_n = [], [], [], [], [], 0
+        for p, (page_words, page_boxes) in enumerate(zip(words[b], boxes[b])):
+            if not isinstance(page_words, list):                                              # :957-960
+                page_boxes = page_boxes.tolist()
+            if len(page_boxes) > 0 and not isinstance(page_boxes[0], list):
+                page_boxes = [pb.tolist() for pb in page_boxes]
+            if page_retrieval == "oracle":                                                    # :962-974
+                d_pages.append(p); d_words.append(page_words); d_boxes.append(page_boxes)
+                d_labels.append(default_label); d_word_labels.append([default_label] * len(page_words))
+                d_n += 1
+                stats.add(stats.chunk_size_dist, len(page_words)); stats.add(stats.n_chunks_per_page_dist, 1)
+                continue
+            if lay_boxes is None or len(lay_boxes[b][p]) == 0:                                # :976-990
+                n = make_chunks(page_words, page_boxes, p, d_words, d_boxes, d_pages, chunk_size, overlap, tol, stats)
+                d_labels.extend([default_label] * n); d_word_labels.append([default_label] * len(page_words))
+                d_n += n
+                stats.add(stats.n_chunks_per_page_dist, n)
+                continue
+            pl_boxes, pl_labels = lay_boxes[b][p], lay_labels[b][p]
+            pl_clusters = lay_clusters[b][p].tolist() if lay_clusters else None
+            order = sorted(range(len(pl_boxes)), key=lambda j: (pl_boxes[j][0], pl_boxes[j][1]))   # :1006-1018, stable
+            pl_boxes = [pl_boxes[j] for j in order]; pl_labels = [pl_labels[j] for j in order]
+            if pl_clusters:
+                pl_clusters = [pl_clusters[j] for j in order]
+            word_labels = [default_label] * len(page_words)
+            inside_w, inside_b = [], []
+            for lbox, llabel in zip(pl_boxes, pl_labels):                                     # :1023-1033
+                ws, bx = [], []
+                for i, (word, box) in enumerate(zip(page_words, page_boxes)):
+                    if containment_ratio(box, lbox) > 0.5:
+                        ws.append(word); bx.append(box); word_labels[i] = llabel
+                inside_w.append(ws); inside_b.append(bx)
+            group_labels = list(pl_labels)
+            if pl_clusters:                                                                   # :1035-1063
+                cw, cb, cl, slot = [], [], [], {}
+                for ws, bx, llabel, cluster in zip(inside_w, inside_b, pl_labels, pl_clusters):
+                    if cluster == -1 or cluster not in slot:
+                        if cluster != -1:
+                            slot[cluster] = len(cw)
+                        cw.append(ws); cb.append(bx); cl.append(Counter([llabel]))
+                    else:
+                        j = slot[cluster]
+                        cw[j].extend(ws); cb[j].extend(bx); cl[j][llabel] += 1
+                inside_w, inside_b = cw, cb
+                group_labels = [c.most_common(1)[0][0] for c in cl]
+            l_words, l_boxes, l_tags, page_n = [], [], [], 0
+            for lb, (ws, bx, glabel) in enumerate(zip(inside_w, inside_b, group_labels)):      # :1064-1076
+                n = make_chunks(ws, bx, lb, l_words, l_boxes, l_tags, chunk_size, overlap, tol, stats)
+                page_n += n
+                d_labels.extend([glabel] * n)
+                stats.add(stats.n_chunks_per_layout_dist, n)
+            d_pages.extend([p] * len(l_words)); d_words.extend(l_words); d_boxes.extend(l_boxes)
+            d_word_labels.append(word_labels)
+            d_n += page_n
+            stats.add(stats.n_chunks_per_page_dist, page_n)
+        out_labels.append(d_labels); out_pages.append(d_pages); out_words.append(d_words); out_boxes.append(d_boxes)
+        out_word_labels.append(d_word_labels)
+        stats.add(stats.n_chunks_per_doc_dist, d_n)
+    return (out_words, out_boxes, out_labels, out_pages, out_word_labels), stats

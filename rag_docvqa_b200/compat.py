@@ -31,7 +31,13 @@ def _make_replacements():
         "mean_pooling": _mean_pooling_dispatch(functional),
         "late_interaction": _late_interaction_dispatch(functional),
         "Reranker": _reranker_class(),
+        "Chunker": _chunker_class(),
     }
+
+
+def _chunker_class():
+    from .chunker import Chunker
+    return Chunker
 
 
 def _reranker_class():
@@ -69,7 +75,7 @@ def _late_interaction_dispatch(functional):
 
 
 def install(modules=None) -> list:
-    """Rebinds the five names in every loaded `src.*` module of the reference that defines or imported
+    """Rebinds the six names in every loaded `src.*` module of the reference that defines or imported
     them.  Returns the list of (module, name) pairs patched.  Idempotent; undo with uninstall()."""
     repl = replacements()
     done = []

@@ -106,16 +106,23 @@ __global__ void __launch_bounds__(kPostWarps * 32) page_vote_kernel(
     const int n_hits = min(min(hit_cnt[b], k), n_doc);        // zip(pages, weights) stops at the shorter one
     const bool f32_acc = weighted && !legacy_promotion;       // NEP 50: int 0 + float32 stays float32
     // ---- sum(w): sequential, in chunk order, starting from the Python int 0 (src/RAGVT5.py:462) ----
+    // The chain of dependent adds is the whole cost (10 k chunks: 10 k adds), so only the chain that is needed runs, the
+    // broadcasts are unrolled ahead of it, and the tail is padded with +0.0 (x + 0.0 == x: a sum that starts at +0 is
+    // never -0).
     double total = 0.0;
     float total32 = 0.0f;
     if (weighted) {
         for (int base = 0; base < n_doc; base += 32) {
             const float v = base + lane < n_doc ? __ldg(sims + c0 + base + lane) : 0.0f;
-            const int m = min(32, n_doc - base);
-            for (int j = 0; j < m; ++j) {
-                const float x = __shfl_sync(0xffffffffu, v, j);
-                total = __dadd_rn(total, (double)x);
-                total32 = __fadd_rn(total32, x);
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __shfl_sync(0xffffffffu, v, j);
+            if (legacy_promotion) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) total = __dadd_rn(total, (double)x[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) total32 = __fadd_rn(total32, x[j]);
             }
         }
     }

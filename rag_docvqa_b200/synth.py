@@ -215,3 +215,49 @@ def make_tokens_for_words(words_text_chunks, seed: int = 0, vocab: int = 32000):
                     n_tok = int(rng.choice([1, 2, 3], p=[0.6, 0.3, 0.1]))
                     table[w] = [int(t) for t in rng.randint(3, vocab, size=n_tok)]
     return table
+
+
+def make_chunker_batch(seed: int, docs: int = 4, max_pages: int = 6, max_words: int = 400, max_layouts: int = 14,
+                       clusters: bool = False, degenerate: bool = True, numpy_pages: bool = False):
+    """Chunker.get_chunks inputs in the reference's format (src/_modules.py:872-898): words [B][pages][n] str, boxes
+    [B][pages][n][4] float 0..1, layout_info [B][pages] {"boxes": [n_l][4], "labels": [n_l] (, "clusters": ndarray)}.
+    Words are laid out on text lines; layout boxes are rectangles over the page, some overlapping, some cutting words
+    exactly in half (ratio == 0.5 is NOT inside), plus pages without layout boxes / without words, zero-area words and
+    duplicate (xmin, ymin) keys for the stable sort."""
+    rng = np.random.RandomState(seed)
+    words, boxes, info = [], [], []
+    for b in range(docs):
+        n_pages = int(rng.randint(1, max_pages + 1))
+        d_words, d_boxes, d_info = [], [], []
+        for p in range(n_pages):
+            n = int(rng.randint(0, max_words + 1)) if (degenerate and rng.rand() < 0.15) else int(rng.randint(max_words // 4, max_words + 1))
+            if degenerate and rng.rand() < 0.05:
+                n = 0
+            per_line = int(rng.randint(6, 16))
+            line = np.arange(n) // per_line
+            col = np.arange(n) % per_line
+            # a 1/1024 grid keeps coordinates exactly representable, so exact halves (ratio == 0.5) really occur
+            x0 = (32 + col * 60 + rng.randint(0, 8, size=n)) / 1024.0
+            y0 = (40 + line * 24) / 1024.0 % 0.95
+            x1 = x0 + rng.choice([16, 32, 48, 56], size=n) / 1024.0
+            y1 = y0 + 16 / 1024.0
+            if degenerate and n:
+                z = rng.rand(n) < 0.02
+                x1 = np.where(z, x0, x1)                      # zero-area word: ratio 0 by definition
+            pb = np.stack([x0, y0, x1, y1], axis=1)
+            d_words.append(["w%d" % i for i in rng.randint(0, 5000, size=n)])
+            d_boxes.append(pb if numpy_pages else pb.tolist())
+            n_l = 0 if (degenerate and rng.rand() < 0.2) else int(rng.randint(1, max_layouts + 1))
+            lx0 = rng.randint(0, 700, size=n_l) // 8 * 8
+            ly0 = rng.randint(0, 800, size=n_l) // 8 * 8
+            lx1 = lx0 + rng.randint(64, 600, size=n_l) // 8 * 8
+            ly1 = ly0 + rng.randint(24, 400, size=n_l) // 8 * 8
+            if degenerate and n_l > 2:
+                lx0[1], ly0[1] = lx0[0], ly0[0]               # equal sort keys: order must stay as given
+            lb = (np.stack([lx0, ly0, lx1, ly1], axis=1) / 1024.0).tolist()
+            page = {"boxes": lb, "labels": [int(x) for x in rng.randint(0, 11, size=n_l)]}
+            if clusters:
+                page["clusters"] = rng.choice([-1, -1, 0, 1, 2], size=n_l).astype(np.int64)
+            d_info.append(page)
+        words.append(d_words); boxes.append(d_boxes); info.append(d_info)
+    return words, boxes, info

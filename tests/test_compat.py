@@ -44,6 +44,9 @@ def test_signatures_equal_live_reference_and_install_rebinds():
     assert params(Reranker.rerank) == params(modules.Reranker.rerank)                  # src/_modules.py:1558-1563
     assert params(Reranker.batch_rerank) == params(modules.Reranker.batch_rerank)      # :1597-1602
     assert params(Reranker.__init__) == params(modules.Reranker.__init__)              # :1541-1545
+    from rag_docvqa_b200.chunker import Chunker
+    assert params(Chunker.get_chunks) == params(modules.Chunker.get_chunks)            # :872-878
+    assert params(Chunker.__init__) == params(modules.Chunker.__init__)
     ref_retriever = modules.Retriever
     try:
         done = compat.install()
