@@ -685,6 +685,41 @@ def run_ours(args):
                         canvas.paste(p_, xy)
                     canvas.resize((224, 224), resample=_Image.Resampling.BICUBIC)
                 extras["visual_pack"]["cpu_reference_ms"] = (time.perf_counter() - t0) * 1e3 * w.docs / min(w.docs, 16)
+                # what consumes the hits: reranker index list + re-emission of the packed inputs in that
+                # order, and the page vote, all on the device (the cross-encoder is a model: random scores stand in for it)
+                from rag_docvqa_b200 import postproc as _pp
+                pk, rs, gplan = retr.retrieve_packed(batches[0]["text_embeddings"], batches[0]["question_embeddings"], store,
+                                                     prompts, return_plan=True)
+                ce_scores = torch.rand((w.docs, w.k), device=dev)
+                row_off_d = torch.from_numpy(np.concatenate([[0], np.cumsum(rs.sizes)]).astype(np.int64)).to(dev)
+
+                def rerank_step(i):
+                    order, kept, _ = _pp.rerank_order(ce_scores, rs.topk_cnt, 0.4, 5, 1)
+                    gplan.set_emit_order(order, kept)
+                    gplan.launch()
+                for _ in range(3):
+                    rerank_step(0)
+                extras["rerank_packed_ms"] = timed_loop(rerank_step, 20, torch.cuda.synchronize) / 20
+                for _ in range(3):
+                    _pp.page_vote(pk.hit_page, rs.topk_cnt, rs.sims, row_off_d, True)
+                extras["page_vote_weighted_ms"] = timed_loop(
+                    lambda i: _pp.page_vote(pk.hit_page, rs.topk_cnt, rs.sims, row_off_d, True), 20, torch.cuda.synchronize) / 20
+                # what feeds the path: Chunker.get_chunks with layout boxes, word x box containment on
+                # the device, against the oracle's Python loops (16 documents)
+                from rag_docvqa_b200.chunker import Chunker as _Chunker
+                cw, cb, ci = synth.make_chunker_batch(77, docs=16, max_pages=20, max_words=700, max_layouts=30, degenerate=False)
+                chunker = _Chunker({**cfg, "page_retrieval": "concat"})
+                chunker.get_chunks(cw[:2], cb[:2], ci[:2], question_id=[0, 1])
+                t0 = time.perf_counter()
+                got_chunks = chunker.get_chunks(cw, cb, ci, question_id=list(range(16)))
+                t_gpu = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                want_chunks, _ = R_.get_chunks(cw, cb, ci)
+                t_cpu = time.perf_counter() - t0
+                extras["chunker_get_chunks"] = {
+                    "documents": 16, "pages": sum(len(d) for d in cw), "words": sum(len(p) for d in cw for p in d),
+                    "word_x_layout_box_pairs": sum(len(p) * len(g["boxes"]) for d, gi in zip(cw, ci) for p, g in zip(d, gi)),
+                    "s": t_gpu, "cpu_oracle_s": t_cpu, "identical": got_chunks[0] == want_chunks[0] and got_chunks[2] == want_chunks[2]}
         else:
             line["cpu_baseline"] = {"value": w.docs / st_best, "unit": "queries/s", "cores": threads, "kind": "port",
                                     "sample": "oracle score+topk on one full %s batch, best of %d reps" % (w.name, st_reps)}
