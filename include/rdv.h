@@ -411,9 +411,10 @@ RDV_API int rdv_visual_pack(const rdv_pagestore* ps, const rdv_visual_args* args
  *   out_start = first output row of the image within its document, row_offset = row ids already used by the
  *   document's earlier images, temp_off = offset (floats) of its horizontally resized rows in `temp`
  *   ((y1-y0) * cols*patch * 3 floats).
- * rdv_p2s_args: images[n_images], stats (2 floats per image: workspace), temp, doc_total[n_docs] = output rows used by
- *   each document, out (n_docs, max_total, 2 + patch*patch*3) fp32, mask (n_docs, max_total) fp32;
- *   max_rw / max_rwh = largest resized width / resized width*height over the images (launch bounds).
+ * rdv_p2s_args: images[n_images], stats (16 bytes per image: workspace for the exact byte sums, zeroed by the call),
+ *   temp, doc_total[n_docs] = output rows used by each document, out (n_docs, max_total, 2 + patch*patch*3) fp32,
+ *   mask (n_docs, max_total) fp32; max_rw / max_rwh / max_h = largest resized width / resized width*height / crop
+ *   height over the images (launch bounds; n_images <= 65535).
  * fp32 like the reference; results agree with torch's CPU kernel to float rounding (tests state the tolerance).
  * ------------------------------------------------------------------------------------------- */
 typedef struct rdv_p2s_img {
@@ -429,11 +430,13 @@ typedef struct rdv_p2s_args {
     int32_t max_total, patch;
     int32_t do_normalize, max_rw;
     int64_t max_rwh;
-    float* stats;
+    void* stats;
     float* temp;
     const int32_t* doc_total;
     float* out;
     float* mask;
+    int32_t max_h;
+    int32_t reserved;
 } rdv_p2s_args;
 
 RDV_API int rdv_pix2struct_patches(const rdv_pagestore* ps, const rdv_p2s_args* args, void* stream);

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Struc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -58,7 +58,7 @@ class P2SArgsStruct(Structure):
     """Mirror of `rdv_p2s_args` (include/rdv.h)."""
     _fields_ = [("images", c_void_p), ("n_images", c_int32), ("n_docs", c_int32), ("max_total", c_int32), ("patch", c_int32),
                 ("do_normalize", c_int32), ("max_rw", c_int32), ("max_rwh", c_int64), ("stats", c_void_p), ("temp", c_void_p),
-                ("doc_total", c_void_p), ("out", c_void_p), ("mask", c_void_p)]
+                ("doc_total", c_void_p), ("out", c_void_p), ("mask", c_void_p), ("max_h", c_int32), ("reserved", c_int32)]
 
 
 # name -> (restype, argtypes); tests/test_abi.py checks this table against include/rdv.h

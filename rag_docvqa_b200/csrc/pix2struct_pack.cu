@@ -27,41 +27,71 @@ struct Params {
     rdv_p2s_args a;
 };
 
-// crop pixel as the reference sees it: uint8 -> float, black outside the page (PIL crop)
-__device__ __forceinline__ float crop_px(const unsigned char* page, int W, int H, int x, int y, int c) {
-    return (x >= 0 && x < W && y >= 0 && y < H) ? (float)__ldg(page + ((size_t)y * W + x) * 3 + c) : 0.f;
-}
+// ---- kernel 1: exact byte sums of every crop (kStatSlices blocks per image) -----------------------------------
+// The statistics are integers (sum of bytes, sum of squared bytes), so the reduction order does not matter: rows are
+// dealt to warps across kStatSlices blocks, each row is read as aligned 32-bit words (dp4a sums four bytes and their
+// squares in one instruction each), and every block adds its part to the image's two u64 accumulators.
+constexpr int kStatSlices = 16;
 
-// ---- kernel 1: whole-image mean and adjusted std (one block per image) -------------------------------------
+struct StatAcc { unsigned long long s, ss; };     // per image, zeroed by the entry point
+
 __global__ void __launch_bounds__(kThreads) p2s_stats_kernel(const Params P) {
-    const rdv_p2s_img& im = P.a.images[blockIdx.x];
-    const int tid = threadIdx.x;
+    const rdv_p2s_img& im = P.a.images[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned char* page = P.ps.pixels + P.ps.page_off[im.page];
     const int W = P.ps.page_wh[2 * im.page], H = P.ps.page_wh[2 * im.page + 1];
-    const int w = im.x1 - im.x0, h = im.y1 - im.y0;
-    unsigned long long s = 0, ss = 0;                               // exact: sums of bytes and of their squares
-    for (int y = im.y0 + tid / 32; y < im.y1; y += kThreads / 32) {
-        if (y < 0 || y >= H) continue;
-        const int xa = max(im.x0, 0), xb = min(im.x1, W);
-        const unsigned char* row = page + (size_t)y * W * 3;
-        for (int t = xa * 3 + (tid & 31); t < xb * 3; t += 32) { const unsigned v = __ldg(row + t); s += v; ss += v * v; }
+    const int xa = max(im.x0, 0), xb = min(im.x1, W);
+    const int ya = max(im.y0, 0), yb = min(im.y1, H);
+    unsigned long long s = 0, ss = 0;
+    for (int y = ya + blockIdx.x * (kThreads / 32) + (tid >> 5); y < yb; y += kStatSlices * (kThreads / 32)) {
+        const unsigned char* p0 = page + ((size_t)y * W + xa) * 3;
+        const unsigned char* p1 = page + ((size_t)y * W + xb) * 3;
+        if (p0 >= p1) continue;
+        const unsigned char* q0 = reinterpret_cast<const unsigned char*>((reinterpret_cast<uintptr_t>(p0) + 3) & ~uintptr_t(3));
+        const unsigned char* q1 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(p1) & ~uintptr_t(3));
+        unsigned rs = 0, rss = 0;                 // one row: < 2^32 (8192 pixels * 3 * 255^2 = 1.6e9)
+        if (q0 >= q1) {                           // too short for an aligned word
+            for (const unsigned char* p = p0 + lane; p < p1; p += 32) { const unsigned v = __ldg(p); rs += v; rss += v * v; }
+        } else {
+            if (p0 + lane < q0) { const unsigned v = __ldg(p0 + lane); rs += v; rss += v * v; }        // head: < 4 bytes
+            if (q1 + lane < p1) { const unsigned v = __ldg(q1 + lane); rs += v; rss += v * v; }        // tail: < 4 bytes
+            const unsigned* w0 = reinterpret_cast<const unsigned*>(q0);
+            const int nw = (int)((q1 - q0) >> 2);
+            for (int i = lane; i < nw; i += 32) {
+                const unsigned v = __ldg(w0 + i);
+                rs = __dp4a(v, 0x01010101u, rs);
+                rss = __dp4a(v, v, rss);
+            }
+        }
+        s += rs; ss += rss;
     }
     __shared__ unsigned long long sh_s[kThreads / 32], sh_ss[kThreads / 32];
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-    if ((tid & 31) == 0) { sh_s[tid >> 5] = s; sh_ss[tid >> 5] = ss; }
+    if (lane == 0) { sh_s[tid >> 5] = s; sh_ss[tid >> 5] = ss; }
     __syncthreads();
     if (tid == 0) {
         for (int i = 1; i < kThreads / 32; ++i) { s += sh_s[i]; ss += sh_ss[i]; }
-        const double n = (double)w * (double)h * 3.0;
-        const double mean = (double)s / n;
-        double var = (double)ss / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float std32 = (float)sqrt(var);
-        const double floor_ = 1.0 / sqrt(n);                       // max(std, 1.0 / math.sqrt(np.prod(shape)))  (:188)
-        const float adj = ((double)std32 > floor_) ? std32 : (float)floor_;
-        P.a.stats[2 * blockIdx.x] = P.a.do_normalize ? (float)mean : 0.f;
-        P.a.stats[2 * blockIdx.x + 1] = P.a.do_normalize ? adj : 1.f;
+        StatAcc* acc = reinterpret_cast<StatAcc*>(P.a.stats) + blockIdx.y;
+        if (s) atomicAdd(&acc->s, s);
+        if (ss) atomicAdd(&acc->ss, ss);
     }
+}
+
+// mean and adjusted std of image `img` from its byte sums (:175-196), and the 256 possible normalised pixel values
+// ((v - mean) / adj in fp32, the reference's own two operations) as a shared-memory table: the resize reads bytes.
+__device__ __forceinline__ void normalised_lut(const Params& P, int img, float* lut /* [256] shared */) {
+    const rdv_p2s_img& im = P.a.images[img];
+    const StatAcc acc = reinterpret_cast<const StatAcc*>(P.a.stats)[img];
+    const double n = (double)(im.x1 - im.x0) * (double)(im.y1 - im.y0) * 3.0;
+    const double mean = (double)acc.s / n;
+    double var = (double)acc.ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float std32 = (float)sqrt(var);
+    const double floor_ = 1.0 / sqrt(n);                           // max(std, 1.0 / math.sqrt(np.prod(shape)))  (:188)
+    const float adj = P.a.do_normalize ? (((double)std32 > floor_) ? std32 : (float)floor_) : 1.f;
+    const float mean32 = P.a.do_normalize ? (float)mean : 0.f;
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = __fdiv_rn(__fsub_rn((float)v, mean32), adj);
+    __syncthreads();
 }
 
 // ATen's anti-aliased linear weights for output position i (upsample_bilinear2d_aa, align_corners = False), fp32
@@ -91,26 +121,39 @@ __device__ __forceinline__ void aa_taps(int i, int in_size, int out_size, Taps& 
 }
 
 // ---- kernel 2: horizontal pass (normalised crop rows -> temp rows of the resized width) ---------------------
+// grid (resized-width tiles, row chunks, images): a thread owns one output column for kRowsH consecutive rows, so its
+// taps are computed once and the grid fills the machine (8 documents x 5 crops: 3 x 28 x 40 blocks, was 3 x 40).
+constexpr int kRowsH = 8;
+
 __global__ void __launch_bounds__(kThreads) p2s_resize_h_kernel(const Params P) {
-    const rdv_p2s_img& im = P.a.images[blockIdx.y];
+    __shared__ float lut[256];
+    const rdv_p2s_img& im = P.a.images[blockIdx.z];
     const int rw = im.cols * P.a.patch, w = im.x1 - im.x0, h = im.y1 - im.y0;
+    const int ybeg = blockIdx.y * kRowsH;
+    if (ybeg >= h) return;                                          // whole block: no barrier is skipped by a part of it
+    normalised_lut(P, blockIdx.z, lut);
     const int X = blockIdx.x * kThreads + threadIdx.x;
     if (X >= rw) return;
     const unsigned char* page = P.ps.pixels + P.ps.page_off[im.page];
     const int W = P.ps.page_wh[2 * im.page], H = P.ps.page_wh[2 * im.page + 1];
-    const float mean = P.a.stats[2 * blockIdx.y], adj = P.a.stats[2 * blockIdx.y + 1];
     Taps t;
     aa_taps(X, w, rw, t);
     float* temp = P.a.temp + im.temp_off;
-    for (int y = 0; y < h; ++y) {
+    const int yend = min(h, ybeg + kRowsH);
+    const int sx0 = im.x0 + t.first;
+    for (int y = ybeg; y < yend; ++y) {
+        const int sy = im.y0 + y;
+        const bool row_in = sy >= 0 && sy < H;
+        const unsigned char* row = page + (size_t)(row_in ? sy : 0) * W * 3;
         float acc[3] = {0.f, 0.f, 0.f};
         for (int j = 0; j < t.count; ++j) {
-            const int sx = im.x0 + t.first + j, sy = im.y0 + y;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = __fdiv_rn(__fsub_rn(crop_px(page, W, H, sx, sy, c), mean), adj);      // normalize first (:220)
-                acc[c] = fmaf(v, t.w[j], acc[c]);
-            }
+            const int sx = sx0 + j;
+            const bool in = row_in && sx >= 0 && sx < W;           // black outside the page (PIL crop), then normalised (:220)
+            const unsigned char* px = row + (size_t)(in ? sx : 0) * 3;
+            const float wj = t.w[j];
+            acc[0] = fmaf(lut[in ? __ldg(px) : 0], wj, acc[0]);
+            acc[1] = fmaf(lut[in ? __ldg(px + 1) : 0], wj, acc[1]);
+            acc[2] = fmaf(lut[in ? __ldg(px + 2) : 0], wj, acc[2]);
         }
         float* o = temp + ((size_t)y * rw + X) * 3;
         o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
@@ -171,15 +214,19 @@ extern "C" int rdv_pix2struct_patches(const rdv_pagestore* ps, const rdv_p2s_arg
     RDV_REQUIRE(ps->page_wh && ps->page_off && ps->pixels, RDV_E_INVALID, "pix2struct_patches: page store has a null array");
     RDV_REQUIRE(args->out && args->mask && args->doc_total && (args->n_images == 0 || (args->images && args->stats && args->temp)),
                 RDV_E_INVALID, "pix2struct_patches: args has a null array");
-    RDV_REQUIRE(args->max_rw >= 0 && args->max_rwh >= 0, RDV_E_INVALID, "pix2struct_patches: bad launch bounds");
+    RDV_REQUIRE(args->max_rw >= 0 && args->max_rwh >= 0 && args->max_h >= 0 && args->max_h <= 65535 * p2s::kRowsH &&
+                args->n_images <= 65535, RDV_E_INVALID, "pix2struct_patches: bad launch bounds");
     p2s::Params P;
     P.ps = *ps;
     P.a = *args;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (args->n_images > 0) {
-        p2s::p2s_stats_kernel<<<args->n_images, p2s::kThreads, 0, s>>>(P);
+        cudaError_t me = cudaMemsetAsync(args->stats, 0, (size_t)args->n_images * sizeof(p2s::StatAcc), s);
+        if (me != cudaSuccess) return cuda_fail(me, "cudaMemsetAsync(p2s stats)");
+        p2s::p2s_stats_kernel<<<dim3(p2s::kStatSlices, args->n_images), p2s::kThreads, 0, s>>>(P);
         RDV_LAUNCH_CHECK("p2s_stats_kernel");
-        p2s::p2s_resize_h_kernel<<<dim3((args->max_rw + p2s::kThreads - 1) / p2s::kThreads, args->n_images), p2s::kThreads, 0, s>>>(P);
+        p2s::p2s_resize_h_kernel<<<dim3((args->max_rw + p2s::kThreads - 1) / p2s::kThreads,
+                                        (args->max_h + p2s::kRowsH - 1) / p2s::kRowsH, args->n_images), p2s::kThreads, 0, s>>>(P);
         RDV_LAUNCH_CHECK("p2s_resize_h_kernel");
         p2s::p2s_resize_v_kernel<<<dim3((args->max_rwh + p2s::kThreads - 1) / p2s::kThreads, args->n_images), p2s::kThreads, 0, s>>>(P);
         RDV_LAUNCH_CHECK("p2s_resize_v_kernel");

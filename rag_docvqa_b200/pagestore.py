@@ -189,7 +189,7 @@ def _pack_pix2struct(self, crops, max_total_patches: int = 2048, patch: int = 16
     o_tot = (images.nbytes + 15) // 16 * 16
     raw[o_tot:o_tot + doc_total.nbytes] = doc_total.view(np.uint8)
     small = blob.to(dev, non_blocking=True)
-    t = dict(small=small, stats=torch.empty((max(len(images), 1), 2), dtype=torch.float32, device=dev),
+    t = dict(small=small, stats=torch.empty((max(len(images), 1), 2), dtype=torch.int64, device=dev),   # byte sums
              temp=torch.empty((max(temp_floats, 1),), dtype=torch.float32, device=dev),
              out=torch.empty((self.B, max_total_patches, depth), dtype=torch.float32, device=dev),
              mask=torch.empty((self.B, max_total_patches), dtype=torch.float32, device=dev))
@@ -198,6 +198,7 @@ def _pack_pix2struct(self, crops, max_total_patches: int = 2048, patch: int = 16
     a.max_total, a.patch, a.do_normalize = max_total_patches, patch, 1 if normalize else 0
     a.max_rw = int((images["cols"] * patch).max()) if len(images) else 0
     a.max_rwh = int((images["cols"].astype(np.int64) * images["rows"] * patch * patch).max()) if len(images) else 0
+    a.max_h = int((images["y1"] - images["y0"]).max()) if len(images) else 0
     a.stats, a.temp, a.doc_total = t["stats"].data_ptr(), t["temp"].data_ptr(), small.data_ptr() + o_tot
     a.out, a.mask = t["out"].data_ptr(), t["mask"].data_ptr()
     with torch.cuda.device(dev):
