@@ -87,7 +87,7 @@ def test_integer_pixel_boxes_and_object_labels():
     rng = np.random.RandomState(9)
     n = 120
     x0, y0 = rng.randint(0, 800, size=n), rng.randint(0, 1000, size=n)
-    boxes = [[[int(a), int(b), int(a + w), int(b + 12)] for a, b, w in zip(x0, y0, rng.randint(1, 60, size=n))]]
+    boxes = [[[[int(a), int(b), int(a + w), int(b + 12)] for a, b, w in zip(x0, y0, rng.randint(1, 60, size=n))]]]
     words = [[["w%d" % i for i in range(n)]]]
     info = [[{"boxes": [[0, 0, 400, 500], [300, 300, 850, 1100], [0, 0, 400, 500]], "labels": ["title", "text", "table"]}]]
     got = ch.get_chunks(words, boxes, info, question_id=["q"])
