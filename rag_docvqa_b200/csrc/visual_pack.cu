@@ -144,13 +144,18 @@ __global__ void __launch_bounds__(kThreads) visual_layout_kernel(const Params P)
 }
 
 // ---- kernel 2: horizontal pass, canvas rows read through the layout ---------------------------------------
-// One block = one document x R consecutive canvas rows (R <= 8, as many as fit the row budget).  The R virtual
-// rows are staged in shared memory once (black, then the row segments of every patch that covers them), the
-// document's coefficient table sits beside them, and a thread owns one (output x, channel) for all R rows, so a
-// weight is fetched once per tap and applied R times.
+// One block = one document x kGroups groups of R consecutive canvas rows (R <= 8, as many as fit the row budget).
+// The R virtual rows of a group are staged in shared memory (black, then the row segments of every patch that covers
+// them: warp w stages row w), the document's coefficient table sits beside them for the whole block, and a thread owns
+// one (output x, channel) for all R rows, so a weight is fetched once per tap and applied R times.
+// The kernel is bound by instruction issue (ncu: 81 % issue-active, 1.06 G warp instructions for a C2 batch of which
+// the taps are a fifth), so what pays is fewer instructions around the taps.  Measured and rejected: rows staged as
+// RGBX words with one 32-bit shared load per tap (1 LDS + 3 extractions + 3 IMAD for 3 channel-taps instead of
+// 3 LDS.U8 + 3 IMAD: as many instructions, lower occupancy; 1.83 ms per C2 batch against 1.61).
 constexpr int kRowBudget = 64 * 1024;          // most bytes of staged rows
 constexpr int kCoeffBudget = 32 * 1024;        // most bytes of the coefficient table kept in shared memory (else L1/L2)
 constexpr int kMaxRows = 8;
+constexpr int kGroups = 4;                     // row groups per block: the coefficient table is loaded once for all of them
 
 __host__ __device__ __forceinline__ int row_pitch(int gw) { return (gw * 3 + 15) & ~15; }
 // shared memory the launch reserves for rows: 8 rows of the widest possible canvas, within the budget -- sized by
@@ -165,38 +170,38 @@ __host__ __device__ __forceinline__ int rows_per_block(int gw, int row_bytes) {
     return r < 1 ? 1 : (r > kMaxRows ? kMaxRows : r);
 }
 
-// n bytes global -> shared, any alignment on either side: destination words are assembled from two aligned source
-// words with a byte permute (one 32-bit store per 4 bytes instead of four byte loads and stores).  The source
+// n bytes global -> shared by ONE WARP, any alignment on either side: destination words are assembled from two aligned
+// source words with a byte permute (one 32-bit store per 4 bytes instead of four byte loads and stores).  The source
 // buffer's size is a multiple of 4, so the aligned word holding the last byte is readable.
-__device__ __forceinline__ void copy_row_bytes(unsigned char* dst, const unsigned char* __restrict__ src, int n, int tid) {
+__device__ __forceinline__ void copy_row_bytes(unsigned char* dst, const unsigned char* __restrict__ src, int n, int lane) {
     const int head = min(n, (int)((4u - (unsigned)(uintptr_t)dst) & 3u));
-    if (tid < head) dst[tid] = __ldg(src + tid);
+    if (lane < head) dst[lane] = __ldg(src + lane);
     const int words = (n - head) >> 2;
     uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
     const unsigned char* s0 = src + head;
     const unsigned sh = (unsigned)(uintptr_t)s0 & 3u;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - sh);
     const unsigned sel = 0x3210u + 0x1111u * sh;
-    for (int w = tid; w < words; w += kThreads) {
-        const uint32_t lo = __ldg(sw + w), hi = sh ? __ldg(sw + w + 1) : 0u;
-        dw[w] = __byte_perm(lo, hi, sel);
+    if (sh == 0) {
+        for (int w = lane; w < words; w += 32) dw[w] = __ldg(sw + w);
+    } else {
+        for (int w = lane; w < words; w += 32) dw[w] = __byte_perm(__ldg(sw + w), __ldg(sw + w + 1), sel);
     }
     const int done = head + (words << 2);
-    if (tid < n - done) dst[done + tid] = __ldg(src + done + tid);
+    if (lane < n - done) dst[done + lane] = __ldg(src + done + lane);
 }
 
 __global__ void __launch_bounds__(kThreads) visual_resize_h_kernel(const Params P) {
     const rdv_pagestore& ps = P.ps;
     const rdv_visual_args& a = P.a;
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int* hdr = doc_header(a, b);
     if (hdr[kHdrPad] != 0) return;
     const int rows = hdr[kHdrRows];
     const int gw = hdr[kHdrGridW], gh = hdr[kHdrGridH], n = hdr[kHdrN], row_first = hdr[kHdrRowFirst];
     const int row_bytes = row_bytes_for(a.max_page_w);
     const int R = rows_per_block(gw, row_bytes);
-    const int r_begin = blockIdx.x * R;
-    if (r_begin >= rows) return;
+    if (blockIdx.x * (R * kGroups) >= rows) return;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ int s_pat[kMaxK * 4];
     __shared__ int s_page[kMaxK];
@@ -212,53 +217,58 @@ __global__ void __launch_bounds__(kThreads) visual_resize_h_kernel(const Params 
         s_page[i] = ps.doc_page_off[b] + a.hit_page[(size_t)b * a.k + i];
         s_src[2 * i] = a.hit_rect[((size_t)b * a.k + i) * 4]; s_src[2 * i + 1] = a.hit_rect[((size_t)b * a.k + i) * 4 + 1];
     }
+    // the document's coefficient table: loaded ONCE per block and used for kGroups row groups (it is 17 KB at C2 --
+    // reloading it for every 8 rows was a seventh of the kernel's instructions); a warp copies whole table rows
     const int* ch = a.coeff_h + (size_t)b * S * cap;
     if (k_in_smem)
-        for (int i = tid; i < S * ksz; i += kThreads) { const int xx = i / ksz; s_k[i] = __ldg(ch + (size_t)xx * cap + (i - xx * ksz)); }   // (a warp-per-row variant measured no faster)
-    const int nr = min(R, rows - r_begin);
-    for (int i = tid; i < nr * pitch / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_rows)[i] = 0u;      // black canvas
-    __syncthreads();
-    // every patch that covers one of the rows: pastes clip at the canvas border, crops are black outside their page
-    for (int i = 0; i < n; ++i) {
-        const int dx = s_pat[4 * i], dy = s_pat[4 * i + 1], w = s_pat[4 * i + 2], h = s_pat[4 * i + 3];
-        const int y_lo = max(row_first + r_begin, dy), y_hi = min(min(row_first + r_begin + nr, dy + h), gh);
-        if (y_lo >= y_hi) continue;
-        const int pg = s_page[i];
-        const int W = ps.page_wh[2 * pg], H = ps.page_wh[2 * pg + 1];
-        const int sx0 = s_src[2 * i], sy0 = s_src[2 * i + 1];
-        const int cw = min(w, gw - dx);
-        if (cw <= 0) continue;
-        const int x_lo = max(0, -sx0), x_hi = min(cw, W - sx0);                 // patch columns that exist in the page
-        if (x_lo >= x_hi) continue;
-        const int seg = (x_hi - x_lo) * 3;
-        const unsigned char* page = ps.pixels + ps.page_off[pg];
-        for (int y = y_lo; y < y_hi; ++y) {
-            const int sy = sy0 + (y - dy);
-            if (sy < 0 || sy >= H) continue;
-            const unsigned char* src = page + ((size_t)sy * W + sx0 + x_lo) * 3;
-            unsigned char* dst = s_rows + (size_t)(y - row_first - r_begin) * pitch + (dx + x_lo) * 3;
-            copy_row_bytes(dst, src, seg, tid);
+        for (int xx = warp; xx < S; xx += kThreads / 32)
+            for (int j = lane; j < ksz; j += 32) s_k[xx * ksz + j] = __ldg(ch + (size_t)xx * cap + j);
+    for (int g = 0; g < kGroups; ++g) {
+        const int r_begin = (blockIdx.x * kGroups + g) * R;
+        if (r_begin >= rows) break;
+        const int nr = min(R, rows - r_begin);
+        if (g) __syncthreads();                                                // the previous group's taps are done
+        for (int i = tid; i < nr * pitch / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_rows)[i] = 0u;      // black canvas
+        __syncthreads();
+        // every patch that covers one of the rows: pastes clip at the canvas border, crops are black outside their page.
+        // Warp w stages row w of the group (R <= 8 rows, 8 warps): no per-row call overhead, no divisions.
+        if (warp < nr) {
+            const int y = row_first + r_begin + warp;
+            for (int i = 0; i < n; ++i) {
+                const int dx = s_pat[4 * i], dy = s_pat[4 * i + 1], w = s_pat[4 * i + 2], h = s_pat[4 * i + 3];
+                if (y < dy || y >= min(dy + h, gh)) continue;
+                const int pg = s_page[i];
+                const int W = ps.page_wh[2 * pg], H = ps.page_wh[2 * pg + 1];
+                const int sx0 = s_src[2 * i], sy0 = s_src[2 * i + 1];
+                const int cw = min(w, gw - dx);
+                const int x_lo = max(0, -sx0), x_hi = min(cw, W - sx0);         // patch columns that exist in the page
+                const int sy = sy0 + (y - dy);
+                if (cw <= 0 || x_lo >= x_hi || sy < 0 || sy >= H) continue;
+                const unsigned char* src = ps.pixels + ps.page_off[pg] + ((size_t)sy * W + sx0 + x_lo) * 3;
+                copy_row_bytes(s_rows + (size_t)warp * pitch + (dx + x_lo) * 3, src, (x_hi - x_lo) * 3, lane);
+                __syncwarp();                                                    // a later patch may overwrite these bytes
+            }
         }
-    }
-    __syncthreads();
-    unsigned char* temp = a.temp + ((size_t)b * a.rows_cap + r_begin) * S * 3;
-    for (int o = tid; o < S * 3; o += kThreads) {
-        const int xx = o / 3, c = o - xx * 3;
-        const int* k = k_in_smem ? s_k + xx * ksz : ch + (size_t)xx * cap;
-        const int first = k[0], cnt = k[1];
-        int acc[kMaxRows];
+        __syncthreads();
+        unsigned char* temp = a.temp + ((size_t)b * a.rows_cap + r_begin) * S * 3;
+        for (int o = tid; o < S * 3; o += kThreads) {
+            const int xx = o / 3, c = o - xx * 3;
+            const int* k = k_in_smem ? s_k + xx * ksz : ch + (size_t)xx * cap;
+            const int first = k[0], cnt = k[1];
+            int acc[kMaxRows];
 #pragma unroll
-        for (int r = 0; r < kMaxRows; ++r) acc[r] = 1 << (kPrecisionBits - 1);
-        const unsigned char* px = s_rows + first * 3 + c;
-        for (int t = 0; t < cnt; ++t) {
-            const int wgt = k[2 + t];
+            for (int r = 0; r < kMaxRows; ++r) acc[r] = 1 << (kPrecisionBits - 1);
+            const unsigned char* px = s_rows + first * 3 + c;
+            for (int t = 0; t < cnt; ++t) {
+                const int wgt = k[2 + t];
+#pragma unroll
+                for (int r = 0; r < kMaxRows; ++r)
+                    if (r < nr) acc[r] += (int)px[(size_t)r * pitch + t * 3] * wgt;      // predicated loads: set once per group
+            }
 #pragma unroll
             for (int r = 0; r < kMaxRows; ++r)
-                if (r < nr) acc[r] += (int)px[(size_t)r * pitch + t * 3] * wgt;
+                if (r < nr) temp[(size_t)r * S * 3 + o] = (unsigned char)min(max(acc[r] >> kPrecisionBits, 0), 255);
         }
-#pragma unroll
-        for (int r = 0; r < kMaxRows; ++r)
-            if (r < nr) temp[(size_t)r * S * 3 + o] = (unsigned char)min(max(acc[r] >> kPrecisionBits, 0), 255);
     }
 }
 
@@ -338,7 +348,7 @@ extern "C" int rdv_visual_pack(const rdv_pagestore* ps, const rdv_visual_args* a
                 "visual_pack: max_page_w=%d outside [1, %d]", args->max_page_w, vp::kMaxRowBytes / 3);
     const int row_bytes = vp::row_bytes_for(args->max_page_w);
     const int r_min = vp::rows_per_block(args->max_page_w, row_bytes);            // a canvas is at most a page wide
-    const int row_blocks = (args->rows_cap + r_min - 1) / r_min;
+    const int row_blocks = (args->rows_cap + r_min * vp::kGroups - 1) / (r_min * vp::kGroups);
     const long long coeff_bytes = (long long)args->out_size * (args->ksize_cap_h + 2) * 4;
     const size_t smem_h = (size_t)row_bytes + (size_t)(coeff_bytes < vp::kCoeffBudget ? coeff_bytes : vp::kCoeffBudget);
     vp::visual_resize_h_kernel<<<dim3(row_blocks, ps->B), vp::kThreads, smem_h, s>>>(P);
