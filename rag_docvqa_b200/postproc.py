@@ -139,11 +139,11 @@ class Reranker:
         k = max(1, max((len(r) for r in score_rows), default=1))
         if k > MAX_K:
             raise _lib.RdvError(_lib.E_LIMIT, "rerank: more than %d candidates per document" % MAX_K)
-        f64 = any((isinstance(r, torch.Tensor) and r.dtype == torch.float64) or
-                  (isinstance(r, np.ndarray) and r.dtype == np.float64) or
-                  (not isinstance(r, (torch.Tensor, np.ndarray)) and len(r) > 0) for r in score_rows)
-        dt = np.float64 if f64 else np.float32
-        host = [r.detach().cpu().numpy() if isinstance(r, torch.Tensor) else np.asarray(r, dtype=dt) for r in score_rows]
+        # CrossEncoder.predict returns a float32 array, FlagLLMReranker.compute_score a list of Python floats (float64
+        # once np.argsort sees it); the kernel sorts whichever type arrives
+        host = [r.detach().cpu().numpy() if isinstance(r, torch.Tensor) else np.asarray(r) for r in score_rows]
+        host = [h if h.dtype in (np.float32, np.float64) else h.astype(np.float64) for h in host]
+        dt = np.float64 if any(h.dtype == np.float64 and h.size for h in host) else np.float32
         scores = torch.from_numpy(_pad_rows(host, k, dt)).to(self.device)
         cnt = torch.tensor([len(r) for r in host], dtype=torch.int32).to(self.device)
         order, kept, _ = rerank_order(scores, cnt, self.rerank_filter_tresh, self.rerank_max_chunk_num,
