@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) visual_layout_kernel(const Params P)
 constexpr int kRowBudget = 64 * 1024;          // most bytes of staged rows
 constexpr int kCoeffBudget = 32 * 1024;        // most bytes of the coefficient table kept in shared memory (else L1/L2)
 constexpr int kMaxRows = 8;
-constexpr int kGroups = 4;                     // row groups per block: the coefficient table is loaded once for all of them
+constexpr int kGroups = 8;                     // row groups per block: the coefficient table is loaded once for all of them
 
 __host__ __device__ __forceinline__ int row_pitch(int gw) { return (gw * 3 + 15) & ~15; }
 // shared memory the launch reserves for rows: 8 rows of the widest possible canvas, within the budget -- sized by
@@ -182,13 +182,38 @@ __device__ __forceinline__ void copy_row_bytes(unsigned char* dst, const unsigne
     const unsigned sh = (unsigned)(uintptr_t)s0 & 3u;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - sh);
     const unsigned sel = 0x3210u + 0x1111u * sh;
+    // four iterations' loads are issued before the first store: a warp stages its row alone, so without the unrolling
+    // every iteration waited a full global-memory round trip (22 % of the kernel's stall samples)
     if (sh == 0) {
+#pragma unroll 4
         for (int w = lane; w < words; w += 32) dw[w] = __ldg(sw + w);
     } else {
+#pragma unroll 4
         for (int w = lane; w < words; w += 32) dw[w] = __byte_perm(__ldg(sw + w), __ldg(sw + w + 1), sel);
     }
     const int done = head + (words << 2);
     if (lane < n - done) dst[done + lane] = __ldg(src + done + lane);
+}
+
+// one (output x, channel) for the rows of a group.  ALL = the group has all kMaxRows rows (every group of a document but
+// its last): the tap loop is straight-line -- per tap one weight and, per row, one LDS.U8 + one IMAD.  With a per-row
+// `r < nr` test inside the loop the compiler emitted a branch and a recomputed shared-memory base per (tap, row): 8
+// instructions instead of 2, 80 % of the kernel's 1.06 G warp instructions (ncu, profiles/r1e_ncu_summary.md).
+template <bool ALL>
+__device__ __forceinline__ void h_column(const unsigned char* __restrict__ px, int pitch, const int* __restrict__ wts, int cnt,
+                                         int nr, unsigned char* __restrict__ out, int out_pitch) {
+    int acc[kMaxRows];
+#pragma unroll
+    for (int r = 0; r < kMaxRows; ++r) acc[r] = 1 << (kPrecisionBits - 1);
+    for (int t = 0; t < cnt; ++t) {
+        const int wgt = wts[t];
+#pragma unroll
+        for (int r = 0; r < kMaxRows; ++r)
+            if (ALL || r < nr) acc[r] += (int)px[r * pitch + t * 3] * wgt;
+    }
+#pragma unroll
+    for (int r = 0; r < kMaxRows; ++r)
+        if (ALL || r < nr) out[(size_t)r * out_pitch] = (unsigned char)min(max(acc[r] >> kPrecisionBits, 0), 255);
 }
 
 __global__ void __launch_bounds__(kThreads) visual_resize_h_kernel(const Params P) {
@@ -221,18 +246,28 @@ __global__ void __launch_bounds__(kThreads) visual_resize_h_kernel(const Params 
     // reloading it for every 8 rows was a seventh of the kernel's instructions); a warp copies whole table rows
     const int* ch = a.coeff_h + (size_t)b * S * cap;
     if (k_in_smem)
-        for (int xx = warp; xx < S; xx += kThreads / 32)
-            for (int j = lane; j < ksz; j += 32) s_k[xx * ksz + j] = __ldg(ch + (size_t)xx * cap + j);
+    {
+        if (ksz <= 32) {                     // the usual case (bicubic down to a ninth): one load per lane and table row
+#pragma unroll 4
+            for (int xx = warp; xx < S; xx += kThreads / 32)
+                if (lane < ksz) s_k[xx * ksz + lane] = __ldg(ch + (size_t)xx * cap + lane);
+        } else {
+            for (int xx = warp; xx < S; xx += kThreads / 32)
+                for (int j = lane; j < ksz; j += 32) s_k[xx * ksz + j] = __ldg(ch + (size_t)xx * cap + j);
+        }
+    }
     for (int g = 0; g < kGroups; ++g) {
         const int r_begin = (blockIdx.x * kGroups + g) * R;
         if (r_begin >= rows) break;
         const int nr = min(R, rows - r_begin);
-        if (g) __syncthreads();                                                // the previous group's taps are done
-        for (int i = tid; i < nr * pitch / 4; i += kThreads) reinterpret_cast<uint32_t*>(s_rows)[i] = 0u;      // black canvas
-        __syncthreads();
-        // every patch that covers one of the rows: pastes clip at the canvas border, crops are black outside their page.
-        // Warp w stages row w of the group (R <= 8 rows, 8 warps): no per-row call overhead, no divisions.
+        __syncthreads();                                    // the previous group's taps are done (g = 0: s_pat is visible)
+        // Warp w owns row w of the group (R <= 8 rows, 8 warps): it blackens the row, then pastes the row segment of
+        // every patch that covers it (pastes clip at the canvas border, crops are black outside their page) -- no block
+        // barrier between the two, no per-row call overhead, no divisions.
         if (warp < nr) {
+            uint4* zrow = reinterpret_cast<uint4*>(s_rows + (size_t)warp * pitch);
+            for (int i = lane; i < pitch / 16; i += 32) zrow[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
             const int y = row_first + r_begin + warp;
             for (int i = 0; i < n; ++i) {
                 const int dx = s_pat[4 * i], dy = s_pat[4 * i + 1], w = s_pat[4 * i + 2], h = s_pat[4 * i + 3];
@@ -254,20 +289,9 @@ __global__ void __launch_bounds__(kThreads) visual_resize_h_kernel(const Params 
         for (int o = tid; o < S * 3; o += kThreads) {
             const int xx = o / 3, c = o - xx * 3;
             const int* k = k_in_smem ? s_k + xx * ksz : ch + (size_t)xx * cap;
-            const int first = k[0], cnt = k[1];
-            int acc[kMaxRows];
-#pragma unroll
-            for (int r = 0; r < kMaxRows; ++r) acc[r] = 1 << (kPrecisionBits - 1);
-            const unsigned char* px = s_rows + first * 3 + c;
-            for (int t = 0; t < cnt; ++t) {
-                const int wgt = k[2 + t];
-#pragma unroll
-                for (int r = 0; r < kMaxRows; ++r)
-                    if (r < nr) acc[r] += (int)px[(size_t)r * pitch + t * 3] * wgt;      // predicated loads: set once per group
-            }
-#pragma unroll
-            for (int r = 0; r < kMaxRows; ++r)
-                if (r < nr) temp[(size_t)r * S * 3 + o] = (unsigned char)min(max(acc[r] >> kPrecisionBits, 0), 255);
+            const unsigned char* px = s_rows + k[0] * 3 + c;
+            if (nr == kMaxRows) h_column<true>(px, pitch, k + 2, k[1], nr, temp + o, S * 3);
+            else h_column<false>(px, pitch, k + 2, k[1], nr, temp + o, S * 3);
         }
     }
 }
