@@ -55,7 +55,8 @@ def run(images, hit_page, hit_rect, hit_cnt, **kw):
 @pytest.mark.parametrize("resample", [R.PIL_BILINEAR, R.PIL_BICUBIC])
 @pytest.mark.parametrize("seed,B,k,out_size,kw", [
     (1, 6, 5, 224, {}), (2, 4, 8, 224, dict(full_page_every=2)), (3, 5, 3, 64, dict(out_of_page=True)),
-    (4, 3, 20, 224, dict(max_wh=(120, 90))), (5, 2, 1, 224, dict(max_wh=(60, 50)))])       # last: up-scaling
+    (4, 3, 20, 224, dict(max_wh=(120, 90))), (5, 2, 1, 224, dict(max_wh=(60, 50))),        # up-scaling
+    (6, 3, 4, 50, {})])                     # 50 * 3 bytes per row is not a multiple of 4: the strided vertical pass
 def test_visual_pack_matches_oracle(seed, B, k, out_size, kw, resample):
     images, pages_np, hit_page, hit_rect, hit_cnt = make_case(seed, B, k, **kw)
     mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
