@@ -106,12 +106,44 @@ __global__ void __launch_bounds__(kPostWarps * 32) page_vote_kernel(
     const int n_hits = min(min(hit_cnt[b], k), n_doc);        // zip(pages, weights) stops at the shorter one
     const bool f32_acc = weighted && !legacy_promotion;       // NEP 50: int 0 + float32 stays float32
     // ---- sum(w): sequential, in chunk order, starting from the Python int 0 (src/RAGVT5.py:462) ----
-    // The chain of dependent adds is the whole cost (10 k chunks: 10 k adds), so only the chain that is needed runs, the
-    // broadcasts are unrolled ahead of it, and the tail is padded with +0.0 (x + 0.0 == x: a sum that starts at +0 is
-    // never -0).
+    // A chain of n_doc dependent adds is the whole cost of the kernel for long documents (10 k chunks: 156 us measured),
+    // so the float64 sum first asks whether the order can matter at all: the inputs are float32 (24-bit significands);
+    // if the span from the largest input's exponent down to the smallest non-zero input's last bit, plus log2(n) carry
+    // bits, fits the 53-bit significand, EVERY partial sum in ANY order is exact, and a lane-strided sum + warp tree
+    // gives the sequential result bit for bit.  Otherwise (tiny or non-finite values, float32 accumulation) the
+    // sequential chain runs: broadcasts unrolled ahead of it, tail padded with +0.0 (x + 0.0 == x: a sum that starts
+    // at +0 is never -0).
     double total = 0.0;
     float total32 = 0.0f;
-    if (weighted) {
+    bool done = false;
+    if (weighted && legacy_promotion) {
+        int emax = 0, emin = 255;
+        bool odd = false;                                       // NaN / Inf / subnormal: leave it to the chain
+#pragma unroll 8
+        for (int i = lane; i < n_doc; i += 32) {                // 8 loads in flight: one warp walks the document alone
+            const unsigned bits = __float_as_uint(__ldg(sims + c0 + i));
+            const unsigned e = (bits >> 23) & 0xFFu;
+            const bool zero = (bits & 0x7FFFFFFFu) == 0u;
+            odd |= e == 255u || (e == 0u && !zero);
+            emax = max(emax, zero ? 0 : (int)e);
+            emin = min(emin, zero ? 255 : (int)e);
+        }
+        emax = __reduce_max_sync(0xffffffffu, emax);
+        emin = __reduce_min_sync(0xffffffffu, emin);
+        odd = __any_sync(0xffffffffu, odd);
+        // in units of the smallest input's last bit every |partial sum| < n * 2^(emax - emin + 24) <= 2^53: an exact integer
+        const int carry = n_doc > 1 ? 32 - __clz(n_doc - 1) : 0;      // ceil(log2(n_doc))
+        if (!odd && (emin > emax || emax - emin + 24 + carry <= 53)) {
+            double part = 0.0;
+#pragma unroll 8
+            for (int i = lane; i < n_doc; i += 32) part += (double)__ldg(sims + c0 + i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            total = part;
+            done = true;
+        }
+    }
+    if (weighted && !done) {
         for (int base = 0; base < n_doc; base += 32) {
             const float v = base + lane < n_doc ? __ldg(sims + c0 + base + lane) : 0.0f;
             float x[32];

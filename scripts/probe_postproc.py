@@ -34,12 +34,13 @@ for name, B, k, n_b in (("C2", 64, 5, 600), ("C3", 256, 10, 10000)):
     scores = torch.from_numpy(rng.rand(B, k).astype(np.float32)).to(dev)
     cnt = torch.full((B,), k, dtype=torch.int32, device=dev)
     pages = torch.from_numpy(rng.randint(0, 20, size=(B, k)).astype(np.int32)).to(dev)
-    sims = torch.from_numpy(rng.rand(B * n_b).astype(np.float32)).to(dev)
+    sims = torch.from_numpy((0.2 + 0.4 * rng.rand(B * n_b)).astype(np.float32)).to(dev)      # cosines cluster in 0.2 .. 0.6
     row_off = torch.arange(0, (B + 1) * n_b, n_b, dtype=torch.int64, device=dev)
     out[name] = {
         "rerank_order_us": 1e3 * timed(lambda: postproc.rerank_order(scores, cnt, 0.4, 5, 1)),
         "page_vote_major_us": 1e3 * timed(lambda: postproc.page_vote(pages, cnt, None, row_off, False)),
         "page_vote_weighted_us": 1e3 * timed(lambda: postproc.page_vote(pages, cnt, sims, row_off, True)),
+        "page_vote_weighted_f32_accumulation_us": 1e3 * timed(lambda: postproc.page_vote(pages, cnt, sims, row_off, True, legacy_promotion=False)),
     }
 
 # layout assignment: a C2-shaped batch of pages (64 documents x <= 20 pages, <= 700 words, <= 30 layout boxes)

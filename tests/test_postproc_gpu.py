@@ -106,6 +106,9 @@ def test_page_vote_random_vs_oracle(weighted, legacy):
             s[:] = np.float32(0.25)                        # identical weights: page ties decided by CPython's set order
         if b % 50 == 1 and n_b:
             s[0] = np.nan
+        if b % 11 == 3 and n_b > 2:
+            s[1] = np.float32(1e-30)                       # wide exponent span: the order of the float64 sum matters again
+            s[2] = np.float32(-1e-41)                      # subnormal
         sims.append(s)
     got = vote(pages, sims, weighted, legacy)
     want = [R.page_vote(p, s, len(s), weighted, legacy_promotion=legacy) for p, s in zip(pages, sims)]
