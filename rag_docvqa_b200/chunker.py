@@ -138,7 +138,7 @@ class Chunker(StatComponent):
     def get_chunks(self, words: list, boxes: list, layout_info: Optional[list] = None, **kwargs) -> tuple:
         bs = len(words)
         question_id = kwargs.get("question_id", None)
-        use_layout = layout_info != [[]]
+        use_layout = layout_info is not None and layout_info != [[]]      # [[]] = no layout model (src/_modules.py:892)
         use_clusters = use_layout and "clusters" in layout_info[0][0].keys() and self.cluster_layouts
         oracle = self.page_retrieval == "oracle"
 

@@ -79,3 +79,23 @@ def test_oracle_against_live_reference_random():
         assert json.loads(json.dumps(got)) == json.loads(json.dumps(ref))
         want = stats_json(ch.stats)
         assert {k: v for k, v in stats.as_dict().items() if k in want} == want
+
+
+@pytest.mark.parametrize("page_retrieval", ["concat", "oracle"])
+def test_product_chunker_host_paths_need_no_gpu(page_retrieval):
+    """Without layout boxes (or with page_retrieval == "oracle") Chunker.get_chunks launches nothing: the host logic
+    (box normalisation, chunk windows as index ranges, counters) against the oracle's list-extension loop."""
+    from rag_docvqa_b200 import synth
+    from rag_docvqa_b200.chunker import Chunker
+    words, boxes, info = synth.make_chunker_batch(8, 3, 4, 200, 8, numpy_pages=True)
+    cfg = {"compute_stats": True, "compute_stats_examples": True, "n_stats_examples": 2, "layout_model_weights": None,
+           "device": "cuda:0", "page_retrieval": page_retrieval, "chunk_size": 25, "overlap": 5}
+    ch = Chunker(cfg)
+    layout = info if page_retrieval == "oracle" else [[]]
+    got = ch.get_chunks(words, boxes, layout, question_id=["a", "b", "c"])
+    want, stats = R.get_chunks(words, boxes, layout, chunk_size=25, overlap=5, page_retrieval=page_retrieval)
+    assert json.loads(json.dumps(got)) == json.loads(json.dumps(want))
+    assert dict(ch.stats["chunk_size_dist"]) == stats.chunk_size_dist
+    assert dict(ch.stats["n_chunks_per_page_dist"]) == stats.n_chunks_per_page_dist
+    assert dict(ch.stats["n_chunks_per_doc_dist"]) == stats.n_chunks_per_doc_dist
+    assert all(len(v) <= 2 for v in ch.stats_examples["chunk_size_dist"].values())
