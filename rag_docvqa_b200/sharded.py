@@ -1,4 +1,5 @@
-"""Corpus-scale retrieval: chunk embeddings row-sharded across the GPUs of one box
+"""Multi-GPU retrieval.  Per-document retrieval (C1-C4) shards by document with no collective: partition_documents /
+take_documents below.  Corpus-scale retrieval: chunk embeddings row-sharded across the GPUs of one box
 (BASELINE.json configs[4]: 10 M chunks x 768-d bf16 over 8 x B200, 1024 questions, top-10).
 
 No reference counterpart (the reference is single-GPU and scores one question per document); the
@@ -33,6 +34,35 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     base, rem = divmod(n_rows, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def partition_documents(sizes, world: int):
+    """Per-document retrieval across ranks: every (question, document) pair is
+    independent (src/_modules.py:1986-1995 loops over the batch with no cross-talk), so a batch is split by DOCUMENT,
+    with no data-path collective.  Greedy balance on the chunk counts (largest document first onto the least loaded
+    rank, ties to the lower rank), documents of a rank kept in batch order.  Deterministic from `sizes` alone, so every
+    rank computes the same partition without talking.  Returns `world` lists of document indices."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    sizes = [int(x) for x in sizes]
+    load = [0] * world
+    parts = [[] for _ in range(world)]
+    for b in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
+        r = min(range(world), key=lambda j: (load[j], len(parts[j]), j))
+        parts[r].append(b)
+        load[r] += sizes[b]
+    return [sorted(p) for p in parts]
+
+
+def take_documents(indices, *per_document):
+    """The rank's slice of any per-document arguments of Retriever.retrieve (lists, or a (B, d) question tensor)."""
+    out = []
+    for x in per_document:
+        if isinstance(x, torch.Tensor):
+            out.append(x[torch.as_tensor(indices, dtype=torch.long, device=x.device)] if len(indices) else x[:0])
+        else:
+            out.append([x[i] for i in indices])
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 class CorpusShard:
