@@ -43,3 +43,34 @@ def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "--list-elf", build.LIB], stdout=subprocess.PIPE, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    """Every entry point validates its arguments first and returns a negative code with a message -- no CUDA call
+    is made on that path, so it can be exercised without a GPU (error behaviour of the boundary, include/rdv.h:18)."""
+    from rag_docvqa_b200 import _lib
+    lib = _lib.lib
+    cases = [
+        (lib.rdv_rerank_order(None, 0, None, 4, 0, 0.4, 5, 1, None, None, None, None), _lib.E_LIMIT, "rerank_order"),      # k = 0
+        (lib.rdv_rerank_order(None, 0, None, 4, 65, 0.4, 5, 1, None, None, None, None), _lib.E_LIMIT, "rerank_order"),     # k > 64
+        (lib.rdv_rerank_order(None, 0, None, 4, 5, 0.4, -1, 1, None, None, None, None), _lib.E_INVALID, "negative"),
+        (lib.rdv_rerank_order(None, 0, None, 4, 5, 0.4, 5, 1, None, None, None, None), _lib.E_INVALID, "null"),
+        (lib.rdv_page_vote(None, None, None, None, 3, 0, 0, 1, None, None, None), _lib.E_LIMIT, "page_vote"),
+        (lib.rdv_page_vote(None, None, None, None, 3, 5, 1, 1, None, None, None), _lib.E_INVALID, "null"),
+        (lib.rdv_layout_assign(None, None, None, None, None, None, None, -1, 1, None, None, None, None), _lib.E_INVALID, "negative"),
+        (lib.rdv_layout_assign(None, None, None, None, None, None, None, 3, 1, None, None, None, None), _lib.E_INVALID, "null"),
+        (lib.rdv_topk_merge(None, None, 2, 4, 0, None, None, None), _lib.E_INVALID, "topk_merge"),
+    ]
+    for code, want, needle in cases:
+        assert code == want, (code, want, needle)
+    assert lib.rdv_layout_assign(None, None, None, None, None, None, None, 3, 1, None, None, None, None) == _lib.E_INVALID
+    assert b"layout_assign" in lib.rdv_last_error()
+    try:
+        _lib.check(lib.rdv_rerank_order(None, 0, None, 4, 65, 0.4, 5, 1, None, None, None, None))
+        raise AssertionError("no exception")
+    except _lib.RdvError as exc:
+        assert exc.code == _lib.E_LIMIT and "rerank_order" in str(exc)
+    # empty batches are accepted and launch nothing
+    assert lib.rdv_rerank_order(None, 0, None, 0, 5, 0.4, 5, 1, None, None, None, None) == _lib.OK
+    assert lib.rdv_page_vote(None, None, None, None, 0, 5, 1, 1, None, None, None) == _lib.OK
+    assert lib.rdv_layout_assign(None, None, None, None, None, None, None, 0, 1, None, None, None, None) == _lib.OK
