@@ -40,11 +40,16 @@ def assert_same_lists(out, ref):
     assert [[digest(im) for im in doc] for doc in out[6]] == ref[6]
 
 
-@pytest.mark.parametrize("on_device", [True, False, "pinned"])
-def test_retrieve_matches_reference_golden(golden_dir, on_device):
-    """Device tensors (the reference's case), pageable host tensors (packed upload) and pinned host tensors
+@pytest.mark.parametrize("on_device", [True, False, "pinned", "host_general", "pinned_general"])
+def test_retrieve_matches_reference_golden(golden_dir, on_device, monkeypatch):
+    """Device tensors (the reference's case), host tensors through the small-batch path (one blob up, one launch, one
+    read-back) and, with that path switched off, pageable host tensors (packed upload) and pinned host tensors
     (zero-copy: the score kernel reads the page-locked rows over PCIe) must give the same 9-tuple."""
+    from rag_docvqa_b200 import retriever as retriever_module
     from rag_docvqa_b200.retriever import Retriever
+    if isinstance(on_device, str) and on_device.endswith("_general"):
+        monkeypatch.setattr(retriever_module, "_SMALL_BATCH_BYTES", -1)
+        on_device = "pinned" if on_device.startswith("pinned") else False
     gold, emb, q, words, boxes, labels, images, pages = load_retrieve_inputs(golden_dir)
     if on_device == "pinned":
         emb, q, on_device = [e.pin_memory() for e in emb], q.pin_memory(), False
@@ -87,6 +92,58 @@ def test_retrieve_c2_slice_vs_oracle(s, reorder, where):
     for i in (0, 1, 2, 3, 4, 5, 7):
         assert out[i] == ref[i], "output %d differs" % i
     assert [[digest(im) for im in doc] for doc in out[6]] == [[digest(im) for im in doc] for doc in ref[6]]
+
+
+SMALL_SIZES = {1: [30], 3: [45, 0, 3], 7: [60, 0, 3, 150, 1, 90, 31]}
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("docs,k,s,reorder", [(1, 5, 0, False), (1, 40, 0, False), (3, 5, 0, True), (7, 5, 3, False),
+                                              (7, 1, 0, False)])
+def test_retrieve_small_host_batch(docs, k, s, reorder, pinned, monkeypatch):
+    """Host batches of < 8 documents and <= 1 MB (C1, the reference's CPU-runnable case) take _retrieve_host_small: checked
+    against the oracle and against the general host path on the same inputs; duplicates (ties), an empty document,
+    documents with fewer than k chunks and a strided embedding matrix included."""
+    from rag_docvqa_b200 import retriever as retriever_module
+    from rag_docvqa_b200.retriever import Retriever
+    sizes, dim, cpp = SMALL_SIZES[docs], 384, 30
+    emb, q = synth.make_embeddings(sizes, dim, 311 + docs, dup_frac=0.1)
+    words, boxes, labels = synth.make_words(sizes, 318 + docs, min_words=3, max_words=20, empty_chunk_every=13)
+    lists = (words, boxes, labels, synth.make_images(sizes, cpp, width=212, height=275, ragged_sizes=True),
+             synth.make_page_indices(sizes, cpp))
+    wide = torch.randn(sizes[0], 2 * dim, generator=torch.Generator().manual_seed(5))
+    wide[:, ::2] = emb[0]
+    emb[0] = wide[:, ::2]                           # non-contiguous rows
+    assert not emb[0].is_contiguous()
+    assert (sum(sizes) + docs) * dim * 4 <= retriever_module._SMALL_BATCH_BYTES
+    emb_in = [e.pin_memory() if pinned and e.is_contiguous() else e for e in emb]
+    retr = Retriever({**BASE, "chunk_num": k, "include_surroundings": s, "reorder_chunks": reorder})
+    taken = []
+    small = Retriever._retrieve_host_small
+    monkeypatch.setattr(Retriever, "_retrieve_host_small", lambda self, *a: (taken.append(1), small(self, *a))[1])
+    for rep in range(2):                            # the second call reuses the buffers of the first
+        out = retr.retrieve(emb_in, q.pin_memory() if pinned else q, *lists)
+    assert len(taken) == 2
+    sims = out[8]
+    assert len(sims) == docs and all(not x.is_cuda and x.dtype == torch.float32 for x in sims)
+    assert [x.shape[0] for x in sims] == sizes
+    ref_sims = R.score([e.contiguous() for e in emb], q)
+    hits = [R.topk_lowest_index(x, k) for x in sims]
+    for b in range(docs):
+        compare.assert_scores_close(sims[b].numpy(), ref_sims[b].numpy())
+        compare.assert_topk_matches(hits[b], sims[b].numpy(), ref_sims[b].numpy(), k)
+    ref = R.gather_hits(hits, *lists, include_surroundings=s, reorder_chunks=reorder)
+    for i in (0, 1, 2, 3, 4, 5, 7):
+        assert out[i] == ref[i], "output %d differs" % i
+    assert [[digest(im) for im in doc] for doc in out[6]] == [[digest(im) for im in doc] for doc in ref[6]]
+    # the general host path (packed upload, two launches) on the same inputs
+    monkeypatch.setattr(retriever_module, "_SMALL_BATCH_BYTES", -1)
+    gen = retr.retrieve(emb_in, q, *lists)
+    assert len(taken) == 2
+    for i in (0, 1, 2, 3, 4, 5, 7):
+        assert out[i] == gen[i], "output %d differs from the general path" % i
+    for b in range(docs):
+        np.testing.assert_allclose(sims[b].numpy(), gen[8][b].numpy(), rtol=1e-6, atol=1e-7)
 
 
 def test_retriever_contract_attributes():
