@@ -116,6 +116,34 @@ RDV_API int rdv_build_doc_table(const void* const* d_docs, const int64_t* rows, 
 RDV_API int rdv_upload_docs_f32(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, float* d_packed,
                                 void* stream);
 
+/* Small host batches: the device round trip of Retriever.retrieve (src/_modules.py:2155-2180: _get_similarities
+ * :1978-1997 + torch.topk :2015-2016) in ONE call, for batches whose fixed costs exceed their work (C1: 1 page x 30
+ * chunks x 384-d = 46 KB; the reference runs this case on the CPU).
+ *   upload blob  (pinned host h_blob, device twin d_blob):  row_off[B+1] i64 | pad | tiles[n_tiles] | questions (B,d) | rows
+ *   result blob  (device d_out; the first read_bytes are copied to pinned h_out):  sims[total] | idx (B,k) | cnt[B] || val (B,k)
+ * rdv_small_batch_layout   offsets and sizes of both blobs + the launch plan (pure host arithmetic).
+ * rdv_small_batch_pack     fills h_blob: copies the B host matrices h_docs[b] (rows[b] x d fp32, contiguous) and the
+ *                          questions h_q (B,d), and builds offsets + tile descriptors that point into d_blob (pure host code).
+ * rdv_retrieve_small_f32   layout + pack + ONE cudaMemcpyAsync up + the fused score/top-k launch (RDV_SCORE_LDG_FUSED) + ONE
+ *                          cudaMemcpyAsync back + cudaStreamSynchronize: on return h_out holds similarities, hits and counts
+ *                          (same values and ordering as rdv_score_topk_f32).  Returns RDV_SMALL_GROW (> 0), with *lay filled
+ *                          and nothing else touched, when a buffer is smaller than the layout needs.  d_doc_done as in
+ *                          rdv_score_topk_f32.  This entry point synchronises the stream (it is the whole call). */
+typedef struct rdv_small_layout {
+    int32_t algo, tile_rows, n_tiles, max_rows;
+    int64_t total_rows;
+    int64_t o_tiles, o_q, o_emb, in_bytes;                  /* upload blob (row_off at 0) */
+    int64_t o_idx, o_cnt, read_bytes, o_val, out_bytes;     /* result blob (sims at 0)    */
+} rdv_small_layout;
+#define RDV_SMALL_GROW 1
+RDV_API int rdv_small_batch_layout(const int64_t* rows, int32_t B, int32_t d, int32_t k, rdv_small_layout* lay);
+RDV_API int rdv_small_batch_pack(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, const float* h_q,
+                                 const rdv_small_layout* lay, void* h_blob, const void* d_blob);
+RDV_API int rdv_retrieve_small_f32(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, int32_t k,
+                                   const float* h_q, void* h_blob, void* d_blob, int64_t blob_bytes, void* d_out,
+                                   int64_t d_out_bytes, void* h_out, int64_t h_out_bytes, int32_t* d_doc_done,
+                                   rdv_small_layout* lay, void* stream);
+
 /* Scores only (the streaming half of rdv_score_topk_f32): writes d_sims.  Used when the selection runs
  * elsewhere (rdv_topk_segments_f32, or inside rdv_gather_vt5_inputs).  algo: RDV_SCORE_LDG or RDV_SCORE_TMA. */
 RDV_API int rdv_score_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
@@ -335,6 +363,25 @@ RDV_API int rdv_layout_assign(const double* d_word_box, const int32_t* d_page_wo
                               const int32_t* d_lay_label, const int32_t* d_page_lay_off, const int32_t* d_group_page,
                               const int32_t* d_page_group_off, int32_t n_groups, int32_t default_label,
                               const int64_t* d_bits_off, uint32_t* d_bits, int32_t* d_word_label, void* stream);
+
+/* rdv_s2_weights: S2Chunker's pairwise weight matrices of the layout regions ("nodes") of every page of a batch in one
+ *   launch (src/_modules.py:1755-1802).  P pages, N nodes; page p owns nodes
+ *   d_page_node_off[p] .. d_page_node_off[p+1] and the n_p x n_p row-major matrix at d_out[d_out_off[p]] (d_out_off[P+1]
+ *   = prefix sums of n_p^2, total_entries = d_out_off[P]):
+ *     spatial[i][j]  = 1 / (1 + ||centroid_i - centroid_j||)   (_spatial_weights_calculation :1755-1773), float64, each
+ *                      operation rounded as numpy does here (sqrt(fma(dy, dy, dx*dx)): OpenBLAS ddot on an FMA CPU)
+ *     semantic[i][j] = sklearn cosine_similarity of the rows of d_emb (N, d) fp32 (_semantic_weights_calculation
+ *                      :1775-1788): rows divided by their norm (zero rows untouched) in fp32, then the dot product
+ *     out            = (spatial + semantic) / 2                 (_combined_weights :1790-1802)
+ *   d_emb == NULL is cluster_mode "spatial" (semantic = spatial, so out == spatial bit for bit).  `what` selects the
+ *   matrix written: RDV_S2_COMBINED, or one of its two terms (RDV_S2_SPATIAL, RDV_S2_SEMANTIC -- the latter needs d_emb).
+ *   d_node_box (N,4) f64 xyxy, 16-byte aligned. */
+#define RDV_S2_COMBINED 0
+#define RDV_S2_SPATIAL 1
+#define RDV_S2_SEMANTIC 2
+RDV_API int rdv_s2_weights(const double* d_node_box, const int32_t* d_page_node_off, int32_t P, const float* d_emb,
+                           int32_t d, int32_t what, const int64_t* d_out_off, int64_t total_entries, double* d_out,
+                           void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -817,3 +817,108 @@ def get_chunks(words, boxes, layout_info=None, chunk_size: int = 60, overlap: in
         out_word_labels.append(d_word_labels)
         stats.add(stats.n_chunks_per_doc_dist, d_n)
     return (out_words, out_boxes, out_labels, out_pages, out_word_labels), stats
+
+
+# --------------------------------------------------------------------------------------
+# 8f rank 4 (second half): S2Chunker -- layout regions of a page as graph nodes, pairwise weights,
+# spectral clustering          reference: src/_modules.py:1669-1962
+# Pinned by oracle/make_golden_s2chunker.py -> tests/golden/s2chunker.json (tests/test_s2chunker_oracle.py).
+# --------------------------------------------------------------------------------------
+def s2_nodes(page_layout_info: dict, page_info: Optional[dict], cluster_mode: str):
+    """create_nodes_and_edges (:1687-1753): (nodes, edges, used).  In "spatial+semantic" mode with page_info the
+    reference's word loop reuses the node counter `i` (:1724), so global ids start at len(page words) - 1 -- restated
+    as written (cluster() then fails in _add_weights_to_graph exactly as the reference does)."""
+    boxes, labels = page_layout_info["boxes"], page_layout_info["labels"]
+    nodes, used = [], np.zeros(len(boxes), dtype=bool)
+    i = 0
+    if cluster_mode == "spatial" or page_info is None:
+        for l, (box, label) in enumerate(zip(boxes, labels)):
+            nodes.append({"global_id": i, "page": 1, "bbox": box, "text": "", "label": label})
+            i += 1
+            used[l] = True
+    else:
+        page_words, page_boxes = page_info["ocr_tokens"], page_info["ocr_normalized_boxes"]
+        inside = []
+        for box in boxes:
+            inside.append([w for w, wb in zip(page_words, page_boxes) if containment_ratio(wb, box) > 0.5])   # :1724-1730
+        if len(boxes) and len(page_words):
+            i = len(page_words) - 1                                                     # the shadowed loop variable
+        for l, (box, label) in enumerate(zip(boxes, labels)):
+            if not inside[l]:
+                continue
+            nodes.append({"global_id": i, "page": 1, "bbox": box, "text": " ".join(inside[l]), "label": label})
+            i += 1
+            used[l] = True
+    edges = [(nodes[a]["global_id"], nodes[b]["global_id"]) for a in range(len(nodes)) for b in range(a + 1, len(nodes))]
+    return nodes, edges, used
+
+
+def s2_spatial_weights(boxes) -> np.ndarray:
+    """_spatial_weights_calculation (:1755-1773), the reference's own numpy calls per entry."""
+    n = len(boxes)
+    out = np.zeros((n, n))
+    for a in range(n):
+        for b in range(n):
+            ba, bb = boxes[a], boxes[b]
+            ca = np.array([(ba[0] + ba[2]) / 2, (ba[1] + ba[3]) / 2])
+            cb = np.array([(bb[0] + bb[2]) / 2, (bb[1] + bb[3]) / 2])
+            out[a, b] = 1 / (1 + np.linalg.norm(ca - cb))
+    return out
+
+
+def s2_semantic_weights(embeddings: np.ndarray) -> np.ndarray:
+    """_semantic_weights_calculation (:1775-1788): sklearn.metrics.pairwise.cosine_similarity of the node embeddings."""
+    from sklearn.metrics.pairwise import cosine_similarity
+    return cosine_similarity(embeddings)
+
+
+def s2_combined_weights(boxes, embeddings: Optional[np.ndarray] = None) -> np.ndarray:
+    """_combined_weights (:1790-1802); embeddings None = cluster_mode "spatial"."""
+    spatial = s2_spatial_weights(boxes)
+    semantic = spatial if embeddings is None else s2_semantic_weights(embeddings)
+    return (spatial + semantic) / 2
+
+
+def s2_best_clusters(weights: np.ndarray, n_nodes: int, min_k: int = 2, max_k: int = 10):
+    """_calculate_n_clusters with calculate_n_clusters == "best" (:1815-1849)."""
+    from sklearn.cluster import SpectralClustering
+    from sklearn.metrics import silhouette_score
+    degree = np.sum(weights, axis=1)
+    d_inv_sqrt = np.diag(1.0 / (np.sqrt(degree) + 1e-10))
+    l_norm = np.eye(weights.shape[0]) - d_inv_sqrt @ weights @ d_inv_sqrt
+    _, eigenvectors = np.linalg.eigh(l_norm)
+    embedding = eigenvectors[:, :max_k]
+    best_k, best_score, best_labels = min_k, -1, np.full(n_nodes, -1)
+    for k in range(min_k, min(max_k, n_nodes - 1) + 1):
+        labels = SpectralClustering(n_clusters=k, affinity="precomputed").fit_predict(weights)
+        score_k = silhouette_score(embedding, labels)
+        if score_k > best_score:
+            best_score, best_k, best_labels = score_k, k, labels
+    return best_k, best_labels
+
+
+def s2_forward(layout_info: Sequence[dict], pages_info=None, cluster_mode: str = "spatial", embed=None) -> List[np.ndarray]:
+    """S2Chunker.forward (:1929-1962) for calculate_n_clusters == "best" (the shipped setting, precompute_layouts.py:130-131)."""
+    out = []
+    for p, page in enumerate(layout_info):
+        if len(page["boxes"]) == 0:
+            out.append(np.array([]))
+            continue
+        page_info = pages_info[p] if pages_info is not None else None
+        nodes, edges, used = s2_nodes(page, page_info, cluster_mode)
+        if len(nodes) < 2:
+            out.append(np.full(len(page["boxes"]), -1))
+            continue
+        emb = None
+        if cluster_mode == "spatial+semantic":
+            emb = embed([n["text"] for n in nodes if n.get("text", "").strip()])
+        weights = s2_combined_weights([n["bbox"] for n in nodes], emb)
+        ids = [n["global_id"] for n in nodes]
+        for (u, v) in edges:                                # _add_weights_to_graph (:1810-1813): weights[u, v] by GLOBAL id
+            weights[u, v]
+        _, labels = s2_best_clusters(weights, len(nodes))
+        clusters = [lab for _, lab in sorted(zip(ids, labels), key=lambda item: item[0])]
+        complete = np.full(len(used), -1)
+        complete[used] = clusters
+        out.append(complete)
+    return out

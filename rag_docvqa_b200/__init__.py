@@ -1,7 +1,7 @@
 """B200-native retrieval stage of RAG-DocVQA.
 
     from rag_docvqa_b200 import Retriever, VisualRetriever, mean_pooling, late_interaction      # the drop-ins
-    from rag_docvqa_b200 import Reranker, major_page_indices, Chunker                            # either side of the path
+    from rag_docvqa_b200 import Reranker, major_page_indices, Chunker, S2Chunker                 # either side of the path
     from rag_docvqa_b200 import DocStore, PageStore, CorpusShard                                 # device-resident stores
 
 Names are resolved on first use, so `import rag_docvqa_b200` itself needs neither torch nor the built library
@@ -10,7 +10,7 @@ Names are resolved on first use, so `import rag_docvqa_b200` itself needs neithe
 _EXPORTS = {
     "Retriever": "retriever", "VisualRetriever": "retriever",
     "mean_pooling": "functional", "late_interaction": "functional", "score_topk": "functional",
-    "Reranker": "postproc", "major_page_indices": "postproc", "Chunker": "chunker",
+    "Reranker": "postproc", "major_page_indices": "postproc", "Chunker": "chunker", "S2Chunker": "s2chunker",
     "DocStore": "docstore", "PageStore": "pagestore", "CorpusShard": "sharded", "CorpusIndex": "sharded",
 }
 

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Struc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
@@ -61,6 +61,15 @@ class P2SArgsStruct(Structure):
                 ("doc_total", c_void_p), ("out", c_void_p), ("mask", c_void_p), ("max_h", c_int32), ("reserved", c_int32)]
 
 
+class SmallLayoutStruct(Structure):
+    """Mirror of `rdv_small_layout` (include/rdv.h)."""
+    _fields_ = [(n, c_int32) for n in ("algo", "tile_rows", "n_tiles", "max_rows")] + [(n, c_int64) for n in (
+        "total_rows", "o_tiles", "o_q", "o_emb", "in_bytes", "o_idx", "o_cnt", "read_bytes", "o_val", "out_bytes")]
+
+
+SMALL_GROW = 1
+S2_COMBINED, S2_SPATIAL, S2_SEMANTIC = 0, 1, 2
+
 # name -> (restype, argtypes); tests/test_abi.py checks this table against include/rdv.h
 SIGNATURES = {
     "rdv_abi_version": (c_int32, []),
@@ -71,6 +80,10 @@ SIGNATURES = {
     "rdv_build_doc_table": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64,
                                       POINTER(c_int32)]),
     "rdv_upload_docs_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "rdv_small_batch_layout": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "rdv_small_batch_pack": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_retrieve_small_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                         c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "rdv_score_topk_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                      c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_score_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
@@ -103,6 +116,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "rdv_layout_assign": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_s2_weights": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p,
+                                 c_void_p]),
     "rdv_gather_vt5_inputs": (c_int32, [POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
 }
 

@@ -32,7 +32,26 @@ def _make_replacements():
         "late_interaction": _late_interaction_dispatch(functional),
         "Reranker": _reranker_class(),
         "Chunker": _chunker_class(),
+        "S2Chunker": _s2chunker_class(),
     }
+
+
+def _s2chunker_class():
+    from . import s2chunker
+
+    class S2Chunker(s2chunker.S2Chunker):
+        """reference constructor (src/_modules.py:1670-1685): in "spatial+semantic" mode without an embedder the
+        REFERENCE's own BiEncoder(config) is built (the encoder stays the reference's)."""
+
+        def __init__(self, config: dict, embedder=None):
+            if embedder is None and config.get("cluster_mode", "spatial+semantic") == "spatial+semantic":
+                ref = sys.modules.get("src._modules")
+                if ref is None:
+                    raise ValueError("S2Chunker: no embedder given and src._modules is not imported")
+                embedder = ref.BiEncoder(config)
+            super().__init__(config, embedder)
+
+    return S2Chunker
 
 
 def _chunker_class():
@@ -75,7 +94,7 @@ def _late_interaction_dispatch(functional):
 
 
 def install(modules=None) -> list:
-    """Rebinds the six names in every loaded `src.*` module of the reference that defines or imported
+    """Rebinds the seven names in every loaded `src.*` module of the reference that defines or imported
     them.  Returns the list of (module, name) pairs patched.  Idempotent; undo with uninstall()."""
     repl = replacements()
     done = []

@@ -52,7 +52,7 @@ int sm_count() {
 
 }  // namespace rdv
 
-extern "C" int rdv_abi_version(void) { return 14; }
+extern "C" int rdv_abi_version(void) { return 15; }
 
 extern "C" const char* rdv_last_error(void) { return rdv::g_error; }
 
@@ -131,5 +131,100 @@ extern "C" int rdv_upload_docs_f32(const void* const* h_docs, const int64_t* row
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync (upload_docs_f32)");
         off += n;
     }
+    return RDV_OK;
+}
+
+// ---- small host batches: the whole Retriever.retrieve device round trip in ONE call ----------------------------
+// (C1 = 1 page x 30 chunks x 384-d is 46 KB: every framework-level call on the way -- table building, two copies, a
+// launch, a synchronise -- costs more than the work.  The layout / pack halves are pure host code, testable without a GPU.)
+static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int rdv_small_batch_layout(const int64_t* rows, int32_t B, int32_t d, int32_t k, rdv_small_layout* lay) {
+    using namespace rdv;
+    RDV_REQUIRE(lay && (rows || B == 0), RDV_E_INVALID, "small_batch_layout: null pointer");
+    RDV_REQUIRE(B >= 1 && d >= 4 && d <= 8192 && (d & 3) == 0, RDV_E_INVALID, "small_batch_layout: bad B=%d / d=%d", B, d);
+    RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "small_batch_layout: k=%d outside [1, 1024]", k);
+    int64_t total = 0, mx = 0;
+    for (int32_t b = 0; b < B; ++b) {
+        RDV_REQUIRE(rows[b] >= 0 && rows[b] < (1ll << 31), RDV_E_LIMIT, "small_batch_layout: document %d has %lld rows", b,
+                    (long long)rows[b]);
+        total += rows[b];
+        if (rows[b] > mx) mx = rows[b];
+    }
+    RDV_REQUIRE(total * (int64_t)d * 4 <= (1ll << 30), RDV_E_LIMIT, "small_batch_layout: %lld rows is not a small batch",
+                (long long)total);
+    int32_t algo = 0, tile_rows = 0;
+    int rc = rdv_score_plan(total, d, RDV_SCORE_LDG_FUSED, &algo, &tile_rows);
+    if (rc) return rc;
+    const int64_t T = rdv_count_tiles(rows, B, tile_rows);
+    RDV_REQUIRE(T >= 0 && T < (1ll << 31), RDV_E_LIMIT, "small_batch_layout: too many tiles");
+    memset(lay, 0, sizeof(*lay));
+    lay->algo = algo; lay->tile_rows = tile_rows; lay->n_tiles = (int32_t)T; lay->max_rows = (int32_t)mx;
+    lay->total_rows = total;
+    lay->o_tiles = round_up(8 * ((int64_t)B + 1), 32);
+    lay->o_q = lay->o_tiles + 32 * (T > 0 ? T : 1);
+    lay->o_emb = lay->o_q + (int64_t)B * d * 4;
+    lay->in_bytes = lay->o_emb + total * (int64_t)d * 4;
+    lay->o_idx = total * 4;
+    lay->o_cnt = lay->o_idx + (int64_t)B * k * 4;
+    lay->read_bytes = lay->o_cnt + (int64_t)B * 4;
+    lay->o_val = lay->read_bytes;
+    lay->out_bytes = lay->o_val + (int64_t)B * k * 4;
+    return RDV_OK;
+}
+
+extern "C" int rdv_small_batch_pack(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, const float* h_q,
+                                    const rdv_small_layout* lay, void* h_blob, const void* d_blob) {
+    using namespace rdv;
+    RDV_REQUIRE(h_docs && rows && h_q && lay && h_blob && d_blob, RDV_E_INVALID, "small_batch_pack: null pointer");
+    RDV_REQUIRE(B >= 1 && B <= 4096, RDV_E_LIMIT, "small_batch_pack: B=%d outside [1, 4096]", B);
+    RDV_REQUIRE(aligned16(h_blob) && aligned16(d_blob), RDV_E_ALIGN, "small_batch_pack: blobs must be 16-byte aligned");
+    char* hb = static_cast<char*>(h_blob);
+    const char* db = static_cast<const char*>(d_blob);
+    const void* d_docs[4096];
+    int64_t off = 0;
+    const size_t row_bytes = (size_t)d * 4;
+    for (int32_t b = 0; b < B; ++b) {
+        const int64_t n = rows[b];
+        RDV_REQUIRE(n >= 0 && (n == 0 || h_docs[b]), RDV_E_INVALID, "small_batch_pack: document %d is null", b);
+        d_docs[b] = n ? db + lay->o_emb + (size_t)off * row_bytes : nullptr;
+        if (n) memcpy(hb + lay->o_emb + (size_t)off * row_bytes, h_docs[b], (size_t)n * row_bytes);
+        off += n;
+    }
+    RDV_REQUIRE(off == lay->total_rows, RDV_E_INVALID, "small_batch_pack: layout is for %lld rows, batch has %lld",
+                (long long)lay->total_rows, (long long)off);
+    memcpy(hb + lay->o_q, h_q, (size_t)B * row_bytes);
+    int32_t mx = 0;
+    return rdv_build_doc_table(d_docs, rows, B, d, lay->tile_rows, reinterpret_cast<int64_t*>(hb),
+                               reinterpret_cast<rdv_tile_desc*>(hb + lay->o_tiles), lay->n_tiles, &mx);
+}
+
+extern "C" int rdv_retrieve_small_f32(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, int32_t k,
+                                      const float* h_q, void* h_blob, void* d_blob, int64_t blob_bytes, void* d_out,
+                                      int64_t d_out_bytes, void* h_out, int64_t h_out_bytes, int32_t* d_doc_done,
+                                      rdv_small_layout* lay, void* stream) {
+    using namespace rdv;
+    int rc = rdv_small_batch_layout(rows, B, d, k, lay);
+    if (rc) return rc;
+    if (lay->in_bytes > blob_bytes || lay->out_bytes > d_out_bytes || lay->read_bytes > h_out_bytes)
+        return RDV_SMALL_GROW;                                   // nothing touched: the caller grows its buffers and calls again
+    RDV_REQUIRE(d_out && h_out && d_doc_done, RDV_E_INVALID, "retrieve_small_f32: null pointer");
+    rc = rdv_small_batch_pack(h_docs, rows, B, d, h_q, lay, h_blob, d_blob);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(d_blob, h_blob, (size_t)lay->in_bytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync (retrieve_small_f32, upload)");
+    char* in = static_cast<char*>(d_blob);
+    char* out = static_cast<char*>(d_out);
+    rc = rdv_score_topk_f32(reinterpret_cast<const rdv_tile_desc*>(in + lay->o_tiles), lay->n_tiles, lay->tile_rows, lay->algo,
+                            reinterpret_cast<const int64_t*>(in), reinterpret_cast<const float*>(in + lay->o_q), B, d, k,
+                            lay->max_rows, reinterpret_cast<float*>(out), reinterpret_cast<int32_t*>(out + lay->o_idx),
+                            reinterpret_cast<float*>(out + lay->o_val), reinterpret_cast<int32_t*>(out + lay->o_cnt),
+                            d_doc_done, stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(h_out, d_out, (size_t)lay->read_bytes, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync (retrieve_small_f32, read-back)");
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize (retrieve_small_f32)");
     return RDV_OK;
 }

@@ -349,75 +349,59 @@ class Retriever(StatComponent):
     def _small_buffers(self, dev, n_in: int, n_dev_out: int, n_host_out: int):
         """Pinned upload blob, its device twin, the device result buffer and its pinned read-back buffer, kept
         between calls (every call ends with a stream synchronise, so nothing is in flight when they are reused)."""
-        key = (dev.index, F._stream_ptr(dev))
-        bufs = self._small_bufs.get(key)
-        if bufs is None or bufs[0].numel() < n_in or bufs[2].numel() < n_dev_out or bufs[3].numel() < n_host_out:
-            c_in, c_dev, c_host = (max(2 * n, 1 << 16) for n in (n_in, n_dev_out, n_host_out))
+        c_in, c_dev, c_host = (max(2 * n, 1 << 16) for n in (n_in, n_dev_out, n_host_out))
+        with torch.cuda.device(dev):
             bufs = (torch.empty(c_in, dtype=torch.uint8, pin_memory=True),
                     torch.empty(c_in, dtype=torch.uint8, device=dev),
                     torch.empty(c_dev, dtype=torch.uint8, device=dev),
-                    torch.empty(c_host, dtype=torch.uint8, pin_memory=True))
-            self._small_bufs[key] = bufs
+                    torch.empty(c_host, dtype=torch.uint8, pin_memory=True),
+                    torch.zeros(4096, dtype=torch.int32, device=dev))          # doc_done: the kernel leaves it zeroed
+            torch.cuda.current_stream(dev).synchronize()
+        bufs = bufs + tuple(t.data_ptr() for t in bufs) + (bufs[3].numpy(),)
+        self._small_bufs[dev.index] = bufs
         return bufs
 
     def _retrieve_host_small(self, text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
                              layout_labels_chunks, images, page_indices) -> tuple:
         """Host inputs of at most a megabyte (C1: one page of 30 chunks, the reference's own CPU-runnable case): a 46 KB
-        problem is all fixed cost, so the call is cut to ONE upload (row offsets, tile descriptors, questions and the
-        embedding rows in one pinned blob), ONE launch (fused score + top-k) and ONE read-back (similarities, hits and
-        counts in one buffer) -- 0.16 ms per call through the general path was 7 transfers and 2 launches."""
+        problem is all fixed cost, so the device round trip is ONE C call (rdv_retrieve_small_f32): row offsets, tile
+        descriptors, questions and embedding rows packed into one pinned blob, one upload, one launch (fused score +
+        top-k), one read-back of similarities, hits and counts, one synchronise.  Measured on B200 at C1: 0.164 ms per
+        call through the general path (7 transfers, 2 launches) -> 0.124 ms with one blob each way driven from Python."""
         dev = self.device
         B, d, k = len(text_embeddings), int(question_embeddings.shape[1]), int(self.k)
-        lib, check = F._lib_fn, F._lib.check
-        sizes = np.fromiter((e.shape[0] for e in text_embeddings), dtype=np.int64, count=B)
+        docs, sizes = [], []
         for b, e in enumerate(text_embeddings):
-            if e.shape[0] and e.shape[1] != d:
+            n = e.shape[0]
+            if n and e.shape[1] != d:
                 raise ValueError("document %d: expected (n, %d) embeddings, got %s" % (b, d, tuple(e.shape)))
-        total = int(sizes.sum())
-        algo, tile_rows = F.plan_score(total, d, F._lib.SCORE_LDG_FUSED)
-        T = int(lib.rdv_count_tiles(sizes.ctypes.data, B, tile_rows))
-        if T < 0:
-            raise ValueError("bad document sizes")
-        # upload blob: row_off[B+1] i64 | pad | tiles[T] | questions (B, d) | rows (total, d); every part 16-byte aligned
-        o_tiles = (8 * (B + 1) + 31) // 32 * 32
-        o_q = o_tiles + 32 * max(T, 1)
-        o_emb = o_q + B * d * 4
-        n_in = o_emb + total * d * 4
-        # result buffer: sims[total] | idx (B, k) | cnt[B] are read back; val (B, k) stays on the device
-        o_idx = total * 4
-        o_cnt = o_idx + B * k * 4
-        n_read = o_cnt + B * 4
-        with torch.cuda.device(dev):
-            host, blob, out, out_h = self._small_buffers(dev, n_in, n_read + B * k * 4, n_read)
-            done = F._Workspace.zeros_i32(dev, B)
-            raw = host.numpy()
-            raw[o_q:o_emb].view(np.float32).reshape(B, d)[:] = question_embeddings.detach().numpy()
-            rows = raw[o_emb:n_in].view(np.float32).reshape(total, d)
-            row0 = np.zeros(B + 1, dtype=np.int64)
-            np.cumsum(sizes, out=row0[1:])
-            for b, e in enumerate(text_embeddings):
-                if e.shape[0]:
-                    rows[row0[b]:row0[b + 1]] = e.detach().numpy()
-            ptrs = (np.uint64(blob.data_ptr() + o_emb) + (row0[:-1] * (d * 4)).astype(np.uint64)) * (sizes > 0).astype(np.uint64)
-            max_rows = ctypes.c_int32(0)
-            base = host.data_ptr()
-            check(lib.rdv_build_doc_table(ptrs.ctypes.data, sizes.ctypes.data, B, d, tile_rows, base, base + o_tiles, T,
-                                          ctypes.byref(max_rows)))
-            stream = torch.cuda.current_stream(dev)
-            blob[:n_in].copy_(host[:n_in], non_blocking=True)
-            p_in, p_out = blob.data_ptr(), out.data_ptr()
-            check(lib.rdv_score_topk_f32(p_in + o_tiles, T, tile_rows, algo, p_in, p_in + o_q, B, d, k, int(max_rows.value),
-                                         p_out, p_out + o_idx, p_out + n_read, p_out + o_cnt, done.data_ptr(),
-                                         stream.cuda_stream))
-            out_h[:n_read].copy_(out[:n_read], non_blocking=True)
-            stream.synchronize()
-        res = out_h.numpy()
+            docs.append(e.detach().contiguous())
+            sizes.append(n)
+        q = question_embeddings.detach().contiguous()
+        h_docs = (ctypes.c_void_p * B)(*[t.data_ptr() if n else None for t, n in zip(docs, sizes)])
+        rows = (ctypes.c_int64 * B)(*sizes)
+        lay = F._lib.SmallLayoutStruct()
+        bufs = self._small_bufs.get(dev.index) or self._small_buffers(dev, 0, 0, 0)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        call = F._lib_fn.rdv_retrieve_small_f32
+        while True:
+            host, blob, out, out_h, done, p_host, p_blob, p_out, p_out_h, p_done, res = bufs
+            with torch.cuda.device(dev):
+                rc = call(h_docs, rows, B, d, k, q.data_ptr(), p_host, p_blob, host.numel(), p_out, out.numel(), p_out_h,
+                          out_h.numel(), p_done, ctypes.addressof(lay), stream)
+            if rc != F._lib.SMALL_GROW:
+                break
+            bufs = self._small_buffers(dev, lay.in_bytes, lay.out_bytes, lay.read_bytes)
+        if rc:
+            self._small_bufs.pop(dev.index, None)          # doc_done may be dirty after a failed launch
+            F._lib.check(rc)
+        o_idx, o_cnt = lay.o_idx, lay.o_cnt
         idx = res[o_idx:o_cnt].view(np.int32).reshape(B, k)
-        cnt = res[o_cnt:n_read].view(np.int32)
+        cnt = res[o_cnt:lay.read_bytes].view(np.int32).tolist()
         hits = [idx[b, :cnt[b]].tolist() for b in range(B)]
         sims = torch.from_numpy(res[:o_idx].view(np.float32).copy())          # the caller owns its similarities
         lists = self._hit_lists(hits, words_text_chunks, words_box_chunks, layout_labels_chunks, images, page_indices)
-        return (*lists, list(torch.split(sims, sizes.tolist())))
+        return (*lists, list(torch.split(sims, sizes)))
 
     def _retrieve_host_pipelined(self, text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
                                  layout_labels_chunks, images, page_indices) -> tuple:

@@ -261,3 +261,44 @@ def make_chunker_batch(seed: int, docs: int = 4, max_pages: int = 6, max_words: 
             d_info.append(page)
         words.append(d_words); boxes.append(d_boxes); info.append(d_info)
     return words, boxes, info
+
+
+def make_s2_pages(seed: int, pages: int = 6, max_layouts: int = 30, max_words: int = 300, degenerate: bool = True):
+    """S2Chunker.forward inputs (reference src/_modules.py:1929-1962): layout_info [pages] {"boxes": [n_l][4] float 0..1,
+    "labels": [n_l]} and pages_info [pages] {"ocr_tokens": [n] str, "ocr_normalized_boxes": [n][4]}.  Layout boxes have
+    arbitrary float64 coordinates (pixel / page size, as LayoutModel produces them, :520-524), some pages have no or one
+    layout box, some boxes coincide (distance 0) and some hold no word."""
+    rng = np.random.RandomState(seed)
+    layout_info, pages_info = [], []
+    for p in range(pages):
+        n_l = int(rng.randint(2, max_layouts + 1))
+        if degenerate and p % 5 == 3:
+            n_l = int(rng.randint(0, 2))
+        w, h = int(rng.randint(600, 2600)), int(rng.randint(800, 3400))
+        x0 = rng.randint(0, w - 50, size=n_l); y0 = rng.randint(0, h - 50, size=n_l)
+        x1 = np.minimum(w, x0 + rng.randint(20, w // 2, size=n_l)); y1 = np.minimum(h, y0 + rng.randint(10, h // 3, size=n_l))
+        boxes = [[int(a) / w, int(b) / h, int(c) / w, int(d) / h] for a, b, c, d in zip(x0, y0, x1, y1)]
+        if degenerate and n_l > 3:
+            boxes[2] = list(boxes[0])                                    # coincident regions: distance 0, weight 1
+        layout_info.append({"boxes": boxes, "labels": [int(x) for x in rng.randint(0, 11, size=n_l)]})
+        n = int(rng.randint(max_words // 4, max_words + 1))
+        wx0 = rng.uniform(0.0, 0.92, size=n); wy0 = rng.uniform(0.0, 0.96, size=n)
+        wb = np.stack([wx0, wy0, wx0 + rng.uniform(0.01, 0.07, size=n), wy0 + rng.uniform(0.008, 0.02, size=n)], axis=1)
+        pages_info.append({"ocr_tokens": ["w%d" % i for i in rng.randint(0, 5000, size=n)],
+                           "ocr_normalized_boxes": wb.tolist()})
+    return layout_info, pages_info
+
+
+class HashEmbedder:
+    """Stand-in for BiEncoder (a producer outside the path): a deterministic (n, dim) fp32 embedding per text, with a
+    shared direction so cosines are mostly positive; an empty list gives (0, dim) as the reference does (:1463-1464)."""
+
+    def __init__(self, dim: int = 384, device="cpu"):
+        self.dim, self.device = dim, device
+        self.common = torch.randn(dim, generator=_gen(99))
+
+    def forward(self, texts: List[str]) -> torch.Tensor:
+        import zlib
+        rows = [torch.randn(self.dim, generator=_gen(zlib.crc32(t.encode()) & 0x7FFFFFFF)) + 0.7 * self.common for t in texts]
+        out = torch.stack(rows) if rows else torch.empty(0, self.dim)
+        return out.to(self.device)

@@ -60,6 +60,11 @@ def test_argument_errors_are_reported_before_any_launch():
         (lib.rdv_layout_assign(None, None, None, None, None, None, None, -1, 1, None, None, None, None), _lib.E_INVALID, "negative"),
         (lib.rdv_layout_assign(None, None, None, None, None, None, None, 3, 1, None, None, None, None), _lib.E_INVALID, "null"),
         (lib.rdv_topk_merge(None, None, 2, 4, 0, None, None, None), _lib.E_INVALID, "topk_merge"),
+        (lib.rdv_s2_weights(None, None, -1, None, 0, 0, None, 4, None, None), _lib.E_INVALID, "negative"),
+        (lib.rdv_s2_weights(None, None, 2, None, 0, 0, None, 4, None, None), _lib.E_INVALID, "null"),
+        (lib.rdv_s2_weights(16, 16, 2, None, 0, 7, 16, 4, 16, None), _lib.E_INVALID, "what"),
+        (lib.rdv_s2_weights(16, 16, 2, None, 0, _lib.S2_SEMANTIC, 16, 4, 16, None), _lib.E_INVALID, "embeddings"),
+        (lib.rdv_s2_weights(8, 16, 2, None, 0, _lib.S2_SPATIAL, 16, 4, 16, None), _lib.E_ALIGN, "aligned"),
     ]
     for code, want, needle in cases:
         assert code == want, (code, want, needle)
@@ -74,3 +79,4 @@ def test_argument_errors_are_reported_before_any_launch():
     assert lib.rdv_rerank_order(None, 0, None, 0, 5, 0.4, 5, 1, None, None, None, None) == _lib.OK
     assert lib.rdv_page_vote(None, None, None, None, 0, 5, 1, 1, None, None, None) == _lib.OK
     assert lib.rdv_layout_assign(None, None, None, None, None, None, None, 0, 1, None, None, None, None) == _lib.OK
+    assert lib.rdv_s2_weights(None, None, 0, None, 0, 0, None, 0, None, None) == _lib.OK

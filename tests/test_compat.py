@@ -47,11 +47,16 @@ def test_signatures_equal_live_reference_and_install_rebinds():
     from rag_docvqa_b200.chunker import Chunker
     assert params(Chunker.get_chunks) == params(modules.Chunker.get_chunks)            # :872-878
     assert params(Chunker.__init__) == params(modules.Chunker.__init__)
+    from rag_docvqa_b200.s2chunker import S2Chunker
+    for name in ("__init__", "forward", "create_nodes_and_edges", "cluster", "_combined_weights", "_spatial_weights_calculation",
+                 "_semantic_weights_calculation", "_calculate_n_clusters", "_cluster_graph", "_split_clusters_by_token_length"):
+        assert params(getattr(S2Chunker, name)) == params(getattr(modules.S2Chunker, name)), name    # :1669-1962
     ref_retriever = modules.Retriever
     try:
         done = compat.install()
         assert ("src._modules", "Retriever") in done and ("src._modules", "late_interaction") in done
         assert modules.Retriever is Retriever and modules.VisualRetriever is VisualRetriever
+        assert ("src._modules", "S2Chunker") in done and issubclass(modules.S2Chunker, S2Chunker)
         assert utils.late_interaction.__doc__.startswith("reference signature")
         assert compat.install() == []          # idempotent
     finally:

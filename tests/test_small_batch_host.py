@@ -1,0 +1,90 @@
+"""CPU checks of the host half of rdv_retrieve_small_f32 (include/rdv.h): rdv_small_batch_layout and
+rdv_small_batch_pack are pure host code -- the packed upload blob must describe the batch exactly as the general path's
+rdv_build_doc_table does, and scoring the BLOB's rows with the oracle must equal scoring the documents."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_restated as R
+from rag_docvqa_b200 import _lib, synth
+from rag_docvqa_b200.functional import TILE_DTYPE
+
+CASES = [([30], 384, 5), ([45, 0, 3], 384, 5), ([60, 0, 3, 150, 1, 90, 31], 768, 10), ([0, 0], 8, 1), ([700], 128, 40)]
+
+
+def pack(sizes, d, k, seed=3):
+    emb, q = synth.make_embeddings(sizes, d, seed)
+    B = len(sizes)
+    rows = (ctypes.c_int64 * B)(*sizes)
+    lay = _lib.SmallLayoutStruct()
+    _lib.check(_lib.lib.rdv_small_batch_layout(rows, B, d, k, ctypes.addressof(lay)))
+    h_blob = np.zeros(lay.in_bytes + 16, dtype=np.uint8)
+    base = h_blob.ctypes.data + (-h_blob.ctypes.data) % 16
+    h_docs = (ctypes.c_void_p * B)(*[e.data_ptr() if n else None for e, n in zip(emb, sizes)])
+    fake_dev = 0x7F0000000000                       # the tile descriptors point into the DEVICE twin of the blob
+    _lib.check(_lib.lib.rdv_small_batch_pack(h_docs, rows, B, d, q.data_ptr(), ctypes.addressof(lay), base, fake_dev))
+    off = base - h_blob.ctypes.data
+    return emb, q, lay, h_blob[off:off + lay.in_bytes], fake_dev
+
+
+@pytest.mark.parametrize("sizes,d,k", CASES)
+def test_layout_and_pack(sizes, d, k):
+    emb, q, lay, blob, dev = pack(sizes, d, k)
+    B, total = len(sizes), sum(sizes)
+    assert lay.total_rows == total and lay.max_rows == max(sizes)
+    assert lay.algo == _lib.SCORE_LDG_FUSED and 1 <= lay.tile_rows <= 1024
+    assert lay.n_tiles == sum(-(-n // lay.tile_rows) for n in sizes)
+    # every part 16-byte aligned, parts in order and not overlapping
+    assert lay.o_tiles % 32 == 0 and lay.o_q % 16 == 0 and lay.o_emb % 16 == 0
+    assert 8 * (B + 1) <= lay.o_tiles and lay.o_tiles + 32 * lay.n_tiles <= lay.o_q
+    assert lay.o_q + B * d * 4 == lay.o_emb and lay.o_emb + total * d * 4 == lay.in_bytes
+    assert lay.o_idx == total * 4 and lay.o_cnt == lay.o_idx + B * k * 4 and lay.read_bytes == lay.o_cnt + B * 4
+    assert lay.o_val >= lay.read_bytes and lay.out_bytes == lay.o_val + B * k * 4
+    row_off = blob[:8 * (B + 1)].view(np.int64)
+    assert row_off.tolist() == np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    assert np.array_equal(blob[lay.o_q:lay.o_emb].view(np.float32).reshape(B, d), q.numpy())
+    rows = blob[lay.o_emb:].view(np.float32).reshape(total, d)
+    tiles = blob[lay.o_tiles:lay.o_tiles + 32 * lay.n_tiles].view(TILE_DTYPE)
+    seen = np.zeros(total, dtype=bool)
+    prev = (-1, -1)
+    for t in tiles:
+        doc, n, r0 = int(t["doc"]), int(t["rows"]), int(t["sims_off"])
+        assert 1 <= n <= lay.tile_rows and int(t["doc_rows"]) == sizes[doc] and int(t["reserved"]) == 0
+        assert row_off[doc] <= r0 and r0 + n <= row_off[doc + 1]
+        assert int(t["src"]) == dev + lay.o_emb + r0 * d * 4            # the tile's rows sit at sims_off in the packed matrix
+        assert (doc, r0) > prev                                          # tiles of a document contiguous, ordered by sims_off
+        prev = (doc, r0)
+        assert not seen[r0:r0 + n].any()
+        seen[r0:r0 + n] = True
+    assert seen.all()
+    # the packed rows ARE the documents: the oracle's scores and hits from the blob equal those from the inputs
+    packed_docs = [torch.from_numpy(rows[row_off[b]:row_off[b + 1]].copy()) for b in range(B)]
+    for a, b_ in zip(packed_docs, emb):
+        assert torch.equal(a, b_)
+    ref = R.score(emb, q)
+    got = R.score(packed_docs, torch.from_numpy(blob[lay.o_q:lay.o_emb].view(np.float32).reshape(B, d).copy()))
+    for x, y in zip(ref, got):
+        assert torch.equal(x, y)
+        assert np.array_equal(R.topk_lowest_index(x, k), R.topk_lowest_index(y, k))
+
+
+def test_small_batch_argument_errors():
+    lib = _lib.lib
+    lay = _lib.SmallLayoutStruct()
+    rows = (ctypes.c_int64 * 2)(3, -1)
+    assert lib.rdv_small_batch_layout(rows, 2, 384, 5, ctypes.addressof(lay)) == _lib.E_LIMIT
+    assert b"document 1" in lib.rdv_last_error()
+    rows = (ctypes.c_int64 * 2)(3, 4)
+    assert lib.rdv_small_batch_layout(rows, 2, 386, 5, ctypes.addressof(lay)) == _lib.E_INVALID
+    assert lib.rdv_small_batch_layout(rows, 2, 384, 0, ctypes.addressof(lay)) == _lib.E_LIMIT
+    assert lib.rdv_small_batch_layout(rows, 2, 384, 5, None) == _lib.E_INVALID
+    assert lib.rdv_small_batch_layout(rows, 2, 384, 5, ctypes.addressof(lay)) == _lib.OK
+    # buffers smaller than the layout: RDV_SMALL_GROW before anything is touched (no CUDA call on this path)
+    q = np.zeros((2, 384), dtype=np.float32)
+    docs = (ctypes.c_void_p * 2)(q.ctypes.data, q.ctypes.data)
+    rc = lib.rdv_retrieve_small_f32(docs, rows, 2, 384, 5, q.ctypes.data, None, None, 0, None, 0, None, 0, None,
+                                    ctypes.addressof(lay), None)
+    assert rc == _lib.SMALL_GROW and lay.in_bytes > 0 and lay.out_bytes > lay.read_bytes > 0
+    assert lib.rdv_small_batch_pack(docs, rows, 2, 384, q.ctypes.data, ctypes.addressof(lay), None, None) == _lib.E_INVALID
