@@ -11,7 +11,8 @@ files (bit-exact: same torch CPU ops in the same order), and -- when /root/refer
 against the live reference as well.  The components either side of the path are pinned the same way:
 oracle/make_golden_postproc.py (the reference's Reranker.rerank and the page vote of RAGVT5.forward, run as
 written on a stand-in `self`) -> postproc.json, tests/test_postproc_oracle.py; oracle/make_golden_chunker.py (the
-reference's Chunker.get_chunks) -> chunker.json, tests/test_chunker_oracle.py.
+reference's Chunker.get_chunks) -> chunker.json, tests/test_chunker_oracle.py; oracle/make_golden_s2chunker.py (the reference's
+S2Chunker node building, weight matrices and forward) -> s2chunker.json, tests/test_s2chunker_oracle.py.
 
 Each function cites the reference lines it restates.  Floating-point work uses the same torch CPU
 operators the reference calls (torch.norm / matmul / topk / F.normalize / bmm), so results are
