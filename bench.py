@@ -824,6 +824,37 @@ def run_corpus(args):
         "gpu_launches": args.steps * (5 if world == 1 else 6),
         "clocks": clocks.summary(),
     }
+    if world == 1:
+        # bf16 mode against the fp32 result (north_star): recall@k of the tensor-core path for the first 32 questions
+        # against fp32 cosine scores of the same stored rows (un-rounded fp32 questions, plain torch matmul in fp32,
+        # row chunks of 1 M).  Sharding does not change the hits (sharded == unsharded bit for bit, tests/test_tc_gpu.py),
+        # so it is measured on the single-GPU run only.  Verification code after the timed region; never a bench value.
+        try:
+            n_q = min(32, Qn)
+            allow = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            _, got_idx = sharded.search(shard, q_dev, k)
+            qs = q_dev[:n_q].float()
+            qs = qs / qs.norm(dim=1, keepdim=True)
+            best_v = torch.full((n_q, k), float("-inf"), device=dev)
+            best_i = torch.zeros((n_q, k), dtype=torch.int64, device=dev)
+            for a in range(0, hi - lo, 1 << 20):
+                b = min(hi - lo, a + (1 << 20))
+                r = rows[a:b].float()
+                sc = (qs @ r.T) / r.norm(dim=1)
+                v, i = sc.topk(min(k, b - a), dim=1)
+                cat_v, cat_i = torch.cat([best_v, v], dim=1), torch.cat([best_i, i + a + lo], dim=1)
+                best_v, pos = cat_v.topk(k, dim=1)
+                best_i = torch.gather(cat_i, 1, pos)
+                del r, sc
+            torch.backends.cuda.matmul.allow_tf32 = allow
+            got = got_idx[:n_q].to(torch.int64).cpu().numpy()
+            ref_i = best_i.cpu().numpy()
+            hits = sum(len(set(got[j].tolist()) & set(ref_i[j].tolist())) for j in range(n_q))
+            line["recall_at_k_vs_fp32"] = {"value": hits / float(n_q * k), "questions": n_q, "k": k,
+                                           "reference": "fp32 cosine (torch, TF32 off) of the fp32 questions against the stored bf16 rows"}
+        except Exception as exc:                                   # reporting only: the bench line must still be printed
+            line["recall_at_k_vs_fp32"] = {"value": None, "error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0 and world == 1:
         # CPU: 1/64 row slice via torch.matmul + topk, scaled
         from oracle import ref_restated as R
