@@ -13,7 +13,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every `d_` pointer is DEVICE memory of the current CUDA device,
- *     owned by the caller; nothing is allocated, freed or synchronised inside the library.
+ *     owned by the caller; nothing is allocated, freed or synchronised inside the library (one exception, stated
+ *     at its declaration: rdv_retrieve_small_f32 is a whole host-to-host call and ends with a stream synchronise).
  *   - `stream` is a cudaStream_t / CUstream passed as void* (NULL = legacy default stream).
  *   - return value: 0 = launched, <0 = rejected before launch (RDV_E_*); rdv_last_error() describes it.
  *     There is no CPU fallback: a build without the CUDA kernels does not exist.
