@@ -106,3 +106,34 @@ def test_product_host_half_needs_no_gpu(golden_dir, monkeypatch):
             assert nodes == ref[0] and edges == ref[1] and used.tolist() == ref[2].tolist()
     with pytest.raises(ValueError):
         S2Chunker({"cluster_mode": "spatial+semantic", "device": "cuda:0"})
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+def test_product_heuristic_mode_equals_live_reference(monkeypatch):
+    """calculate_n_clusters == "heuristic" (KMeans on the spectral embedding, SpectralClustering, then the split by token
+    length): the reference needs `max_token_length` set by hand (:1678 is commented out) and a tokenizer; with both given,
+    the product's host half (weights from the oracle) must return the reference's arrays under the same numpy seed."""
+    from rag_docvqa_b200.s2chunker import S2Chunker
+    modules, _, _ = import_reference()
+    monkeypatch.setattr(S2Chunker, "weights_batch",
+                        lambda self, boxes, emb=None, what=0: [R.s2_combined_weights(b, None) for b in boxes])
+
+    class Tok:
+        @staticmethod
+        def tokenize(text):
+            return text.split() or ["x"] * 7
+
+    layout_info, _ = synth.make_s2_pages(seed=51, pages=5, max_layouts=10, max_words=60)
+    ref = modules.S2Chunker({"cluster_mode": "spatial", "calculate_n_clusters": "heuristic"})
+    mine = S2Chunker({"cluster_mode": "spatial", "calculate_n_clusters": "heuristic", "device": "cuda:0"})
+    for s2 in (ref, mine):
+        s2.tokenizer, s2.max_token_length = Tok(), 20
+    np.random.seed(3)
+    want = ref.forward(layout_info)
+    np.random.seed(3)
+    got = mine.forward(layout_info)
+    assert [np.asarray(c).tolist() for c in got] == [np.asarray(c).tolist() for c in want]
+    # without max_token_length both fail the same way
+    del mine.max_token_length
+    with pytest.raises(AttributeError):
+        mine.forward(layout_info)
