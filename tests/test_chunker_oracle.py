@@ -100,3 +100,42 @@ def test_product_chunker_host_paths_need_no_gpu(page_retrieval):
     assert dict(ch.stats["n_chunks_per_page_dist"]) == stats.n_chunks_per_page_dist
     assert dict(ch.stats["n_chunks_per_doc_dist"]) == stats.n_chunks_per_doc_dist
     assert all(len(v) <= 2 for v in ch.stats_examples["chunk_size_dist"].values())
+
+
+def emulated_assign(self, page_boxes, layout_boxes, layout_labels, default_label=-1):
+    """Stand-in for Chunker.assign_words_to_layouts (one rdv_layout_assign launch on the GPU): the same two outputs from
+    the oracle's containment_ratio in Python floats -- the decisions the kernel is tested to reproduce bit for bit
+    (tests/test_chunker_gpu.py::test_layout_assign_bit_exact_on_arbitrary_floats)."""
+    import numpy as np
+    inside, labels = [], []
+    for pb, lb, ll in zip(page_boxes, layout_boxes, layout_labels):
+        assert pb.dtype == np.float64 and lb.dtype == np.float64 and pb.shape[1:] == (4,) and lb.shape[1:] == (4,)
+        ins = np.zeros((len(lb), len(pb)), dtype=bool)
+        lab = np.full(len(pb), default_label, dtype=np.int32)
+        for g, box in enumerate(lb.tolist()):
+            for w, wb in enumerate(pb.tolist()):
+                if R.containment_ratio(wb, box) > 0.5:
+                    ins[g, w] = True
+                    lab[w] = ll[g]
+        inside.append(ins)
+        labels.append(lab)
+    return inside, labels
+
+
+def test_product_get_chunks_host_half_matches_reference_golden(golden_dir, monkeypatch):
+    """Chunker.get_chunks with layout boxes, everything but the kernel: box normalisation, the stable (xmin, ymin) order,
+    cluster grouping, chunk windows, word labels and counters against the reference's frozen outputs, on CPU."""
+    from oracle.make_golden_chunker import config_of
+    from rag_docvqa_b200.chunker import Chunker
+    monkeypatch.setattr(Chunker, "assign_words_to_layouts", emulated_assign)
+    for rec in load_cases(golden_dir):
+        case = rec["case"]
+        words, boxes, info = inputs_of(case)
+        ch = Chunker({**config_of(case), "device": "cuda:0"})
+        res = ch.get_chunks(words, boxes, info, question_id=["q%d" % b for b in range(len(words))])
+        res = json.loads(json.dumps(res))
+        assert [crc(x) for x in res] == rec["crc"], case
+        if "outputs" in rec:
+            assert res == rec["outputs"]
+        got = {k: {str(a): int(b) for a, b in v.items()} for k, v in ch.stats.items()}
+        assert got == rec["stats"], case
