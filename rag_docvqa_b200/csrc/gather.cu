@@ -379,14 +379,10 @@ extern "C" int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_ar
     P.a = *args;
     size_t smem = 0;
     if (args->sims) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(gather_vt5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(gather_vt5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gather_vt5)");
-            attr_set = true;
-        }
+        RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(gather_vt5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024),
+                            "cudaFuncSetAttribute(gather_vt5<false>)");
+        RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(gather_vt5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024),
+                            "cudaFuncSetAttribute(gather_vt5<true>)");
         smem = (size_t)(cache_floats_for(args->max_rows, args->k, 16 * kScoreThreads)) * sizeof(float) + 16;
     }
     cudaError_t le = args->include_surroundings != 0

@@ -175,12 +175,8 @@ extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int
     const int G = kPoolThreads / cols;
     // [G][cols] group partials + [d4] stash for the normalise pass
     const size_t smem = ((size_t)G * cols + (size_t)d4) * sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mean_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mean_pool)");
-        attr_set = true;
-    }
+    RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024),
+                        "cudaFuncSetAttribute(mean_pool)");
     mean_pool_kernel<<<n, kPoolThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     RDV_LAUNCH_CHECK("mean_pool_kernel");
     return RDV_OK;

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "../../include/rdv.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -31,6 +33,32 @@ int sm_count();
     do {                                                         \
         cudaError_t e__ = cudaGetLastError();                    \
         if (e__ != cudaSuccess) return ::rdv::cuda_fail(e__, what); \
+    } while (0)
+
+// Function attributes (opt-in dynamic shared memory, carve-out preference) belong to ONE device's context, so a
+// "set it once" guard has to be per device: a process that launches on cuda:0 and then on cuda:1 must opt in on
+// both.  One bit per device ordinal; ordinals >= 64 simply set the attribute every time (the call is cheap).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0ull};
+    bool pending(int* dev) {
+        *dev = 0;
+        if (cudaGetDevice(dev) != cudaSuccess) return true;
+        return *dev >= 64 || !((done.load(std::memory_order_acquire) >> *dev) & 1ull);
+    }
+    void mark(int dev) {
+        if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+    }
+};
+
+#define RDV_ONCE_PER_DEVICE(expr, what)                                 \
+    do {                                                                \
+        static ::rdv::PerDeviceOnce once__;                             \
+        int dev__;                                                      \
+        if (once__.pending(&dev__)) {                                   \
+            cudaError_t e__ = (expr);                                   \
+            if (e__ != cudaSuccess) return ::rdv::cuda_fail(e__, what); \
+            once__.mark(dev__);                                         \
+        }                                                               \
     } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -66,8 +94,9 @@ static inline void prefer_carveout(void (*kernel)(KArgs...)) {
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args&&... args) {
-    static bool carve_set = false;            // one static per kernel instantiation
-    if (!carve_set) { prefer_carveout(kernel); carve_set = true; }
+    static PerDeviceOnce carve_once;          // one static per kernel instantiation, one bit per device
+    int carve_dev;
+    if (carve_once.pending(&carve_dev)) { prefer_carveout(kernel); carve_once.mark(carve_dev); }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;

@@ -325,13 +325,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) score_tma_kernel(const ScorePa
 template <int VPL, int ROWS, int MINB>
 static int launch_ldg(const ScoreParams& p, cudaStream_t stream) {
     if (p.fused) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(score_ldg_kernel<VPL, ROWS, MINB, true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_ldg)");
-            attr_set = true;
-        }
+        RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(score_ldg_kernel<VPL, ROWS, MINB, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024),
+                            "cudaFuncSetAttribute(score_ldg)");
         const int grid = p.total_tiles > 0 ? p.total_tiles : 1;
         const size_t smem = (size_t)p.sel.cache_floats * sizeof(float) + 16;
         cudaError_t e = launch_pdl(kPdlStream, score_ldg_kernel<VPL, ROWS, MINB, true>, dim3(grid), dim3(kScoreThreads), smem, stream, p);
@@ -358,13 +354,8 @@ static void tma_plan(int d, int* tile_rows, int* stages, int64_t total_rows = 0)
 
 template <int VPL>
 static int launch_tma(ScoreParams p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(score_tma_kernel<VPL>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaRingBytes + 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_tma)");
-        attr_set = true;
-    }
+    RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(score_tma_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kTmaRingBytes + 1024), "cudaFuncSetAttribute(score_tma)");
     if (p.total_tiles == 0) return RDV_OK;
     int max_rows = 0, stages = 0;
     tma_plan(p.d, &max_rows, &stages);
@@ -428,12 +419,8 @@ __global__ void __launch_bounds__(kScoreThreads) topk_segments_kernel(const int6
 }
 
 static int launch_segments(const float* scores, const int64_t* row_off, int B, const SelectArgs& sel, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(topk_segments)");
-        attr_set = true;
-    }
+    RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024),
+                        "cudaFuncSetAttribute(topk_segments)");
     const size_t smem = (size_t)sel.cache_floats * sizeof(float) + 16;
     cudaError_t e = launch_pdl(kPdlSelect, topk_segments_kernel, dim3(B), dim3(kScoreThreads), smem, s, row_off, scores, sel);
     if (e != cudaSuccess) return cuda_fail(e, "topk_segments_kernel");

@@ -396,13 +396,9 @@ static int make_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows,
 
 template <int NCTA>
 static int launch_n(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
-    static bool attr_set = false;
     const size_t smem = (size_t)Cfg<NCTA>::kStages * Cfg<NCTA>::kStageBytes + 1024 + 16 * 256 * 4;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_score_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_score_kernel)");
-        attr_set = true;
-    }
+    RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(tc_score_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(tc_score_kernel)");
     int grid = sm_count() / NCTA * NCTA;
     const int items = ((p.n_a + NCTA - 1) / NCTA) * p.n_groups;
     if (grid > items * NCTA) grid = items * NCTA;

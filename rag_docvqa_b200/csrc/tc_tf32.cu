@@ -259,13 +259,9 @@ extern "C" int rdv_maxsim_tf32x3_tc(const float* d_q_hi, const float* d_q_lo, co
     if (!rc) rc = tc::make_map_bytes(&mbh, d_p_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d, Lp, n, tc3::BN);
     if (!rc) rc = tc::make_map_bytes(&mbl, d_p_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d, Lp, n, tc3::BN);
     if (rc) return rc;
-    static bool attr_set = false;
     const size_t smem = (size_t)tc3::kStages * tc3::kStageBytes + 1024;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc3::maxsim_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(maxsim_tf32x3_kernel)");
-        attr_set = true;
-    }
+    RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(tc3::maxsim_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(maxsim_tf32x3_kernel)");
     int grid = sm_count();
     const int items = p.n_a * p.n_strips;
     if (grid > items) grid = items;

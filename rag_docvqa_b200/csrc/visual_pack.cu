@@ -389,13 +389,8 @@ extern "C" int rdv_visual_pack(const rdv_pagestore* ps, const rdv_visual_args* a
     P.ps = *ps;
     P.a = *args;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(vp::visual_resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             vp::kRowBudget + vp::kCoeffBudget);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(visual_resize_h)");
-        attr_set = true;
-    }
+    RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(vp::visual_resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             vp::kRowBudget + vp::kCoeffBudget), "cudaFuncSetAttribute(visual_resize_h)");
     vp::visual_layout_kernel<<<ps->B, vp::kThreads, 0, s>>>(P);
     RDV_LAUNCH_CHECK("visual_layout_kernel");
     // the grid covers the row capacity at the smallest rows-per-block any document can have; blocks past a document's
