@@ -193,7 +193,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_text(w)},
+        "config": text_config(w),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -225,7 +225,7 @@ def run_reference_corpus(args):
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C5: %d chunks x %d-d, %d questions, top-k=%d" % (N, d, Qn, k)},
+        "config": corpus_config(N, d, Qn, k),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": "oracle corpus_scores + torch.topk on a 1/64 row slice (%d rows) per step, time x64" % n_cpu},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -252,7 +252,7 @@ def run_reference_visual(args):
         "impl": "reference", "metric": METRIC, "value": 1.0 / dt, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4: questions x %d strips x (%d x %d) tokens, MaxSim late interaction" % (strips, L, d)},
+        "config": visual_config(args.visual_docs, strips, L, d, 5),
         "cpu_baseline": {"value": 1.0 / dt, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": "oracle late_interaction on %d of %d strips of one question per step, time x%d" % (n_cpu, strips, strips // n_cpu)},
         "e2e": {"value": 1.0 / dt, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -262,6 +262,43 @@ def run_reference_visual(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class Ctx:
+    """One process per GPU: device, barrier, max / gather over ranks."""
+
+    def __init__(self):
+        self.rank, self.world, self.local = dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_ranks(self, x):
+        """[x of rank 0, x of rank 1, ...] on every rank."""
+        if self.dist is None:
+            return [float(x)]
+        t = torch.tensor([float(x)], device=self.dev, dtype=torch.float64)
+        out = torch.empty(self.world, device=self.dev, dtype=torch.float64)
+        self.dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.tolist()]
+
+    def maxr(self, x):
+        return max(self.all_ranks(x))
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
 def timed_loop(fn, steps, barrier):
     """`steps` calls of fn(i) between two CUDA events on the current stream; returns ms total."""
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -272,6 +309,219 @@ def timed_loop(fn, steps, barrier):
     ev1.record()
     barrier()
     return ev0.elapsed_time(ev1)
+
+
+def rotation(step_bytes, lanes):
+    """Distinct resident batches the steps rotate over: by the time a batch is read again at least 2 x L2 bytes of other
+    batches have streamed through (plus the batches in flight in the other lanes); a multiple of `lanes` so that a
+    batch's buffers are only ever touched by one lane."""
+    R = int(np.ceil(2.0 * L2_BYTES / max(1, step_bytes))) + 1
+    if lanes > 1:
+        R += lanes
+        R = (R + lanes - 1) // lanes * lanes
+    return max(2, R)
+
+
+def capture(dev, make_fn, n, lanes=1):
+    """A CUDA graph of n steps: step i is make_fn(stream)(i), steps alternate over `lanes` captured streams."""
+    g = torch.cuda.CUDAGraph()
+    main = torch.cuda.Stream(dev)
+    extra = [torch.cuda.Stream(dev) for _ in range(lanes - 1)]
+    fns = [make_fn(st.cuda_stream) for st in [main] + extra]
+    main.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.graph(g, stream=main):
+        for st in extra:
+            st.wait_stream(main)
+        for i in range(n):
+            fns[i % lanes](i)
+        for st in extra:
+            main.wait_stream(st)
+    return g
+
+
+def timed_replays(ctx, g, steps_in_graph, min_ms, min_reps):
+    """The timed region: `reps` replays of a captured graph of `steps_in_graph` steps, one CUDA event between replays
+    (on the launching stream), barrier + synchronize on both sides.  reps is the same on every rank and large enough
+    for the region to last >= min_ms.  Returns per-step statistics in ms."""
+    for _ in range(3):
+        g.replay()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    one = max(e0.elapsed_time(e1) / 3, 1e-3)
+    reps = int(min(4000, max(min_reps, np.ceil(min_ms / one))))
+    reps = int(ctx.maxr(reps))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ctx.barrier()
+    ev[0].record()
+    for i in range(reps):
+        g.replay()
+        ev[i + 1].record()
+    ctx.barrier()
+    per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]) / steps_in_graph
+    return {"median": float(np.median(per)), "mean": float(per.mean()), "min": float(per.min()),
+            "p90": float(np.percentile(per, 90)), "replays": reps, "region_ms": float(ev[0].elapsed_time(ev[reps]))}
+
+
+def text_leg(ctx, args, wl, lanes, compact=False):
+    """Per-document retrieval on resident inputs (C1 / C2 / C3): returns (result dict, live objects for the e2e leg).
+    A step = the retrieval of ONE batch of B questions: with a pre-tokenised DocStore the ONE-launch kernel
+    (rdv_retrieve_vt5_f32: score + per-document top-k + gather into the generator tensors); without one (C3) the
+    product's score + top-k call (rdv_score_topk_f32, the algo rdv_score_plan picks)."""
+    from rag_docvqa_b200 import functional as F
+    from rag_docvqa_b200 import synth, _lib
+    from rag_docvqa_b200.docstore import DocStore
+    dev, rank = ctx.dev, ctx.rank
+    w = synth.WORKLOADS[wl]
+    hbm_peak, _, peak_kind = measured_peaks()
+    with_lists = wl != "C3"
+    # weak scaling: every rank gets documents of the SAME sizes (the seeded shape) with its own embedding values
+    base_seed = synth.SEED_BASE + w.config_id
+    rank_seed = base_seed + 100000 * rank
+    host_batch = synth.make_text_batch(wl, with_lists=with_lists, share_image_pool=24, seed=base_seed)
+    sizes = host_batch["sizes"]
+    step_bytes = score_bytes(sizes, w.dim, w.k)
+    R = rotation(step_bytes, lanes)
+    K = args.steps if not compact else max(1, min(args.steps, 8))
+    steps_in_graph = K * int(np.ceil(R / K)) if K < R else K          # every replay walks the whole rotation at least once
+    batches = [synth.make_text_batch(wl, device=dev, seed=base_seed, emb_seed=rank_seed + 1000 * (r + 1)) for r in range(R)]
+    tables = [F.build_doc_table(b["text_embeddings"], w.dim, dev, algo=args.algo) for b in batches]
+    outs = [dict(sims=torch.empty(t.total_rows, dtype=torch.float32, device=dev),
+                 idx=torch.empty((t.B, w.k), dtype=torch.int32, device=dev),
+                 val=torch.empty((t.B, w.k), dtype=torch.float32, device=dev),
+                 cnt=torch.empty((t.B,), dtype=torch.int32, device=dev)) for t in tables]
+    lib = _lib.lib
+    qs = [F._f32_contig_aligned(b["question_embeddings"]) for b in batches]
+    plans, store, prompts, docstore_build_s = None, None, None, None
+    if with_lists:
+        table_w = synth.make_tokens_for_words(host_batch["words_text_chunks"], seed=3)
+        t_store = time.perf_counter()
+        store = DocStore.from_lists(host_batch["words_text_chunks"], host_batch["words_box_chunks"],
+                                    host_batch["layout_labels_chunks"], host_batch["page_indices"],
+                                    lambda wd: table_w.get(wd, [2]), dev, images=host_batch["images"])
+        docstore_build_s = time.perf_counter() - t_store
+        prompts = prompts_for(w.docs)
+        plans = [store.prepare_gather(o["idx"], o["cnt"], prompts, max_len=512, sims=o["sims"], topk_val=o["val"],
+                                      max_rows=t.max_rows) for o, t in zip(outs, tables)]
+    # what the product's own calls launch (rdv_retrieve_plan); --one-launch forces the cluster kernels for a measurement
+    one_launch = bool(plans) and (plans[0].prefers_one_launch(tables[0]) or
+                                  (args.one_launch and plans[0].can_retrieve_in_one_launch(tables[0])))
+    topk_cluster = plans is None and (tables[0].use_cluster(w.k) or (args.one_launch and tables[0].cluster_fits(w.k)))
+    topk_algo = tables[0].algo
+    torch.cuda.synchronize()
+
+    def make_launchers(sp):
+        """step / score-only closures launching on stream `sp` through the C ABI."""
+        def score(i):
+            t, o = tables[i % R], outs[i % R]
+            rc = lib.rdv_score_f32(t.pointers()[0], t.total_tiles, t.tile_rows, t.algo, qs[i % R].data_ptr(), t.B,
+                                   t.d, o["sims"].data_ptr(), sp)
+            if rc:
+                _lib.check(rc)
+
+        if one_launch:
+            def step(i):
+                plans[i % R].launch_retrieve(tables[i % R], qs[i % R], outs[i % R]["sims"], sp)
+        elif plans is not None:
+            def step(i):
+                score(i)
+                plans[i % R].launch(sp)
+        elif topk_cluster:
+            def step(i):
+                t, o = tables[i % R], outs[i % R]
+                d_ctas, n_ctas, cl = t.cluster_pointers()
+                rc = lib.rdv_score_topk_cluster_f32(d_ctas, n_ctas, cl, qs[i % R].data_ptr(), t.B, t.d, w.k, t.max_rows,
+                                                    o["sims"].data_ptr(), o["idx"].data_ptr(), o["val"].data_ptr(),
+                                                    o["cnt"].data_ptr(), sp)
+                if rc:
+                    _lib.check(rc)
+        else:
+            def step(i):
+                t, o = tables[i % R], outs[i % R]
+                rc = lib.rdv_score_topk_f32(t.pointers()[0], t.total_tiles, t.tile_rows, t.algo, t.pointers()[1],
+                                            qs[i % R].data_ptr(), t.B, t.d, w.k, t.max_rows, o["sims"].data_ptr(),
+                                            o["idx"].data_ptr(), o["val"].data_ptr(), o["cnt"].data_ptr(), sp)
+                if rc:
+                    _lib.check(rc)
+        return step, score
+
+    launches_per_step = 1 if (one_launch or topk_cluster) else 2
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    launch_step, launch_score = make_launchers(stream)
+    warmup = max(3, args.warmup)
+    for i in range(max(warmup, R)):
+        launch_step(i)
+    torch.cuda.synchronize()
+
+    g_chain = capture(dev, lambda sp: make_launchers(sp)[0], steps_in_graph, 1)
+    g_lanes = capture(dev, lambda sp: make_launchers(sp)[0], steps_in_graph, lanes) if lanes >= 2 else None
+    g_score = capture(dev, lambda sp: make_launchers(sp)[1], steps_in_graph, 1) if launches_per_step == 2 else None
+    min_ms, min_reps = (args.min_ms, args.min_replays) if not compact else (args.min_ms / 2, 10)
+    with ClockSampler(ctx.local) as clocks:
+        st_lanes = timed_replays(ctx, g_lanes, steps_in_graph, min_ms, min_reps) if g_lanes is not None else None
+        st_chain = timed_replays(ctx, g_chain, steps_in_graph, min_ms, min_reps)
+        st_score = timed_replays(ctx, g_score, steps_in_graph, min_ms / 2, 10) if g_score is not None else None
+        ms_plain = timed_loop(launch_step, steps_in_graph, ctx.barrier) / steps_in_graph
+    headline = st_lanes if st_lanes is not None else st_chain
+    per_rank = ctx.all_ranks(headline["median"])
+    per_rank_chain = ctx.all_ranks(st_chain["median"])
+    ms_per_step = max(per_rank)
+    ms_chain = max(per_rank_chain)
+    qps = w.docs * ctx.world / (ms_per_step * 1e-3)
+
+    # algorithmic bytes of the gather half (SURVEY 8d): records read per hit / per emitted token + the packed tensors written
+    gather_bytes = 0
+    if plans is not None:
+        meta = plans[0].t["meta"].cpu().numpy()
+        emitted = int(np.minimum(meta[0], 512).sum())
+        gather_bytes = w.docs * w.k * 64 + emitted * 32 + w.docs * 512 * 48 + w.docs * w.k * (16 + 32 + 16)
+    if launches_per_step == 1:
+        kernel = ("retrieve_cluster_kernel<mode 2> (rdv_retrieve_vt5_f32: score + top-k + gather, a cluster per document)"
+                  if one_launch else "retrieve_cluster_kernel<mode 1> (rdv_score_topk_cluster_f32: score + top-k)")
+        kernel_bytes, kernel_ms = step_bytes + gather_bytes, ms_chain
+        how = ("the step IS this one kernel: launches back to back in one dependent chain (CUDA graph, programmatic "
+               "dependent launch), CUDA events around each replay, median over the replays, max over ranks")
+    else:
+        kernel = "score_tma_kernel" if topk_algo == _lib.SCORE_TMA else "score_ldg_kernel (rdv_score_f32)"
+        kernel_bytes, kernel_ms = step_bytes, ctx.maxr(st_score["median"])
+        how = ("the streaming kernel alone: launches back to back in one dependent chain (CUDA graph, programmatic dependent "
+               "launch), CUDA events around each replay, median over the replays, max over ranks")
+    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
+    res = {
+        "value": qps, "ms_per_step": ms_per_step, "steps_in_graph": steps_in_graph, "replays": headline["replays"],
+        "timed_region_ms": headline["region_ms"], "rotation_batches": R, "rotation_MB": R * step_bytes / 1e6,
+        "lanes": lanes if g_lanes is not None else 1, "launches_per_step": launches_per_step,
+        "gpu_launches": launches_per_step * steps_in_graph * headline["replays"],
+        "per_rank_ms_per_step": per_rank,
+        "one_chain": {"ms_per_step": ms_chain, "queries_per_s": w.docs * ctx.world / (ms_chain * 1e-3),
+                      "GBps": (step_bytes + gather_bytes) / (ms_chain * 1e-3) / 1e9,
+                      "frac_hbm": (step_bytes + gather_bytes) / (ms_chain * 1e-3) / 1e9 / hbm_peak,
+                      "per_rank_ms_per_step": per_rank_chain, "p90_ms": st_chain["p90"], "min_ms": st_chain["min"]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "peak_kind": peak_kind, "kernel": kernel, "algorithmic_bytes_per_launch": kernel_bytes,
+                     "ms_per_launch": kernel_ms, "how": how,
+                     "pipelined_frac": (step_bytes + gather_bytes) / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                     "traffic": None},
+        "stages": {"step_ms_graph_one_chain": ms_chain, "step_ms_graph_lanes": ms_per_step if g_lanes is not None else None,
+                   "step_ms_plain_stream_launches": ctx.maxr(ms_plain),
+                   "score_ms": ctx.maxr(st_score["median"]) if st_score is not None else None,
+                   "step_bytes": step_bytes, "gather_bytes": gather_bytes,
+                   "step_GBps": (step_bytes + gather_bytes) / (ms_per_step * 1e-3) / 1e9,
+                   "step_frac_hbm": (step_bytes + gather_bytes) / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
+        "clocks": clocks.summary(),
+    }
+    if ctx.rank == 0:
+        traffic = ncu_traffic(("retrieve" if one_launch else "score_topk" if launches_per_step == 1 else "score") + ":" + w.name)
+        if traffic:
+            res["roofline"]["traffic"] = traffic.get("dram_bytes_per_launch")
+            res["roofline"]["traffic_from"] = {k: traffic.get(k) for k in ("capture", "commit")}
+    live = dict(w=w, host_batch=host_batch, batches=batches, tables=tables, outs=outs, plans=plans, store=store,
+                prompts=prompts, sizes=sizes, step_bytes=step_bytes, docstore_build_s=docstore_build_s, R=R)
+    return res, live
 
 
 def stage_extras(dev, hbm_peak, steps):
@@ -351,403 +601,289 @@ def stage_extras(dev, hbm_peak, steps):
     return out
 
 
-def run_ours(args):
+def pool_leg(ctx, n_chunks, dim, hbm_peak):
+    """Masked mean pooling (a1) of the token outputs of one batch's chunks: the embedder's tail, feeding the step."""
     from rag_docvqa_b200 import functional as F
-    from rag_docvqa_b200 import synth, _lib
-    from rag_docvqa_b200.docstore import DocStore
+    from rag_docvqa_b200 import synth
+    embs, mask = synth.make_token_batch(n_chunks, dim, 7, device=ctx.dev, max_len=160)
+    valid = int(mask.sum().item())
+    n, L, d = embs.shape
+    by = valid * d * 4 + n * L * 8 + n * d * 4
+    for _ in range(3):
+        F.mean_pooling(embs, mask)
+    ms = timed_loop(lambda i: F.mean_pooling(embs, mask), 10, torch.cuda.synchronize) / 10
+    return {"kernel": "mean_pool_kernel", "shape": [n, L, d], "valid_tokens": valid, "ms": ms, "algorithmic_bytes": by,
+            "GBps": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / hbm_peak}
+
+
+def e2e_text(ctx, args, live, lazy):
+    """The drop-in Retriever.retrieve with HOST inputs: pinned host embeddings + the reference's nested lists + PIL pages in,
+    the 9-tuple out; H2D and D2H inside the timed region."""
+    from rag_docvqa_b200 import functional as F
     from rag_docvqa_b200.retriever import Retriever
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    w = synth.WORKLOADS[args.workload]
-    hbm_peak, _, peak_kind = measured_peaks()
-    warmup = max(3, args.warmup)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world > 1:
-            t = torch.tensor([x], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return x
-
-    # ---- setup (untimed): lists + DocStore once, R resident embedding batches -------------------------
-    with_lists = args.workload != "C3"
-    # weak scaling: every rank gets documents of the SAME sizes (the seeded C2 / C3 shape) with its own embedding
-    # values, so per-GPU work is fixed as N grows
-    base_seed = synth.SEED_BASE + w.config_id
-    rank_seed = base_seed + 100000 * rank
-    host_batch = synth.make_text_batch(args.workload, with_lists=with_lists, share_image_pool=24, seed=base_seed)
-    sizes = host_batch["sizes"]
-    step_bytes = score_bytes(sizes, w.dim, w.k)
-    R = max(2, min(16, int(np.ceil(2.2 * L2_BYTES / max(1, step_bytes)))))
-    while R % max(1, args.lanes):     # a batch's buffers are only ever touched by one lane
-        R += 1
-    batches = [synth.make_text_batch(args.workload, device=dev, seed=base_seed, emb_seed=rank_seed + 1000 * (r + 1))
-               for r in range(R)]
-    tables = [F.build_doc_table(b["text_embeddings"], w.dim, dev, algo=args.algo) for b in batches]
-    outs = [dict(sims=torch.empty(t.total_rows, dtype=torch.float32, device=dev),
-                 idx=torch.empty((t.B, w.k), dtype=torch.int32, device=dev),
-                 val=torch.empty((t.B, w.k), dtype=torch.float32, device=dev),
-                 cnt=torch.empty((t.B,), dtype=torch.int32, device=dev)) for t in tables]
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    # a step = streaming score kernel (rdv_score_f32) + ONE kernel per batch that selects each document's
-    # top-k and gathers it into the generator tensors (rdv_gather_vt5_inputs with fused selection).  Without a
-    # DocStore (C3) the second kernel is the stand-alone selection (rdv_topk_segments_f32).
-    lib = _lib.lib
-    stream_algo = [(_lib.SCORE_LDG if t.algo == _lib.SCORE_LDG_FUSED else t.algo) for t in tables]
-    score_args, select_args = [], []
-    for t, o, b, algo in zip(tables, outs, batches, stream_algo):
-        p_tiles, p_row = t.pointers()
-        score_args.append((p_tiles, t.total_tiles, t.tile_rows, algo, b["question_embeddings"].data_ptr(), t.B, t.d,
-                           o["sims"].data_ptr(), stream))
-        select_args.append((o["sims"].data_ptr(), p_row, t.B, w.k, t.max_rows, o["idx"].data_ptr(), o["val"].data_ptr(),
-                            o["cnt"].data_ptr(), stream))
-    plans = None
-    if with_lists:
-        table = synth.make_tokens_for_words(host_batch["words_text_chunks"], seed=3)
-        t_store = time.perf_counter()
-        store = DocStore.from_lists(host_batch["words_text_chunks"], host_batch["words_box_chunks"],
-                                    host_batch["layout_labels_chunks"], host_batch["page_indices"],
-                                    lambda wd: table.get(wd, [2]), dev, images=host_batch["images"])
-        docstore_build_s = time.perf_counter() - t_store
-        prompts = prompts_for(w.docs)
-        plans = [store.prepare_gather(o["idx"], o["cnt"], prompts, max_len=512, sims=o["sims"], topk_val=o["val"],
-                                      max_rows=t.max_rows) for o, t in zip(outs, tables)]
-    torch.cuda.synchronize()
-
-    def make_launchers(stream_ptr):
-        """(score, gather, step) closures launching on the given stream through the C ABI."""
-        s_args = [a[:-1] + (stream_ptr,) for a in score_args]
-        g_args = [a[:-1] + (stream_ptr,) for a in select_args]
-
-        def score(i):
-            rc = lib.rdv_score_f32(*s_args[i % R])
-            if rc:
-                _lib.check(rc)
-
-        def gather(i):
-            if plans is not None:
-                plans[i % R].launch(stream_ptr)
-            else:
-                rc = lib.rdv_topk_segments_f32(*g_args[i % R])
-                if rc:
-                    _lib.check(rc)
-
-        def step(i):
-            score(i)
-            gather(i)
-        return score, gather, step
-
-    launch_score, launch_gather, launch_step = make_launchers(stream)
-    launches_per_step = 2
-    for i in range(warmup):
-        launch_step(i)
-    torch.cuda.synchronize()
-
-    # The timed region is ONE CUDA-graph launch holding exactly `steps` steps (2 kernel nodes each), rotating over
-    # the R resident batches: the hot loop is launch-bound (a step is ~13 us of device time, ~8 us of host
-    # enqueue), so it is captured once and replayed.  `lanes` = 1: the steps form one dependent chain.
-    # `lanes` = L: successive (independent) batches rotate over L captured streams, so the latency-bound
-    # select+gather of one batch overlaps the HBM-bound score of the next, as a serving loop with L batches in
-    # flight would (measured on B200, C2: 13.0 us per step with 1 lane, 11.7 with 2, 8.1 with 3, 7.2 with 4, 5.1 with 8 --
-    # 32.5 MB per 5.1 us = 6.3 TB/s: the whole step at the HBM roofline).
-    def capture(fn, n, lanes=1):
-        g = torch.cuda.CUDAGraph()
-        main = torch.cuda.Stream(dev)
-        extra = [torch.cuda.Stream(dev) for _ in range(lanes - 1)]
-        fns = [fn(st.cuda_stream) for st in [main] + extra]
-        main.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.graph(g, stream=main):
-            for st in extra:
-                st.wait_stream(main)
-            for i in range(n):
-                fns[i % lanes](i)
-            for st in extra:
-                main.wait_stream(st)
-        return g
-
-    def timed_graph(g, reps):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        for _ in range(reps):
-            g.replay()
-        ev1.record()
-        barrier()
-        return ev0.elapsed_time(ev1)
-
-    g_seq = capture(lambda sp: make_launchers(sp)[2], args.steps, 1)
-    g_pipe = capture(lambda sp: make_launchers(sp)[2], args.steps, max(2, args.lanes))
-    g_score = capture(lambda sp: make_launchers(sp)[0], args.steps, 1)
-    g_gather = capture(lambda sp: make_launchers(sp)[1], args.steps, 1)
-    for g in (g_seq, g_pipe, g_score, g_gather):
-        g.replay()
-    torch.cuda.synchronize()
-
-    # ---- value: K steps, device resident --------------------------------------------------------------
-    with ClockSampler(local) as clocks:
-        ms_seq = timed_graph(g_seq, 1)
-        ms_pipe = timed_graph(g_pipe, 1)
-        # per-kernel timings over the same rotation (roofline = the dominant kernel alone)
-        ms_score = timed_graph(g_score, 1) / args.steps
-        ms_gather = timed_graph(g_gather, 1) / args.steps
-        ms_plain = timed_loop(launch_step, args.steps, barrier)          # the same steps as plain stream launches
-        ms_score_plain = timed_loop(launch_score, args.steps, barrier) / args.steps
-        t_end = time.perf_counter() + 0.6          # keep the GPU busy so the sampler sees clocks under load
-        while time.perf_counter() < t_end:
-            g_pipe.replay()
-            torch.cuda.synchronize()
-    ms_seq, ms_pipe, ms_plain = max_over_ranks(ms_seq), max_over_ranks(ms_pipe), max_over_ranks(ms_plain)
-    pipelined = args.lanes >= 2
-    ms_total = ms_pipe if pipelined else ms_seq
-    ms_per_step = ms_total / args.steps
-    qps = w.docs * world / (ms_per_step * 1e-3)
-    achieved = step_bytes / (ms_score * 1e-3) / 1e9
-
-    # ---- e2e: the drop-in Retriever.retrieve with HOST inputs ------------------------------------------
-    e2e = None
-    extras = {}
+    w, dev, host_batch, batches, sizes = live["w"], ctx.dev, live["host_batch"], live["batches"], live["sizes"]
     host_sets = [([e.cpu().pin_memory() for e in b["text_embeddings"]], b["question_embeddings"].cpu().pin_memory())
-                 for b in batches[:min(R, 4)]]
+                 for b in batches[:min(len(batches), 4)]]
     h2d = sum(e.numel() * 4 for e in host_sets[0][0]) + host_sets[0][1].numel() * 4
     cfg = {"compute_stats": False, "compute_stats_examples": False, "n_stats_examples": 0, "chunk_num": w.k,
            "device": str(dev)}
-    e2e_steps = max(5, min(args.steps, 40))
-    if args.skip_e2e:
-        e2e = {"value": None, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 0,
-               "api": "skipped (--skip-e2e: profiling run, keeps the kernel launch list to the device-resident steps)"}
-    elif with_lists:
+    if host_batch.get("words_text_chunks") is not None:
         lists = (host_batch["words_text_chunks"], host_batch["words_box_chunks"], host_batch["layout_labels_chunks"],
                  host_batch["images"], host_batch["page_indices"])
-        retr = Retriever({**cfg, "retrieval_lazy_patches": True})
+        retr = Retriever({**cfg, "retrieval_lazy_patches": bool(lazy)})
 
-        def e2e_step(i):
+        def step(i):
             emb_h, q_h = host_sets[i % len(host_sets)]
             return retr.retrieve(emb_h, q_h, *lists)
-        for i in range(3):
-            e2e_step(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            out = e2e_step(i)
-        torch.cuda.synchronize()
-        e2e_dt = max_over_ranks(time.perf_counter() - t0)
         d2h = w.docs * (w.k + 1) * 4 + sum(sizes) * 4
-        e2e = {"value": w.docs * world * e2e_steps / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt / e2e_steps * 1e3,
-               "api": "rag_docvqa_b200.retriever.Retriever.retrieve (reference signature; pinned host embeddings, "
-                      "nested lists and PIL pages in; 9-tuple out; patches = deferred crops)"}
+        api = ("rag_docvqa_b200.retriever.Retriever.retrieve (reference signature; pinned host embeddings, nested lists and "
+               "PIL pages in; 9-tuple out; patches = %s)" % ("deferred crops" if lazy else "eager PIL crops, as the reference"))
+        n_steps = max(5, min(args.steps, 40)) if lazy else 3
     else:
-        def e2e_step(i):
+        def step(i):
             emb_h, q_h = host_sets[i % len(host_sets)]
             table_h = F.upload_doc_table(emb_h, w.dim, dev)
             res = F.score_topk_table(table_h, q_h.to(dev, non_blocking=True), w.k)
             return res.topk_idx.cpu(), res.topk_cnt.cpu()
-        for i in range(2):
-            e2e_step(i)
-        barrier()
-        e2e_steps = 5
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        e2e_dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": w.docs * world * e2e_steps / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": w.docs * (w.k + 1) * 4, "ms_per_step": e2e_dt / e2e_steps * 1e3,
-               "api": "rag_docvqa_b200.functional.upload_doc_table + score_topk_table (pinned host embeddings in, top-k out)"}
+        d2h = w.docs * (w.k + 1) * 4
+        api = "rag_docvqa_b200.functional.upload_doc_table + score_topk_table (pinned host embeddings in, top-k out)"
+        n_steps = 5
+    for i in range(3 if lazy else 1):
+        step(i)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        step(i)
+    torch.cuda.synchronize()
+    per_rank = ctx.all_ranks(time.perf_counter() - t0)
+    dt = max(per_rank)
+    return {"value": w.docs * ctx.world * n_steps / dt, "unit": "queries/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": dt / n_steps * 1e3, "steps": n_steps,
+            "per_rank_ms_per_step": [t / n_steps * 1e3 for t in per_rank], "api": api}
 
+
+CONFIG_L2 = "inputs larger than L2: every step streams a different resident batch (rotation > 2 x 126 MB)"
+CONFIG_PAR = "documents sharded across ranks, no data-path collective"
+
+
+def text_config(w):
+    """The `config` object of a per-document workload -- identical in both arms (the driver compares them)."""
+    return {"workload": workload_text(w), "l2": CONFIG_L2, "parallelism": CONFIG_PAR}
+
+
+def corpus_config(N, d, Qn, k):
+    return {"workload": "C5: %d chunks x %d-d bf16 row-sharded over the GPUs, %d questions, top-k=%d" % (N, d, Qn, k),
+            "l2": "inputs larger than L2 (15.4 GB of corpus rows)",
+            "parallelism": "corpus rows sharded across ranks, one NCCL all-gather of (Q, k) candidates per step"}
+
+
+def run_ours(args):
+    from rag_docvqa_b200 import synth
+    ctx = Ctx()
+    rank, world = ctx.rank, ctx.world
+    w = synth.WORKLOADS[args.workload]
+    hbm_peak, _, _ = measured_peaks()
+    res, live = text_leg(ctx, args, args.workload, args.lanes)
+    pipelined = res["lanes"] >= 2
+    e2e = None
+    if args.skip_e2e:
+        e2e = {"value": None, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "api": "skipped (--skip-e2e: profiling run, keeps the kernel launch list to the device-resident steps)"}
+    else:
+        e2e = e2e_text(ctx, args, live, lazy=True)
     line = {
-        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_text(w),
-                   "step": "streaming score kernel + %s, one batch of %d questions; the %d steps are one CUDA-graph "
-                           "launch, %s" % (
-                       "select+gather kernel (per-document top-k, packed VT5 inputs, max_source_length 512)"
-                       if plans is not None else "per-document top-k kernel", w.docs, args.steps,
-                       "successive independent batches rotate over %d captured streams (the latency-bound select+gather "
-                       "of one batch overlaps the HBM-bound score of the next ones)" % args.lanes if pipelined
-                       else "one dependent chain"),
-                   "l2": "inputs larger than L2: %d distinct resident batches rotated (%.0f MB in total)" % (
-                       R, R * step_bytes / 1e6),
-                   "parallelism": "documents sharded across ranks (dp%d), no data-path collective" % world},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "peak_kind": peak_kind,
-                     "traffic": ncu_traffic("%s:%s" % ("score_tma_kernel" if stream_algo[0] == 2 else "score_ldg_kernel", w.name))
-                     if rank == 0 else None,
-                     "kernel": "score_tma_kernel" if stream_algo[0] == 2 else "score_ldg_kernel", "algorithmic_bytes_per_launch": step_bytes,
-                     "ms_per_launch": ms_score},
+        "metric": METRIC, "value": res["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": text_config(w),
+        "timing": {"what": "a step = the retrieval of one batch of %d questions = %s; %d steps are captured into one CUDA "
+                           "graph and the timed region is %d replays of it (one CUDA event between replays, barrier + "
+                           "synchronize on both sides); ms_per_step = median over the replays, max over ranks; %s"
+                           % (w.docs,
+                              "ONE launch (score + per-document top-k + gather into the packed VT5 inputs, max_source_length 512)"
+                              if res["launches_per_step"] == 1 and live["plans"] is not None else
+                              "ONE launch (score + per-document top-k)" if res["launches_per_step"] == 1 else
+                              "streaming score kernel + select/gather kernel", res["steps_in_graph"], res["replays"],
+                              "successive independent batches rotate over %d captured streams (a serving loop with %d batches in "
+                              "flight); `one_chain` is the same steps as one dependent chain" % (res["lanes"], res["lanes"])
+                              if pipelined else "one dependent chain"),
+                   "steps_in_graph": res["steps_in_graph"], "replays": res["replays"], "timed_region_ms": res["timed_region_ms"],
+                   "rotation_batches": res["rotation_batches"], "rotation_MB": res["rotation_MB"], "lanes": res["lanes"],
+                   "per_rank_ms_per_step": res["per_rank_ms_per_step"]},
+        "one_chain": res["one_chain"],
+        "roofline": res["roofline"],
         "e2e": e2e,
-        "gpu_launches": args.steps * launches_per_step,
-        "clocks": clocks.summary(),
-        "stages": {"score_ms": ms_score, "select_gather_ms": ms_gather, "step_ms": ms_per_step,
-                   "step_ms_graph_one_chain": ms_seq / args.steps, "step_ms_graph_lanes": ms_pipe / args.steps,
-                   "step_ms_plain_stream_launches": ms_plain / args.steps, "score_ms_plain_stream_launches": ms_score_plain,
-                   "step_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9, "step_frac_hbm": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
+        "gpu_launches": res["gpu_launches"],
+        "clocks": res["clocks"],
+        "stages": res["stages"],
     }
-
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
-        cpu_batch = dict(host_batch)
-        cpu_batch["text_embeddings"] = [e.cpu() for e in batches[0]["text_embeddings"]]
-        cpu_batch["question_embeddings"] = batches[0]["question_embeddings"].cpu()
+        cpu_batch = dict(live["host_batch"])
+        cpu_batch["text_embeddings"] = [e.cpu() for e in live["batches"][0]["text_embeddings"]]
+        cpu_batch["question_embeddings"] = live["batches"][0]["question_embeddings"].cpu()
         st_best, st_reps = time_cpu(cpu_score_topk_fn(cpu_batch, w.k), min(3.0, args.cpu_seconds))
-        if with_lists:
+        if live["plans"] is not None:
             best, reps = time_cpu(cpu_retrieve_fn(cpu_batch, w.k, crop=False), args.cpu_seconds)
             line["cpu_baseline"] = {
                 "value": w.docs / best, "unit": "queries/s", "cores": threads, "kind": "port",
                 "sample": "oracle retrieve() (score + torch.topk + Python list gather + crop rectangles, no PIL pixel "
                           "copy) on one full %s batch, best of %d reps" % (w.name, reps),
                 "score_topk_only_queries_per_s": w.docs / st_best}
-            if not args.no_extras:
-                # the same comparison WITH the eager PIL pixel copy of the reference, both arms
-                eager = Retriever(cfg)
-                t0 = time.perf_counter()
-                for i in range(2):
-                    eager.retrieve(host_sets[i % len(host_sets)][0], host_sets[i % len(host_sets)][1], *lists)
-                torch.cuda.synchronize()
-                extras["e2e_eager_pil_crops_queries_per_s"] = w.docs * 2 / (time.perf_counter() - t0)
-                best_c, _ = time_cpu(cpu_retrieve_fn(cpu_batch, w.k, crop=True), 2.0, min_reps=1)
-                extras["cpu_eager_pil_crops_queries_per_s"] = w.docs / best_c
-                # the reference's own situation: the embedder left the embeddings on the GPU (src/RAGVT5.py:230-252)
-                dev_emb, dev_q = batches[0]["text_embeddings"], batches[0]["question_embeddings"]
-                retr.retrieve(dev_emb, dev_q, *lists)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for i in range(e2e_steps):
-                    retr.retrieve(dev_emb, dev_q, *lists)
-                torch.cuda.synchronize()
-                extras["retrieve_device_embeddings_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
-                # B200-native API: host embeddings in, packed generator tensors on the device out
-                def packed_step(i):
-                    emb_h, q_h = host_sets[i % len(host_sets)]
-                    packed, _ = retr.retrieve_packed(emb_h, q_h, store, prompts)
-                    return packed
-                packed_step(0)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for i in range(e2e_steps):
-                    packed_step(i)
-                torch.cuda.synchronize()
-                extras["e2e_packed_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
-                # the packed path needs the documents pre-tokenised (DocStore): a per-DOCUMENT cost paid at ingest, not per
-                # question -- it walks every word of every chunk on the host
-                extras["docstore_build_s_per_batch_of_documents"] = docstore_build_s
-                extras["docstore_words"] = store.n_words
-                # ... and with the visual input as well: crops of the hits grid-packed and resized to 224 x 224 on the device
-                from rag_docvqa_b200.pagestore import PageStore
-                pstore = PageStore.from_images(host_batch["images"], dev)
-
-                def packed_visual_step(i):
-                    emb_h, q_h = host_sets[i % len(host_sets)]
-                    return retr.retrieve_packed(emb_h, q_h, store, prompts, pages=pstore)
-                packed_visual_step(0)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for i in range(e2e_steps):
-                    packed_visual_step(i)
-                torch.cuda.synchronize()
-                extras["e2e_packed_with_visual_input_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
-                # the visual pack kernels alone (hits resident): crop + grid pack + Pillow-exact bicubic resize + normalise
-                pk, rs = retr.retrieve_packed(batches[0]["text_embeddings"], batches[0]["question_embeddings"], store, prompts)
-                vplan = pstore.prepare_pack(pk.hit_page, pk.hit_rect, rs.topk_cnt)
-                for _ in range(3):
-                    vplan.launch()
-                ms_v = timed_loop(lambda i: vplan.launch(), 20, torch.cuda.synchronize) / 20
-                area = int(((pk.hit_rect[..., 2] - pk.hit_rect[..., 0]).clamp(min=0) * (pk.hit_rect[..., 3] - pk.hit_rect[..., 1]).clamp(min=0)).sum().item())
-                extras["visual_pack"] = {"ms": ms_v, "patch_pixels": area, "algorithmic_bytes": area * 3 + w.docs * 224 * 224 * 15,
-                                         "GBps": (area * 3 + w.docs * 224 * 224 * 15) / ms_v / 1e6,
-                                         "cpu_reference_ms": None,
-                                         "what": "64 documents x 5 crops -> grid canvas -> 224 x 224 bicubic (Pillow-exact) -> fp32 pixel_values"}
-                # the same on the host, as the reference does it (PIL crop + concatenate grid + PIL resize), one thread
-                from oracle import ref_restated as R_
-                hr, hp, hc = pk.hit_rect.cpu().numpy(), pk.hit_page.cpu().numpy(), rs.topk_cnt.cpu().numpy()
-                from PIL import Image as _Image
-                t0 = time.perf_counter()
-                for b in range(min(w.docs, 16)):
-                    patches = [host_batch["images"][b][int(hp[b, j])].crop(tuple(int(v) for v in hr[b, j])) for j in range(int(hc[b]))]
-                    if not patches:
-                        continue
-                    gw, gh, pos = R_.grid_layout([p_.size for p_ in patches])
-                    canvas = _Image.new("RGB", (gw, gh))
-                    for p_, xy in zip(patches, pos):
-                        canvas.paste(p_, xy)
-                    canvas.resize((224, 224), resample=_Image.Resampling.BICUBIC)
-                extras["visual_pack"]["cpu_reference_ms"] = (time.perf_counter() - t0) * 1e3 * w.docs / min(w.docs, 16)
-                # what consumes the hits (SURVEY 8f rank 3): reranker index list + re-emission of the packed inputs in that
-                # order, and the page vote, all on the device (the cross-encoder is a model: random scores stand in for it)
-                from rag_docvqa_b200 import postproc as _pp
-                pk, rs, gplan = retr.retrieve_packed(batches[0]["text_embeddings"], batches[0]["question_embeddings"], store,
-                                                     prompts, return_plan=True)
-                ce_scores = torch.rand((w.docs, w.k), device=dev)
-                row_off_d = torch.from_numpy(np.concatenate([[0], np.cumsum(rs.sizes)]).astype(np.int64)).to(dev)
-
-                def rerank_step(i):
-                    order, kept, _ = _pp.rerank_order(ce_scores, rs.topk_cnt, 0.4, 5, 1)
-                    gplan.set_emit_order(order, kept)
-                    gplan.launch()
-                for _ in range(3):
-                    rerank_step(0)
-                extras["rerank_packed_ms"] = timed_loop(rerank_step, 20, torch.cuda.synchronize) / 20
-                for _ in range(3):
-                    _pp.page_vote(pk.hit_page, rs.topk_cnt, rs.sims, row_off_d, True)
-                extras["page_vote_weighted_ms"] = timed_loop(
-                    lambda i: _pp.page_vote(pk.hit_page, rs.topk_cnt, rs.sims, row_off_d, True), 20, torch.cuda.synchronize) / 20
-                # what feeds the path (SURVEY 8f rank 4): Chunker.get_chunks with layout boxes, word x box containment on
-                # the device, against the oracle's Python loops (16 documents)
-                from rag_docvqa_b200.chunker import Chunker as _Chunker
-                cw, cb, ci = synth.make_chunker_batch(77, docs=16, max_pages=20, max_words=700, max_layouts=30, degenerate=False)
-                chunker = _Chunker({**cfg, "page_retrieval": "concat"})
-                chunker.get_chunks(cw[:2], cb[:2], ci[:2], question_id=[0, 1])
-                t0 = time.perf_counter()
-                got_chunks = chunker.get_chunks(cw, cb, ci, question_id=list(range(16)))
-                t_gpu = time.perf_counter() - t0
-                t0 = time.perf_counter()
-                want_chunks, _ = R_.get_chunks(cw, cb, ci)
-                t_cpu = time.perf_counter() - t0
-                extras["chunker_get_chunks"] = {
-                    "documents": 16, "pages": sum(len(d) for d in cw), "words": sum(len(p) for d in cw for p in d),
-                    "word_x_layout_box_pairs": sum(len(p) * len(g["boxes"]) for d, gi in zip(cw, ci) for p, g in zip(d, gi)),
-                    "s": t_gpu, "cpu_oracle_s": t_cpu, "identical": got_chunks[0] == want_chunks[0] and got_chunks[2] == want_chunks[2]}
         else:
             line["cpu_baseline"] = {"value": w.docs / st_best, "unit": "queries/s", "cores": threads, "kind": "port",
                                     "sample": "oracle score+topk on one full %s batch, best of %d reps" % (w.name, st_reps)}
-        if not args.no_extras:
-            del batches, tables, outs
-            torch.cuda.empty_cache()
-            extras.update(stage_extras(dev, hbm_peak, 20))
+    if live["plans"] is not None and not args.skip_e2e and args.workload == "C2":
+        # the reference's own output format: eager PIL crops in both arms (the crop is a host memcpy either way)
+        eager = e2e_text(ctx, args, live, lazy=False)
+        line["e2e_eager_pil_crops"] = {"value": eager["value"], "unit": "queries/s", "ms_per_step": eager["ms_per_step"]}
+        if rank == 0 and world == 1:
+            best_c, _ = time_cpu(cpu_retrieve_fn(cpu_batch, w.k, crop=True), 2.0, min_reps=1)
+            line["e2e_eager_pil_crops"]["cpu_queries_per_s"] = w.docs / best_c
+    extras = {}
+    if args.extras and rank == 0 and world == 1 and live["plans"] is not None:
+        extras.update(text_extras(ctx, args, live, cpu_batch))
+    n_chunks = int(sum(live["sizes"]))
+    step_bytes, gather_bytes = res["stages"]["step_bytes"], res["stages"]["gather_bytes"]
+    del live, res
+    torch.cuda.empty_cache()
+    if not args.skip_e2e:
+        # pooling (a1) at this batch's shape: with it the path is pool + score + top-k + gather (north_star's target)
+        pool = pool_leg(ctx, n_chunks if args.workload != "C3" else 65536, w.dim, hbm_peak)
+        tot_ms = pool["ms"] + line["one_chain"]["ms_per_step"]
+        tot_by = pool["algorithmic_bytes"] + step_bytes + gather_bytes
+        if args.workload != "C3":
+            pool["pool_score_topk_gather"] = {"ms": tot_ms, "GBps": tot_by / tot_ms / 1e6, "frac_hbm": tot_by / tot_ms / 1e6 / hbm_peak,
+                                              "what": "pooling of the batch's %d chunks followed by one step, one dependent chain" % n_chunks}
+        line["pool"] = pool
+    if args.extras and rank == 0 and world == 1:
+        extras.update(stage_extras(ctx.dev, hbm_peak, 20))
+    if extras:
         line["extras"] = extras
+    # ---- the other north_star configs, compact, as the LAST keys of the line -------------------------------------
+    if args.workload == "C2" and not args.skip_e2e and not args.no_legs:
+        c3, live3 = text_leg(ctx, args, "C3", 1, compact=True)
+        line["c3"] = {"workload": workload_text(synth.WORKLOADS["C3"]), "queries_per_s": c3["value"], "ms_per_step": c3["ms_per_step"],
+                      "kernel": c3["roofline"]["kernel"], "GBps": c3["roofline"]["achieved"], "frac_hbm": c3["roofline"]["frac"],
+                      "step_frac_hbm": c3["one_chain"]["frac_hbm"], "launches_per_step": c3["launches_per_step"],
+                      "replays": c3["replays"], "timed_region_ms": c3["timed_region_ms"],
+                      "per_rank_ms_per_step": c3["per_rank_ms_per_step"], "scaling": "weak"}
+        del c3, live3
+        torch.cuda.empty_cache()
+        c5 = corpus_leg(ctx, args, compact=True)
+        line["corpus_c5"] = c5
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
+
+
+def text_extras(ctx, args, live, cpu_batch):
+    """Numbers for the widening rows on the C2 batch; rank 0, N = 1, --extras only."""
+    from rag_docvqa_b200.retriever import Retriever
+    w, dev, host_batch, batches, store, prompts = live["w"], ctx.dev, live["host_batch"], live["batches"], live["store"], live["prompts"]
+    extras = {}
+    lists = (host_batch["words_text_chunks"], host_batch["words_box_chunks"], host_batch["layout_labels_chunks"],
+             host_batch["images"], host_batch["page_indices"])
+    cfg = {"compute_stats": False, "compute_stats_examples": False, "n_stats_examples": 0, "chunk_num": w.k, "device": str(dev)}
+    retr = Retriever({**cfg, "retrieval_lazy_patches": True})
+    host_sets = [([e.cpu().pin_memory() for e in b["text_embeddings"]], b["question_embeddings"].cpu().pin_memory())
+                 for b in batches[:2]]
+    e2e_steps = 20
+    # the reference's own situation: the embedder left the embeddings on the GPU (src/RAGVT5.py:230-252)
+    dev_emb, dev_q = batches[0]["text_embeddings"], batches[0]["question_embeddings"]
+    retr.retrieve(dev_emb, dev_q, *lists)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        retr.retrieve(dev_emb, dev_q, *lists)
+    torch.cuda.synchronize()
+    extras["retrieve_device_embeddings_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
+
+    # B200-native API: host embeddings in, packed generator tensors on the device out
+    def packed_step(i):
+        emb_h, q_h = host_sets[i % len(host_sets)]
+        packed, _ = retr.retrieve_packed(emb_h, q_h, store, prompts)
+        return packed
+    packed_step(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        packed_step(i)
+    torch.cuda.synchronize()
+    extras["e2e_packed_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
+    extras["docstore_build_s_per_batch_of_documents"] = live["docstore_build_s"]
+    extras["docstore_words"] = store.n_words
+    from rag_docvqa_b200.pagestore import PageStore
+    pstore = PageStore.from_images(host_batch["images"], dev)
+
+    def packed_visual_step(i):
+        emb_h, q_h = host_sets[i % len(host_sets)]
+        return retr.retrieve_packed(emb_h, q_h, store, prompts, pages=pstore)
+    packed_visual_step(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        packed_visual_step(i)
+    torch.cuda.synchronize()
+    extras["e2e_packed_with_visual_input_queries_per_s"] = w.docs * e2e_steps / (time.perf_counter() - t0)
+    pk, rs = retr.retrieve_packed(batches[0]["text_embeddings"], batches[0]["question_embeddings"], store, prompts)
+    vplan = pstore.prepare_pack(pk.hit_page, pk.hit_rect, rs.topk_cnt)
+    for _ in range(3):
+        vplan.launch()
+    ms_v = timed_loop(lambda i: vplan.launch(), 20, torch.cuda.synchronize) / 20
+    area = int(((pk.hit_rect[..., 2] - pk.hit_rect[..., 0]).clamp(min=0) * (pk.hit_rect[..., 3] - pk.hit_rect[..., 1]).clamp(min=0)).sum().item())
+    extras["visual_pack"] = {"ms": ms_v, "patch_pixels": area, "algorithmic_bytes": area * 3 + w.docs * 224 * 224 * 15,
+                             "GBps": (area * 3 + w.docs * 224 * 224 * 15) / ms_v / 1e6,
+                             "what": "64 documents x 5 crops -> grid canvas -> 224 x 224 bicubic (Pillow-exact) -> fp32 pixel_values"}
+    from rag_docvqa_b200 import postproc as _pp
+    pk, rs, gplan = retr.retrieve_packed(batches[0]["text_embeddings"], batches[0]["question_embeddings"], store,
+                                         prompts, return_plan=True)
+    ce_scores = torch.rand((w.docs, w.k), device=dev)
+    row_off_d = torch.from_numpy(np.concatenate([[0], np.cumsum(rs.sizes)]).astype(np.int64)).to(dev)
+
+    def rerank_step(i):
+        order, kept, _ = _pp.rerank_order(ce_scores, rs.topk_cnt, 0.4, 5, 1)
+        gplan.set_emit_order(order, kept)
+        gplan.launch()
+    for _ in range(3):
+        rerank_step(0)
+    extras["rerank_packed_ms"] = timed_loop(rerank_step, 20, torch.cuda.synchronize) / 20
+    for _ in range(3):
+        _pp.page_vote(pk.hit_page, rs.topk_cnt, rs.sims, row_off_d, True)
+    extras["page_vote_weighted_ms"] = timed_loop(
+        lambda i: _pp.page_vote(pk.hit_page, rs.topk_cnt, rs.sims, row_off_d, True), 20, torch.cuda.synchronize) / 20
+    from oracle import ref_restated as R_
+    from rag_docvqa_b200.chunker import Chunker as _Chunker
+    cw, cb, ci = synth_mod().make_chunker_batch(77, docs=16, max_pages=20, max_words=700, max_layouts=30, degenerate=False)
+    chunker = _Chunker({**cfg, "page_retrieval": "concat"})
+    chunker.get_chunks(cw[:2], cb[:2], ci[:2], question_id=[0, 1])
+    t0 = time.perf_counter()
+    got_chunks = chunker.get_chunks(cw, cb, ci, question_id=list(range(16)))
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want_chunks, _ = R_.get_chunks(cw, cb, ci)
+    t_cpu = time.perf_counter() - t0
+    extras["chunker_get_chunks"] = {
+        "documents": 16, "pages": sum(len(d) for d in cw), "words": sum(len(p) for d in cw for p in d),
+        "s": t_gpu, "cpu_oracle_s": t_cpu, "identical": got_chunks[0] == want_chunks[0] and got_chunks[2] == want_chunks[2]}
+    return extras
+
+
+def synth_mod():
+    from rag_docvqa_b200 import synth
+    return synth
 
 
 # ------------------------------------------------------------------------------------------------
 # corpus mode (BASELINE.json configs[4]): row-sharded bf16 corpus, tcgen05 scoring, NCCL all-gather + merge
 # ------------------------------------------------------------------------------------------------
-def run_corpus(args):
-    from rag_docvqa_b200 import functional as F
+def corpus_leg(ctx, args, compact=False):
+    """C5, strong scaling over the ranks: every rank owns N / world rows; a step answers Q questions against the whole
+    corpus: bf16 cast of the questions, tcgen05 score + fused top-k on the local shard, local merge straight into the NCCL
+    send buffer, all-gather of the (Q, k) candidates, final merge.  The step is captured once into a CUDA graph
+    (sharded.CorpusSearcher) and replayed."""
     from rag_docvqa_b200 import sharded
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
     _, tf_peak, peak_kind = measured_peaks()
     N, d, Qn, k = args.corpus_rows, 768, args.corpus_queries, 10
     lo, hi = sharded.shard_bounds(N, world, rank)
@@ -764,98 +900,99 @@ def run_corpus(args):
     q_host = (torch.randn(Qn, d, generator=gq) / d ** 0.5 + 0.5 * u.cpu()).pin_memory()
     q_dev = q_host.to(dev)
     torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world > 1:
-            t = torch.tensor([x], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return x
+    searcher = sharded.CorpusSearcher(shard, Qn, k, group=None, graph=not args.no_graph)
+    steps = max(1, min(args.steps, 20)) if not compact else max(1, min(args.steps, 10))
+    warmup = max(3, args.warmup) if not compact else 3
 
     def step(i):
-        return sharded.search(shard, q_dev, k)
-    warmup = max(3, args.warmup)
+        return searcher.search(q_dev)
     for i in range(warmup):
         step(i)
-    with ClockSampler(local) as clocks:
-        ms_total = timed_loop(step, args.steps, barrier)
-        ms_kernel = timed_loop(lambda i: shard.candidates(q_dev, k), args.steps, barrier) / args.steps
-        t_end = time.perf_counter() + 0.5
-        while time.perf_counter() < t_end:
-            step(0)
-            torch.cuda.synchronize()
-    ms_per_step = max_over_ranks(ms_total) / args.steps
-    ms_kernel = max_over_ranks(ms_kernel)
+    with ClockSampler(ctx.local) as clocks:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ctx.barrier()
+        ev[0].record()
+        for i in range(steps):
+            step(i)
+            ev[i + 1].record()
+        ctx.barrier()
+        per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
+        ms_kernel = timed_loop(lambda i: searcher.local_only(q_dev), steps, ctx.barrier) / steps
+        ms_exchange = timed_loop(lambda i: searcher.exchange_only(), max(steps, 20), ctx.barrier) / max(steps, 20) if world > 1 else 0.0
+    per_rank = ctx.all_ranks(float(np.median(per)))
+    ms_per_step = max(per_rank)
+    per_rank_kernel = ctx.all_ranks(ms_kernel)
+    ms_kernel = max(per_rank_kernel)
+    ms_exchange = ctx.maxr(ms_exchange)
     flops = 2.0 * Qn * (hi - lo) * d
 
     def e2e_step(i):
-        val, idx = sharded.search(shard, q_host.to(dev, non_blocking=True), k)
+        val, idx = searcher.search(q_host.to(dev, non_blocking=True))
         return val.cpu(), idx.cpu()
     for i in range(2):
         e2e_step(i)
-    barrier()
-    e2e_steps = max(5, min(args.steps, 20))
+    ctx.barrier()
+    e2e_steps = max(5, min(args.steps, 20)) if not compact else 5
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        out = e2e_step(i)
+        e2e_step(i)
     torch.cuda.synchronize()
-    e2e_dt = max_over_ranks(time.perf_counter() - t0)
-    line = {
-        "metric": METRIC, "value": Qn / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "C5: %d chunks x %d-d bf16 row-sharded over %d GPU(s), %d questions, top-k=%d" % (N, d, world, Qn, k),
-                   "step": "bf16 cast of the questions, tcgen05 score + fused top-k on the local shard, local merge, "
-                           "NCCL all-gather of (Q,k) candidates, final merge",
-                   "l2": "inputs larger than L2 (%.1f GB per rank)" % ((hi - lo) * d * 2 / 1e9),
-                   "parallelism": "corpus rows sharded across ranks (dp%d), one all-gather of %d bytes per rank" % (
-                       world, Qn * k * 12)},
+    e2e_dt = ctx.maxr(time.perf_counter() - t0)
+    out = {
+        "value": Qn / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "steps": steps, "per_rank_ms_per_step": per_rank,
         "roofline": {"bound": "tensor", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                      "frac": flops / (ms_kernel * 1e-3) / 1e12 / tf_peak, "traffic": None, "peak_kind": peak_kind + " (burst)",
-                     "kernel": "tc_score_kernel", "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_kernel},
+                     "kernel": "tc_score_kernel", "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_kernel,
+                     "how": "local half of the step alone (question cast + tc_score_kernel + local merge), CUDA events, max over ranks"},
+        "local_ms": ms_kernel, "per_rank_local_ms": per_rank_kernel, "exchange_ms": ms_exchange,
+        "tail_ms": ms_per_step - ms_kernel,
+        "nccl_bytes_per_rank_per_step": Qn * k * 12 if world > 1 else 0,
         "e2e": {"value": Qn * e2e_steps / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": Qn * d * 4,
                 "d2h_bytes_per_step": Qn * k * 12, "ms_per_step": e2e_dt / e2e_steps * 1e3,
-                "api": "rag_docvqa_b200.sharded.search (pinned host questions in, (Q,k) scores + global ids out)"},
-        "gpu_launches": args.steps * (5 if world == 1 else 6),
-        "clocks": clocks.summary(),
+                "api": "rag_docvqa_b200.sharded.CorpusSearcher.search (pinned host questions in, (Q,k) scores + global ids out)"},
+        "graph": searcher.graphed, "clocks": clocks.summary(),
+        "limiter": ("N=1: tc_score_kernel (tensor pipe / 1 kW power cap)" if world == 1 else
+                    "tc_score_kernel %.3f ms of the %.3f ms step; the rest (%.3f ms) is the question cast, the two merges and "
+                    "the all-gather (%.3f ms alone)" % (ms_kernel, ms_per_step, ms_per_step - ms_kernel, ms_exchange)),
     }
-    if world == 1:
-        # bf16 mode against the fp32 result (north_star): recall@k of the tensor-core path for the first 32 questions
-        # against fp32 cosine scores of the same stored rows (un-rounded fp32 questions, plain torch matmul in fp32,
-        # row chunks of 1 M).  Sharding does not change the hits (sharded == unsharded bit for bit, tests/test_tc_gpu.py),
-        # so it is measured on the single-GPU run only.  Verification code after the timed region; never a bench value.
-        try:
-            n_q = min(32, Qn)
-            allow = torch.backends.cuda.matmul.allow_tf32
-            torch.backends.cuda.matmul.allow_tf32 = False
-            _, got_idx = sharded.search(shard, q_dev, k)
-            qs = q_dev[:n_q].float()
-            qs = qs / qs.norm(dim=1, keepdim=True)
-            best_v = torch.full((n_q, k), float("-inf"), device=dev)
-            best_i = torch.zeros((n_q, k), dtype=torch.int64, device=dev)
-            for a in range(0, hi - lo, 1 << 20):
-                b = min(hi - lo, a + (1 << 20))
-                r = rows[a:b].float()
-                sc = (qs @ r.T) / r.norm(dim=1)
-                v, i = sc.topk(min(k, b - a), dim=1)
-                cat_v, cat_i = torch.cat([best_v, v], dim=1), torch.cat([best_i, i + a + lo], dim=1)
-                best_v, pos = cat_v.topk(k, dim=1)
-                best_i = torch.gather(cat_i, 1, pos)
-                del r, sc
-            torch.backends.cuda.matmul.allow_tf32 = allow
-            got = got_idx[:n_q].to(torch.int64).cpu().numpy()
-            ref_i = best_i.cpu().numpy()
-            hits = sum(len(set(got[j].tolist()) & set(ref_i[j].tolist())) for j in range(n_q))
-            line["recall_at_k_vs_fp32"] = {"value": hits / float(n_q * k), "questions": n_q, "k": k,
-                                           "reference": "fp32 cosine (torch, TF32 off) of the fp32 questions against the stored bf16 rows"}
-        except Exception as exc:                                   # reporting only: the bench line must still be printed
-            line["recall_at_k_vs_fp32"] = {"value": None, "error": "%s: %s" % (type(exc).__name__, exc)}
-    if rank == 0 and world == 1:
+    # bf16 mode against the fp32 result (north_star): recall@k of the tensor-core hits of 32 questions against fp32 cosine scores
+    # of the same stored rows (un-rounded fp32 questions, torch matmul in fp32, TF32 off), merged over the ranks' shards.
+    # Verification code after the timed region; never a bench value.
+    try:
+        n_q = min(32, Qn)
+        allow = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        _, got_idx = searcher.search(q_dev)
+        got = got_idx[:n_q].to(torch.int64).clone()
+        qs = q_dev[:n_q].float()
+        qs = qs / qs.norm(dim=1, keepdim=True)
+        best_v = torch.full((n_q, k), float("-inf"), device=dev)
+        best_i = torch.full((n_q, k), -1, dtype=torch.int64, device=dev)
+        for a in range(0, hi - lo, 1 << 20):
+            b = min(hi - lo, a + (1 << 20))
+            r = rows[a:b].float()
+            sc = (qs @ r.T) / r.norm(dim=1)
+            v, i = sc.topk(min(k, b - a), dim=1)
+            cat_v, cat_i = torch.cat([best_v, v], dim=1), torch.cat([best_i, i + a + lo], dim=1)
+            best_v, pos = cat_v.topk(k, dim=1)
+            best_i = torch.gather(cat_i, 1, pos)
+            del r, sc
+        torch.backends.cuda.matmul.allow_tf32 = allow
+        if world > 1:
+            all_v = torch.empty((world, n_q, k), device=dev)
+            all_i = torch.empty((world, n_q, k), dtype=torch.int64, device=dev)
+            ctx.dist.all_gather_into_tensor(all_v, best_v.contiguous())
+            ctx.dist.all_gather_into_tensor(all_i, best_i.contiguous())
+            cat_v, cat_i = all_v.permute(1, 0, 2).reshape(n_q, -1), all_i.permute(1, 0, 2).reshape(n_q, -1)
+            best_v, pos = cat_v.topk(k, dim=1)
+            best_i = torch.gather(cat_i, 1, pos)
+        got_np, ref_np = got.cpu().numpy(), best_i.cpu().numpy()
+        hits = sum(len(set(got_np[j].tolist()) & set(ref_np[j].tolist())) for j in range(n_q))
+        out["recall_at_k_vs_fp32"] = {"value": hits / float(n_q * k), "questions": n_q, "k": k,
+                                      "reference": "fp32 cosine (torch, TF32 off) of the fp32 questions against the stored bf16 rows"}
+    except Exception as exc:                                   # reporting only: the bench line must still be printed
+        out["recall_at_k_vs_fp32"] = {"value": None, "error": "%s: %s" % (type(exc).__name__, exc)}
+    if rank == 0 and world == 1 and not compact:
         # CPU: 1/64 row slice via torch.matmul + topk, scaled
         from oracle import ref_restated as R
         threads = os.cpu_count() or 1
@@ -867,13 +1004,37 @@ def run_corpus(args):
         def cpu_fn():
             return torch.topk(R.corpus_scores(e_cpu, q_cpu), k, dim=1)
         best, reps = time_cpu(cpu_fn, min(args.cpu_seconds, 10.0))
-        line["cpu_baseline"] = {"value": Qn / (best * 64), "unit": "queries/s", "cores": threads, "kind": "port",
-                                "sample": "oracle corpus_scores (torch matmul) + torch.topk on a 1/64 row slice (%d rows), "
-                                          "time scaled x64, best of %d reps" % (n_cpu, reps)}
-    if rank == 0:
+        out["cpu_baseline"] = {"value": Qn / (best * 64), "unit": "queries/s", "cores": threads, "kind": "port",
+                               "sample": "oracle corpus_scores (torch matmul) + torch.topk on a 1/64 row slice (%d rows), "
+                                         "time scaled x64, best of %d reps" % (n_cpu, reps)}
+    del searcher, shard, rows
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_corpus(args):
+    ctx = Ctx()
+    N, d, Qn, k = args.corpus_rows, 768, args.corpus_queries, 10
+    c5 = corpus_leg(ctx, args)
+    line = {
+        "metric": METRIC, "value": c5["value"], "unit": "queries/s", "n_gpus": ctx.world, "steps": c5["steps"],
+        "warmup": max(3, args.warmup), "ms_per_step": c5["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": corpus_config(N, d, Qn, k),
+        "timing": {"what": "a step = Q questions against the whole corpus: bf16 cast of the questions, tcgen05 score + fused top-k "
+                           "on the local shard, local merge into the send buffer, NCCL all-gather of (Q,k) candidates, final merge"
+                           + ("; captured once into a CUDA graph and replayed" if c5["graph"] else ""),
+                   "per_rank_ms_per_step": c5["per_rank_ms_per_step"]},
+        "roofline": c5["roofline"], "e2e": c5["e2e"],
+        "gpu_launches": c5["steps"] * (5 if ctx.world == 1 else 6), "clocks": c5["clocks"],
+        "stages": {k_: c5[k_] for k_ in ("local_ms", "per_rank_local_ms", "exchange_ms", "tail_ms", "nccl_bytes_per_rank_per_step",
+                                         "limiter", "graph")},
+        "recall_at_k_vs_fp32": c5.get("recall_at_k_vs_fp32"),
+    }
+    if "cpu_baseline" in c5:
+        line["cpu_baseline"] = c5["cpu_baseline"]
+    if ctx.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -969,11 +1130,9 @@ def run_visual(args):
         "metric": METRIC, "value": B * world / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32x3 (fp32 operands split exactly into two tf32 parts, fp32 accumulation)", "data": "synthetic",
-        "config": {"workload": "C4: %d questions x %d strips x (%d x %d) tokens, MaxSim late interaction, top-k=%d" % (B, strips, L, d, k),
-                   "step": "per document: F.normalize + tf32 hi/lo split of question and strips, tcgen05 kind::tf32 MaxSim, "
-                           "strip sums; then one segmented top-k kernel for the batch",
-                   "l2": "inputs larger than L2 (%.0f MB of strip tokens per document)" % (strips * L * d * 4 / 1e6),
-                   "parallelism": "documents sharded across ranks (dp%d), no data-path collective" % world},
+        "config": visual_config(B, strips, L, d, k),
+        "timing": {"what": "a step = per document: F.normalize + tf32 hi/lo split of question and strips, tcgen05 kind::tf32 "
+                           "MaxSim, strip sums; then one segmented top-k kernel for the batch"},
         "roofline": {"bound": "tensor", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": ceiling, "unit": "TFLOP/s",
                      "frac": flops / (ms_kernel * 1e-3) / 1e12 / ceiling, "traffic": None,
                      "peak_kind": peak_kind + " bf16 burst / 2 (tf32 rate) / 3 (products per fp32 product)",
@@ -989,7 +1148,7 @@ def run_visual(args):
         from oracle import ref_restated as R
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
-        if not args.no_extras:
+        if args.extras:
             # a12, Pix2Struct half: the 5 retrieved strips of every document -> (2048, 770) flattened patches on the device
             from rag_docvqa_b200.pagestore import PageStore
             rng = np.random.RandomState(7)
@@ -1017,6 +1176,12 @@ def run_visual(args):
         dist.destroy_process_group()
 
 
+def visual_config(B, strips, L, d, k):
+    return {"workload": "C4: %d questions x %d strips x (%d x %d) tokens, MaxSim late interaction, top-k=%d" % (B, strips, L, d, k),
+            "l2": "inputs larger than L2 (%.0f MB of strip tokens per document)" % (strips * L * d * 4 / 1e6),
+            "parallelism": CONFIG_PAR}
+
+
 def synth_seed(config_id):
     from rag_docvqa_b200 import synth
     return synth.SEED_BASE + config_id
@@ -1033,14 +1198,20 @@ def main():
     ap.add_argument("--corpus-rows", type=int, default=10_000_000)
     ap.add_argument("--corpus-queries", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="numbers for the widening rows (SURVEY 8f) and the other kernels; N=1 only")
+    ap.add_argument("--no-extras", action="store_true", help="(default; kept for old command lines)")
+    ap.add_argument("--no-legs", action="store_true", help="leave out the compact C3 / C5 legs of the default line")
+    ap.add_argument("--one-launch", action="store_true", help="force the one-launch cluster kernels (measurement; the plan prefers two launches)")
+    ap.add_argument("--no-graph", action="store_true", help="C5: eager launches instead of the captured step")
+    ap.add_argument("--min-ms", type=float, default=25.0, help="shortest timed region (ms) of the replayed graph")
+    ap.add_argument("--min-replays", type=int, default=50)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-input arm")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 LDG kernel, 2 TMA kernel")
     ap.add_argument("--lanes", type=int, default=8, choices=[1, 2, 3, 4, 8],
                     help="captured streams the steps alternate between (1 = one dependent chain)")
     args = ap.parse_args()
     if args.skip_e2e:
-        args.no_extras = True
+        args.extras = False
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "C5":

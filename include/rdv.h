@@ -72,12 +72,11 @@ RDV_API int rdv_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_mi
  *   d_topk_idx  (B,k)  out: int32 chunk index within the document, rank order, -1 padded
  *   d_topk_val  (B,k)  out: fp32 score of each hit (-inf padded)
  *   d_topk_cnt  [B]    out: k_b
- *   d_doc_done  [B]    int32 workspace, all zero on entry; the kernel leaves it all zero again
  *   tile_rows          the maximum rdv_tile_desc.rows used (from rdv_score_plan)
- *   algo               RDV_SCORE_TMA (d in {128,256,384,512,768,1024}), RDV_SCORE_LDG or RDV_SCORE_LDG_FUSED
- *                      (any d % 4 == 0); see the defines below.  TMA / LDG launch the streaming score kernel
- *                      followed by the per-document selection kernel (two launches, no device-scope fence on
- *                      the streaming path); LDG_FUSED does both in one launch.
+ *   algo               RDV_SCORE_TMA (d in {128,256,384,512,768,1024}) or RDV_SCORE_LDG (any d % 4 == 0); see the
+ *                      defines below.  Both launch the streaming score kernel followed by the per-document selection
+ *                      kernel (two launches, no device-scope fence on the streaming path).  Batches of short
+ *                      documents have a ONE-launch path: rdv_score_topk_cluster_f32 below.
  *   max_rows           max_b n_b (sizes the shared-memory cache of the selection pass)
  * Requirements: d % 4 == 0, 4 <= d <= 8192, 1 <= k <= 1024, B >= 0.
  * ------------------------------------------------------------------------------------------- */
@@ -93,7 +92,6 @@ typedef struct rdv_tile_desc {
 #define RDV_SCORE_AUTO 0
 #define RDV_SCORE_LDG 1        /* one block per tile, 128-bit loads; selection in a second kernel        */
 #define RDV_SCORE_TMA 2        /* persistent, bulk-async-copy (TMA) rings in shared memory; selection in a second kernel */
-#define RDV_SCORE_LDG_FUSED 3  /* LDG kernel with the selection fused in (last block per document): ONE launch */
 
 /* Picks the kernel (AUTO -> RDV_SCORE_LDG, the faster one on B200 at every measured size) and the tile
  * height for a batch of total_rows rows. */
@@ -102,7 +100,65 @@ RDV_API int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t*
 RDV_API int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
                                const int64_t* d_row_off, const float* d_q, int32_t B, int32_t d, int32_t k,
                                int32_t max_rows, float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
-                               int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream);
+                               int32_t* d_topk_cnt, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The same contract in ONE launch, for batches of short documents: row tiles packed into thread-block CLUSTERS.
+ *
+ * The unit of work is a slice of <= 32 rows per CTA (the streaming kernel's parallelism); the host packs the CTAs into
+ * clusters of `cluster` CTAs (rdv_cluster_plan) so that all CTAs of a document sit in ONE cluster (a document of n rows
+ * takes min(max(ceil(n / slice_rows), 1), cluster) CTAs and splits its rows evenly over them).  Every CTA reduces its
+ * slice to the k best (score, index) keys and pushes them into the shared memory of its document's first CTA
+ * (distributed shared memory); one cluster barrier later that CTA merges the candidates.  No global-memory handshake
+ * (fence / atomic / re-read of the scores) sits between scoring and selection; same values and ordering as
+ * rdv_score_topk_f32.
+ *   rdv_cta_desc          one 32-byte descriptor per CTA: src = the DOCUMENT's (doc_rows, d) fp32 matrix, sims_off = index
+ *                         of its first similarity in d_sims (= its first global chunk number), doc = its index, part /
+ *                         nparts = this CTA's place among the document's CTAs (CTA `part` takes rows part * per .. of the
+ *                         document, per = ceil(doc_rows / nparts)); nparts == 0 marks a padding CTA.  The CTAs of a document are consecutive within a cluster.
+ *   rdv_cluster_table_size   number of descriptors (a multiple of the cluster size) for a batch; -1 on bad input
+ *   rdv_build_cluster_table  fills HOST descriptors (best-fit decreasing packing); the caller uploads them
+ *   max_rows                 max_b n_b
+ * Requirements: k <= rdv_cluster_max_k() (32), max_rows <= rdv_cluster_max_rows(cluster), d % 4 == 0, fewer than 2^31
+ * rows; `cluster` the size the table was built for; outside that: RDV_E_LIMIT, run rdv_score_topk_f32.  rdv_retrieve_plan says
+ * whether this path is the faster one.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rdv_cta_desc {
+    const void* src;
+    int32_t sims_off;
+    int32_t doc_rows;
+    int32_t doc;
+    int16_t part;
+    int16_t nparts;
+    int32_t reserved[2];
+} rdv_cta_desc;
+
+/* The plan for a batch (no launch): `cluster` = 16 (non-portable cluster size) where the current device places 16 CTAs of
+ * the kernel variant such a batch runs in one GPC, else the portable 8; `slice_rows` = the most rows a CTA takes of a document
+ * of at most cluster CTAs (32, 40, ... 64): the smallest for which ALL clusters of the batch are resident at once (a second
+ * wave of clusters would start only when whole clusters retire); `n_ctas` = descriptors the table needs, 0 when the batch is
+ * outside the kernels' limits.  The occupancy calculator is asked once per device and variant; without a device: 8 / 32.
+ * RDV_CLUSTER_SIZE=8|16 and RDV_CLUSTER_SLICE=32..64 in the environment force the two (measurement knobs). */
+RDV_API int rdv_cluster_plan(const int64_t* rows, int32_t B, int32_t d, int32_t k, int32_t with_gather, int32_t* cluster,
+                             int32_t* slice_rows, int64_t* n_ctas);
+RDV_API int32_t rdv_cluster_max_rows(int32_t cluster);     /* 4 slices of 32 rows per CTA: 1024 (clusters of 8), 2048 (16) */
+RDV_API int32_t rdv_cluster_max_k(void);
+/* *use_cluster = 1 when the one-launch cluster kernels apply to the batch (limits above) AND are the measured better choice
+ * on B200.  As measured in round 2 they are not (C2, one dependent chain: the whole step 14.4-16.3 us against 13.3 us for two
+ * launches; score + top-k alone 10.3-10.7 us), so this answers 1 only for batches of at most 1 MB (one launch less in a call
+ * that is all fixed cost) unless RDV_CLUSTER=1 / 0 in the environment forces it; the kernels stay selectable and are covered by
+ * the parity tests. */
+RDV_API int rdv_retrieve_plan(int64_t total_rows, int32_t max_rows, int32_t B, int32_t d, int32_t k, int32_t* use_cluster);
+RDV_API int64_t rdv_cluster_table_size(const int64_t* rows, int32_t B, int32_t cluster, int32_t slice_rows);
+RDV_API int rdv_build_cluster_table(const void* const* d_docs, const int64_t* rows, int32_t B, int32_t d, int32_t cluster,
+                                    int32_t slice_rows, rdv_cta_desc* h_ctas, int64_t n_ctas);
+/* Diagnostics of the cluster kernels (never on in the product): while d_trace is non-NULL every CTA writes %globaltimer
+ * (ns) stamps to d_trace[cta * 8 + s]: s = 0 started, 1 rows streamed, 2 cluster complete, 3 candidates pushed, 4 (merging
+ * CTA) candidates here, 5 merged, 6 gathered.  The buffer holds 8 x n_ctas uint64; NULL switches it off. */
+RDV_API int rdv_debug_trace(void* d_trace);
+RDV_API int rdv_score_topk_cluster_f32(const rdv_cta_desc* d_ctas, int64_t n_ctas, int32_t cluster, const float* d_q, int32_t B,
+                                       int32_t d, int32_t k, int32_t max_rows, float* d_sims, int32_t* d_topk_idx,
+                                       float* d_topk_val, int32_t* d_topk_cnt, void* stream);
 
 /* Host-side staging helpers (no kernel is launched): the per-batch bookkeeping of the caller, in C.
  *   rdv_count_tiles      number of row tiles a ragged batch cuts into (sum of ceil(rows[b] / tile_rows)); -1 on bad input.
@@ -120,30 +176,33 @@ RDV_API int rdv_upload_docs_f32(const void* const* h_docs, const int64_t* rows, 
 /* Small host batches: the device round trip of Retriever.retrieve (src/_modules.py:2155-2180: _get_similarities
  * :1978-1997 + torch.topk :2015-2016) in ONE call, for batches whose fixed costs exceed their work (C1: 1 page x 30
  * chunks x 384-d = 46 KB; the reference runs this case on the CPU).
- *   upload blob  (pinned host h_blob, device twin d_blob):  row_off[B+1] i64 | pad | tiles[n_tiles] | questions (B,d) | rows
+ *   upload blob  (pinned host h_blob, device twin d_blob):  row_off[B+1] i64 | pad | tiles[n_tiles] | ctas[n_ctas] | questions (B,d) | rows
  *   result blob  (device d_out; the first read_bytes are copied to pinned h_out):  sims[total] | idx (B,k) | cnt[B] || val (B,k)
  * rdv_small_batch_layout   offsets and sizes of both blobs + the launch plan (pure host arithmetic).
  * rdv_small_batch_pack     fills h_blob: copies the B host matrices h_docs[b] (rows[b] x d fp32, contiguous) and the
  *                          questions h_q (B,d), and builds offsets + tile descriptors that point into d_blob (pure host code).
- * rdv_retrieve_small_f32   layout + pack + ONE cudaMemcpyAsync up + the fused score/top-k launch (RDV_SCORE_LDG_FUSED) + ONE
- *                          cudaMemcpyAsync back + cudaStreamSynchronize: on return h_out holds similarities, hits and counts
- *                          (same values and ordering as rdv_score_topk_f32).  Returns RDV_SMALL_GROW (> 0), with *lay filled
- *                          and nothing else touched, when a buffer is smaller than the layout needs.  d_doc_done as in
- *                          rdv_score_topk_f32.  This entry point synchronises the stream (it is the whole call). */
+ * rdv_retrieve_small_f32   layout + pack + ONE cudaMemcpyAsync up + ONE launch (rdv_score_topk_cluster_f32; two launches,
+ *                          rdv_score_topk_f32, outside the cluster kernel's limits) + ONE cudaMemcpyAsync back +
+ *                          cudaStreamSynchronize: on return h_out holds similarities, hits and counts (same values and
+ *                          ordering as rdv_score_topk_f32).  Returns RDV_SMALL_GROW (> 0), with *lay filled and nothing
+ *                          else touched, when a buffer is smaller than the layout needs.  This entry point synchronises
+ *                          the stream (it is the whole call). */
 typedef struct rdv_small_layout {
-    int32_t algo, tile_rows, n_tiles, max_rows;
-    int64_t total_rows;
-    int64_t o_tiles, o_q, o_emb, in_bytes;                  /* upload blob (row_off at 0) */
+    int32_t algo, tile_rows, n_tiles, max_rows;             /* algo: RDV_SCORE_LDG / _TMA, or RDV_SMALL_CLUSTER */
+    int64_t total_rows, n_ctas;                             /* n_ctas: cluster-kernel descriptors (0 when not taken) */
+    int64_t cluster, slice_rows;                            /* ... and the plan they were packed for (rdv_cluster_plan) */
+    int64_t o_tiles, o_ctas, o_q, o_emb, in_bytes;          /* upload blob (row_off at 0) */
     int64_t o_idx, o_cnt, read_bytes, o_val, out_bytes;     /* result blob (sims at 0)    */
 } rdv_small_layout;
 #define RDV_SMALL_GROW 1
+#define RDV_SMALL_CLUSTER 3    /* rdv_small_layout.algo: the batch takes the one-launch cluster kernel */
 RDV_API int rdv_small_batch_layout(const int64_t* rows, int32_t B, int32_t d, int32_t k, rdv_small_layout* lay);
 RDV_API int rdv_small_batch_pack(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, const float* h_q,
                                  const rdv_small_layout* lay, void* h_blob, const void* d_blob);
 RDV_API int rdv_retrieve_small_f32(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, int32_t k,
                                    const float* h_q, void* h_blob, void* d_blob, int64_t blob_bytes, void* d_out,
-                                   int64_t d_out_bytes, void* h_out, int64_t h_out_bytes, int32_t* d_doc_done,
-                                   rdv_small_layout* lay, void* stream);
+                                   int64_t d_out_bytes, void* h_out, int64_t h_out_bytes, rdv_small_layout* lay,
+                                   void* stream);
 
 /* Scores only (the streaming half of rdv_score_topk_f32): writes d_sims.  Used when the selection runs
  * elsewhere (rdv_topk_segments_f32, or inside rdv_gather_vt5_inputs).  algo: RDV_SCORE_LDG or RDV_SCORE_TMA. */
@@ -201,6 +260,13 @@ RDV_API int32_t rdv_maxsim_tiles_i(int32_t Lq);
  * ------------------------------------------------------------------------------------------- */
 RDV_API int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx, int32_t Q, int32_t m, int32_t k,
                            float* d_out_val, int64_t* d_out_idx, void* stream);
+/* The same merge over `parts` candidate lists that live `part_stride_*` ELEMENTS apart: list r of query q is
+ * d_cand_val[r * part_stride_val + q * k_in .. + k_in) (ids likewise).  With parts = world this reads the receive buffer
+ * of the all-gather exactly as NCCL fills it (rank-major), so no transpose copy sits between the collective and the
+ * merge; parts = 1 is rdv_topk_merge. */
+RDV_API int rdv_topk_merge_parts(const float* d_cand_val, const int64_t* d_cand_idx, int32_t Q, int32_t parts, int32_t k_in,
+                                 int64_t part_stride_val, int64_t part_stride_idx, int32_t k, float* d_out_val,
+                                 int64_t* d_out_idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Gather of the retrieved chunks into the VT5 generator's input tensors.
@@ -318,6 +384,22 @@ typedef struct rdv_gather_args {
 } rdv_gather_args;
 
 RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args* args, void* stream);
+
+/* The whole retrieval step of RAGVT5 in ONE launch: Retriever._get_similarities (src/_modules.py:1978-1997), the
+ * per-document torch.topk (:2015-2016), Retriever._get_top_k (:2014-2121) and the id / box / mask packing of
+ * VT5.prepare_inputs_for_vqa (src/VT5.py:141-185): rdv_score_topk_cluster_f32 whose merging CTA goes straight on to
+ * gather its document (rdv_gather_vt5_inputs' body).  Every CTA also stages the 32-byte chunk records / bounding boxes of
+ * its rows into shared memory while the rows stream (cp.async) and pushes those of its candidates along with the keys,
+ * so after the streaming phase the step has ONE dependent global load left (the winners' token records) before the
+ * packed tensors are written.
+ *   d_ctas / n_ctas / d_q / d / max_rows / d_sims   as rdv_score_topk_cluster_f32 (B = ds->B; document b's sims_off must
+ *                   equal ds->chunk_off[b]: the store and the embeddings describe the same chunks)
+ *   ds, args        as rdv_gather_vt5_inputs; args->topk_idx / topk_val / topk_cnt are WRITTEN, args->sims is ignored
+ * Requirements: the cluster kernel's limits, include_surroundings == 0, emit_order == NULL (otherwise RDV_E_LIMIT /
+ * RDV_E_INVALID: run rdv_score_f32 + rdv_gather_vt5_inputs). */
+RDV_API int rdv_retrieve_vt5_f32(const rdv_cta_desc* d_ctas, int64_t n_ctas, int32_t cluster, const float* d_q, int32_t d,
+                                 int32_t max_rows, float* d_sims, const rdv_docstore* ds, const rdv_gather_args* args,
+                                 void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------

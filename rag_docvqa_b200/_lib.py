@@ -10,10 +10,10 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Struc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
-SCORE_AUTO, SCORE_LDG, SCORE_TMA, SCORE_LDG_FUSED = 0, 1, 2, 3
+SCORE_AUTO, SCORE_LDG, SCORE_TMA = 0, 1, 2
 
 
 class RdvError(RuntimeError):
@@ -64,10 +64,11 @@ class P2SArgsStruct(Structure):
 class SmallLayoutStruct(Structure):
     """Mirror of `rdv_small_layout` (include/rdv.h)."""
     _fields_ = [(n, c_int32) for n in ("algo", "tile_rows", "n_tiles", "max_rows")] + [(n, c_int64) for n in (
-        "total_rows", "o_tiles", "o_q", "o_emb", "in_bytes", "o_idx", "o_cnt", "read_bytes", "o_val", "out_bytes")]
+        "total_rows", "n_ctas", "cluster", "slice_rows", "o_tiles", "o_ctas", "o_q", "o_emb", "in_bytes", "o_idx", "o_cnt", "read_bytes", "o_val", "out_bytes")]
 
 
 SMALL_GROW = 1
+SMALL_CLUSTER = 3          # rdv_small_layout.algo: the batch takes the one-launch cluster kernel
 S2_COMBINED, S2_SPATIAL, S2_SEMANTIC = 0, 1, 2
 
 # name -> (restype, argtypes); tests/test_abi.py checks this table against include/rdv.h
@@ -83,9 +84,21 @@ SIGNATURES = {
     "rdv_small_batch_layout": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "rdv_small_batch_pack": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_retrieve_small_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                         c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+                                         c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "rdv_score_topk_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
-                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_cluster_plan": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32),
+                                   POINTER(c_int64)]),
+    "rdv_cluster_max_rows": (c_int32, [c_int32]),
+    "rdv_cluster_max_k": (c_int32, []),
+    "rdv_retrieve_plan": (c_int32, [c_int64, c_int32, c_int32, c_int32, c_int32, POINTER(c_int32)]),
+    "rdv_debug_trace": (c_int32, [c_void_p]),
+    "rdv_cluster_table_size": (c_int64, [c_void_p, c_int32, c_int32, c_int32]),
+    "rdv_build_cluster_table": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64]),
+    "rdv_score_topk_cluster_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_retrieve_vt5_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p,
+                                       POINTER(DocStoreStruct), POINTER(GatherArgsStruct), c_void_p]),
     "rdv_score_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "rdv_topk_segments_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
@@ -96,6 +109,8 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_maxsim_tiles_i": (c_int32, [c_int32]),
     "rdv_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "rdv_topk_merge_parts": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_int32, c_void_p,
+                                       c_void_p, c_void_p]),
     "rdv_rows_to_bf16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "rdv_bf16_inv_norm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "rdv_corpus_groups": (c_int32, [c_int64, c_int32]),

@@ -52,7 +52,7 @@ int sm_count() {
 
 }  // namespace rdv
 
-extern "C" int rdv_abi_version(void) { return 15; }
+extern "C" int rdv_abi_version(void) { return 16; }
 
 extern "C" const char* rdv_last_error(void) { return rdv::g_error; }
 
@@ -153,16 +153,30 @@ extern "C" int rdv_small_batch_layout(const int64_t* rows, int32_t B, int32_t d,
     }
     RDV_REQUIRE(total * (int64_t)d * 4 <= (1ll << 30), RDV_E_LIMIT, "small_batch_layout: %lld rows is not a small batch",
                 (long long)total);
-    int32_t algo = 0, tile_rows = 0;
-    int rc = rdv_score_plan(total, d, RDV_SCORE_LDG_FUSED, &algo, &tile_rows);
+    int32_t algo = 0, tile_rows = 0, use_cluster = 0;
+    int rc = rdv_score_plan(total, d, RDV_SCORE_AUTO, &algo, &tile_rows);
     if (rc) return rc;
+    rc = rdv_retrieve_plan(total, (int32_t)mx, B, d, k, &use_cluster);
+    if (rc) return rc;
+    int32_t cluster = 0, slice_rows = 0;
+    int64_t n_ctas = 0;
+    if (use_cluster) {
+        rc = rdv_cluster_plan(rows, B, d, k, 0, &cluster, &slice_rows, &n_ctas);
+        if (rc) return rc;
+        if (n_ctas == 0) use_cluster = 0;
+    }
+    if (use_cluster) algo = RDV_SMALL_CLUSTER;
     const int64_t T = rdv_count_tiles(rows, B, tile_rows);
     RDV_REQUIRE(T >= 0 && T < (1ll << 31), RDV_E_LIMIT, "small_batch_layout: too many tiles");
     memset(lay, 0, sizeof(*lay));
     lay->algo = algo; lay->tile_rows = tile_rows; lay->n_tiles = (int32_t)T; lay->max_rows = (int32_t)mx;
     lay->total_rows = total;
     lay->o_tiles = round_up(8 * ((int64_t)B + 1), 32);
-    lay->o_q = lay->o_tiles + 32 * (T > 0 ? T : 1);
+    lay->cluster = use_cluster ? cluster : 0;
+    lay->slice_rows = use_cluster ? slice_rows : 0;
+    lay->n_ctas = use_cluster ? n_ctas : 0;
+    lay->o_ctas = lay->o_tiles + 32 * (T > 0 ? T : 1);
+    lay->o_q = lay->o_ctas + 32 * lay->n_ctas;
     lay->o_emb = lay->o_q + (int64_t)B * d * 4;
     lay->in_bytes = lay->o_emb + total * (int64_t)d * 4;
     lay->o_idx = total * 4;
@@ -194,6 +208,10 @@ extern "C" int rdv_small_batch_pack(const void* const* h_docs, const int64_t* ro
     RDV_REQUIRE(off == lay->total_rows, RDV_E_INVALID, "small_batch_pack: layout is for %lld rows, batch has %lld",
                 (long long)lay->total_rows, (long long)off);
     memcpy(hb + lay->o_q, h_q, (size_t)B * row_bytes);
+    if (lay->n_ctas > 0) {                                                       // the cluster kernel's view of the batch
+        int rc = rdv_build_cluster_table(d_docs, rows, B, d, (int32_t)lay->cluster, (int32_t)lay->slice_rows, reinterpret_cast<rdv_cta_desc*>(hb + lay->o_ctas), lay->n_ctas);
+        if (rc) return rc;
+    }
     int32_t mx = 0;
     return rdv_build_doc_table(d_docs, rows, B, d, lay->tile_rows, reinterpret_cast<int64_t*>(hb),
                                reinterpret_cast<rdv_tile_desc*>(hb + lay->o_tiles), lay->n_tiles, &mx);
@@ -201,14 +219,14 @@ extern "C" int rdv_small_batch_pack(const void* const* h_docs, const int64_t* ro
 
 extern "C" int rdv_retrieve_small_f32(const void* const* h_docs, const int64_t* rows, int32_t B, int32_t d, int32_t k,
                                       const float* h_q, void* h_blob, void* d_blob, int64_t blob_bytes, void* d_out,
-                                      int64_t d_out_bytes, void* h_out, int64_t h_out_bytes, int32_t* d_doc_done,
-                                      rdv_small_layout* lay, void* stream) {
+                                      int64_t d_out_bytes, void* h_out, int64_t h_out_bytes, rdv_small_layout* lay,
+                                      void* stream) {
     using namespace rdv;
     int rc = rdv_small_batch_layout(rows, B, d, k, lay);
     if (rc) return rc;
     if (lay->in_bytes > blob_bytes || lay->out_bytes > d_out_bytes || lay->read_bytes > h_out_bytes)
         return RDV_SMALL_GROW;                                   // nothing touched: the caller grows its buffers and calls again
-    RDV_REQUIRE(d_out && h_out && d_doc_done, RDV_E_INVALID, "retrieve_small_f32: null pointer");
+    RDV_REQUIRE(d_out && h_out, RDV_E_INVALID, "retrieve_small_f32: null pointer");
     rc = rdv_small_batch_pack(h_docs, rows, B, d, h_q, lay, h_blob, d_blob);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -216,11 +234,17 @@ extern "C" int rdv_retrieve_small_f32(const void* const* h_docs, const int64_t* 
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync (retrieve_small_f32, upload)");
     char* in = static_cast<char*>(d_blob);
     char* out = static_cast<char*>(d_out);
-    rc = rdv_score_topk_f32(reinterpret_cast<const rdv_tile_desc*>(in + lay->o_tiles), lay->n_tiles, lay->tile_rows, lay->algo,
-                            reinterpret_cast<const int64_t*>(in), reinterpret_cast<const float*>(in + lay->o_q), B, d, k,
-                            lay->max_rows, reinterpret_cast<float*>(out), reinterpret_cast<int32_t*>(out + lay->o_idx),
-                            reinterpret_cast<float*>(out + lay->o_val), reinterpret_cast<int32_t*>(out + lay->o_cnt),
-                            d_doc_done, stream);
+    if (lay->algo == RDV_SMALL_CLUSTER)
+        rc = rdv_score_topk_cluster_f32(reinterpret_cast<const rdv_cta_desc*>(in + lay->o_ctas), lay->n_ctas, (int32_t)lay->cluster,
+                                        reinterpret_cast<const float*>(in + lay->o_q), B, d, k, lay->max_rows,
+                                        reinterpret_cast<float*>(out), reinterpret_cast<int32_t*>(out + lay->o_idx),
+                                        reinterpret_cast<float*>(out + lay->o_val), reinterpret_cast<int32_t*>(out + lay->o_cnt),
+                                        stream);
+    else
+        rc = rdv_score_topk_f32(reinterpret_cast<const rdv_tile_desc*>(in + lay->o_tiles), lay->n_tiles, lay->tile_rows, lay->algo,
+                                reinterpret_cast<const int64_t*>(in), reinterpret_cast<const float*>(in + lay->o_q), B, d, k,
+                                lay->max_rows, reinterpret_cast<float*>(out), reinterpret_cast<int32_t*>(out + lay->o_idx),
+                                reinterpret_cast<float*>(out + lay->o_val), reinterpret_cast<int32_t*>(out + lay->o_cnt), stream);
     if (rc) return rc;
     e = cudaMemcpyAsync(h_out, d_out, (size_t)lay->read_bytes, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync (retrieve_small_f32, read-back)");

@@ -22,15 +22,20 @@ __device__ __forceinline__ bool better(const Cand& a, const Cand& b) {   // a st
     return a.key > b.key || (a.key == b.key && a.idx < b.idx);
 }
 
+// Candidates of query q: `parts` lists of k_in entries; list r starts at cand_val + r * part_stride_val + q * k_in (idx
+// likewise).  parts == 1 is the plain (Q, m) matrix; parts == world is the all-gather receive buffer as NCCL fills it
+// (rank-major), read in place -- no transpose copy between the collective and the merge.
 __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ cand_val,
-                                                         const int64_t* __restrict__ cand_idx, int Q, int m,
+                                                         const int64_t* __restrict__ cand_idx, int Q, int parts, int k_in,
+                                                         long long part_stride_val, long long part_stride_idx,
                                                          int k, float* __restrict__ out_val,
                                                          int64_t* __restrict__ out_idx) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= Q) return;
-    const float* cv = cand_val + (size_t)q * m;
-    const int64_t* ci = cand_idx + (size_t)q * m;
+    const int m = parts * k_in;
+    const float* cv = cand_val + (size_t)q * k_in;
+    const int64_t* ci = cand_idx + (size_t)q * k_in;
     Cand prev;
     prev.key = 0xFFFFFFFFu; prev.idx = -1;    // "nothing selected yet"
     bool have_prev = false;
@@ -39,8 +44,9 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
         Cand best; best.key = 0; best.idx = -1;
         float best_val = -INFINITY;
         for (int i = lane; i < m; i += 32) {
-            Cand c; c.idx = ci[i];
-            const float v = cv[i];
+            const int part = i / k_in, j = i - part * k_in;
+            Cand c; c.idx = ci[(size_t)part * part_stride_idx + j];
+            const float v = cv[(size_t)part * part_stride_val + j];
             c.key = order_key(v);
             if (c.idx < 0) continue;
             if (have_prev && !better(prev, c)) continue;   // already emitted (or equal to prev)
@@ -79,8 +85,25 @@ extern "C" int rdv_topk_merge(const float* d_cand_val, const int64_t* d_cand_idx
     if (Q == 0) return RDV_OK;
     RDV_REQUIRE(d_cand_val && d_cand_idx && d_out_val && d_out_idx, RDV_E_INVALID, "topk_merge: null pointer");
     const int blocks = (Q + 3) / 4;
-    topk_merge_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_cand_val, d_cand_idx, Q, m, k,
+    topk_merge_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_cand_val, d_cand_idx, Q, 1, m, 0, 0, k,
                                                                             d_out_val, d_out_idx);
+    RDV_LAUNCH_CHECK("topk_merge_kernel");
+    return RDV_OK;
+}
+
+extern "C" int rdv_topk_merge_parts(const float* d_cand_val, const int64_t* d_cand_idx, int32_t Q, int32_t parts, int32_t k_in,
+                                    int64_t part_stride_val, int64_t part_stride_idx, int32_t k, float* d_out_val,
+                                    int64_t* d_out_idx, void* stream) {
+    using namespace rdv;
+    RDV_REQUIRE(Q >= 0 && parts >= 1 && k_in >= 0 && k >= 1 && part_stride_val >= 0 && part_stride_idx >= 0, RDV_E_INVALID,
+                "topk_merge_parts: bad sizes Q=%d parts=%d k_in=%d k=%d", Q, parts, k_in, k);
+    RDV_REQUIRE((int64_t)parts * k_in < (1ll << 31), RDV_E_LIMIT, "topk_merge_parts: too many candidates per query");
+    if (Q == 0) return RDV_OK;
+    RDV_REQUIRE(d_cand_val && d_cand_idx && d_out_val && d_out_idx, RDV_E_INVALID, "topk_merge_parts: null pointer");
+    const int blocks = (Q + 3) / 4;
+    topk_merge_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_cand_val, d_cand_idx, Q, parts, k_in,
+                                                                            part_stride_val, part_stride_idx, k, d_out_val,
+                                                                            d_out_idx);
     RDV_LAUNCH_CHECK("topk_merge_kernel");
     return RDV_OK;
 }

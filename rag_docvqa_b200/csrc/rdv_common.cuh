@@ -94,9 +94,8 @@ static inline void prefer_carveout(void (*kernel)(KArgs...)) {
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args&&... args) {
-    static PerDeviceOnce carve_once;          // one static per kernel instantiation, one bit per device
-    int carve_dev;
-    if (carve_once.pending(&carve_dev)) { prefer_carveout(kernel); carve_once.mark(carve_dev); }
+    prefer_carveout(kernel);                  // a measurement knob (RDV_CARVEOUT), off by default: set on every launch,
+                                              // because a function-local flag here would exist once per kernel SIGNATURE
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;

@@ -11,11 +11,13 @@
 // returns the full vector, src/_modules.py:2176-2180):
 //
 //  * score_ldg_kernel (any d % 4 == 0): one block per tile, a warp per row, ROWS rows in flight per warp as
-//    independent 128-bit no-allocate loads; the question vector is loaded in the same burst.
-//    fused = 1: a device-scope row counter per document tells which block finished the document, and
-//    that block runs the selection (one launch for score + top-k).
-//    fused = 0: scores only; the selection runs in topk_segments_kernel / inside the gather kernel, so no
-//    device-scope fence or atomic sits on the streaming path.
+//    independent 128-bit no-allocate loads; the question vector is loaded in the same burst.  Scores only: the
+//    selection runs in topk_segments_kernel / inside the gather kernel, so no device-scope fence or atomic sits on
+//    the streaming path.  (Batches of short documents take retrieve_cluster.cu instead: one launch for score, top-k
+//    and gather, the hand-over inside a thread-block cluster.  A one-launch variant of THIS kernel -- the block that
+//    completes a document selects, told by a device-scope counter -- was measured at 9.7 us (score + top-k) / 14.0 us
+//    (+ gather) against 6.9 + 5.8 us for two launches at C2, and 617 against 610 us at C3: every stage after the
+//    streaming phase is a dependent global round trip, fence -> atomic -> re-read.  Removed.)
 //  * score_tma_kernel (d in {128,256,384,512,768,1024}): persistent, one block per SM owning a contiguous
 //    run of tiles; every warp owns a private shared-memory ring and ITS OWN mbarriers, requests its tiles with
 //    1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) and consumes them with conflict-free LDS.128 -- no
@@ -37,7 +39,7 @@ struct ScoreParams {
     const rdv_tile_desc* tiles;
     const int64_t* row_off;
     const float* q;
-    int32_t B, d, total_tiles, fused;
+    int32_t B, d, total_tiles, reserved;
     int32_t tile_rows, stages;                // TMA kernel: rows per stage (max), ring depth per warp
     float* sims;
     SelectArgs sel;
@@ -46,35 +48,6 @@ struct ScoreParams {
 __device__ __forceinline__ float cosine(float dot, float ss_e, float ss_q) {
     // reference: dot / (||e|| * ||q|| + 1e-8), all fp32, IEEE sqrt and divide
     return __fdiv_rn(dot, __fadd_rn(__fmul_rn(__fsqrt_rn(ss_e), __fsqrt_rn(ss_q)), 1e-8f));
-}
-
-// documents with no chunks own no tile: their (empty) results are written by block 0
-__device__ __forceinline__ void write_empty_docs(const ScoreParams& p, int tid, int nthreads) {
-    for (int b = tid; b < p.B; b += nthreads) {
-        if (p.row_off[b + 1] == p.row_off[b]) {
-            p.sel.topk_cnt[b] = 0;
-            for (int r = 0; r < p.sel.k; ++r) {
-                p.sel.topk_idx[(size_t)b * p.sel.k + r] = -1;
-                p.sel.topk_val[(size_t)b * p.sel.k + r] = -INFINITY;
-            }
-        }
-    }
-}
-
-// `rows` more rows of document b are written: publish, and if that completes the document run its
-// selection.  Called by all 256 compute threads.
-template <class Sync>
-__device__ __forceinline__ void publish_rows(const ScoreParams& p, int b, int rows, int doc_rows, float* cache,
-                                             unsigned long long* s_red, int* s_last, Sync sync) {
-    __threadfence();
-    sync();
-    if (threadIdx.x == 0) {
-        const int prev = atomicAdd(p.sel.doc_done + b, rows);
-        *s_last = (prev + rows == doc_rows);
-        __threadfence();
-    }
-    sync();
-    if (*s_last) select_topk<16>(p.sel, b, p.sims + p.row_off[b], doc_rows, cache, s_red, sync);
 }
 
 template <int VPL>
@@ -103,7 +76,7 @@ __device__ __forceinline__ float sumsq(const float4 (&q)[VPL]) {
 // =====================================================================================================
 // LDG kernel: one block per tile.  VPL > 0: d == 128 * VPL, everything in registers.  VPL == 0: any d % 4 == 0.
 // =====================================================================================================
-template <int VPL, int ROWS, int MINB, bool FUSED>
+template <int VPL, int ROWS, int MINB>
 __global__ void __launch_bounds__(kScoreThreads, MINB) score_ldg_kernel(const ScoreParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d4 = p.d >> 2;
@@ -111,9 +84,6 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) score_ldg_kernel(const Sc
     pdl_launch_dependents();      // the selection / gather kernel may be scheduled behind this grid's last wave
     pdl_wait();                   // embeddings, questions and descriptors come from earlier work in the stream
 
-    if constexpr (FUSED) {
-        if (blockIdx.x == 0) write_empty_docs(p, tid, kScoreThreads);
-    }
     if ((int)blockIdx.x >= p.total_tiles) return;
 
     const rdv_tile_desc t = p.tiles[blockIdx.x];          // one broadcast 32-byte load, no search
@@ -181,12 +151,6 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) score_ldg_kernel(const Sc
             }
             if (lane < ROWS && r + lane < t.rows) out[r + lane] = mine;
         }
-    }
-    if constexpr (FUSED) {
-        extern __shared__ float4 smem_dyn[];
-        __shared__ unsigned long long s_red[kScoreWarps];
-        __shared__ int s_last;
-        publish_rows(p, t.doc, t.rows, t.doc_rows, reinterpret_cast<float*>(smem_dyn), s_red, &s_last, BlockSync());
     }
 }
 
@@ -324,18 +288,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) score_tma_kernel(const ScorePa
 // ---- launch plumbing ------------------------------------------------------------------------------
 template <int VPL, int ROWS, int MINB>
 static int launch_ldg(const ScoreParams& p, cudaStream_t stream) {
-    if (p.fused) {
-        RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(score_ldg_kernel<VPL, ROWS, MINB, true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024),
-                            "cudaFuncSetAttribute(score_ldg)");
-        const int grid = p.total_tiles > 0 ? p.total_tiles : 1;
-        const size_t smem = (size_t)p.sel.cache_floats * sizeof(float) + 16;
-        cudaError_t e = launch_pdl(kPdlStream, score_ldg_kernel<VPL, ROWS, MINB, true>, dim3(grid), dim3(kScoreThreads), smem, stream, p);
-        if (e != cudaSuccess) return cuda_fail(e, "score_ldg_kernel (fused)");
-        return RDV_OK;
-    }
     if (p.total_tiles == 0) return RDV_OK;
-    cudaError_t e = launch_pdl(kPdlStream, score_ldg_kernel<VPL, ROWS, MINB, false>, dim3(p.total_tiles), dim3(kScoreThreads), 0, stream, p);
+    cudaError_t e = launch_pdl(kPdlStream, score_ldg_kernel<VPL, ROWS, MINB>, dim3(p.total_tiles), dim3(kScoreThreads), 0, stream, p);
     if (e != cudaSuccess) return cuda_fail(e, "score_ldg_kernel");
     return RDV_OK;
 }
@@ -393,7 +347,7 @@ static int launch_stream(const ScoreParams& p, int algo, cudaStream_t s) {
     // Two shapes per width (measured with scripts/probe_stream.cu on B200).  Small batches (the plan gives them
     // <= 32-row tiles) are launch/latency-bound: fewer rows in flight per warp, <= 51 registers, 5 blocks per SM
     // so the whole batch is resident in ~1 wave.  Large batches keep more rows in flight per warp.
-    const bool small = p.tile_rows <= 32 && !p.fused;
+    const bool small = p.tile_rows <= 32;
     switch (p.d) {
         case 128:  return small ? launch_ldg<1, 4, 5>(p, s) : launch_ldg<1, 8, 3>(p, s);
         case 256:  return small ? launch_ldg<2, 2, 5>(p, s) : launch_ldg<2, 4, 3>(p, s);
@@ -433,7 +387,7 @@ using namespace rdv;
 
 extern "C" int rdv_score_plan(int64_t total_rows, int32_t d, int32_t algo, int32_t* algo_out, int32_t* tile_rows) {
     RDV_REQUIRE(algo_out && tile_rows, RDV_E_INVALID, "score_plan: null output");
-    RDV_REQUIRE(algo >= RDV_SCORE_AUTO && algo <= RDV_SCORE_LDG_FUSED, RDV_E_INVALID, "score_plan: unknown algo %d", algo);
+    RDV_REQUIRE(algo >= RDV_SCORE_AUTO && algo <= RDV_SCORE_TMA, RDV_E_INVALID, "score_plan: unknown algo %d", algo);
     // measured on B200 (profiles/, scripts/probe_tma.py): the LDG streaming kernel leads at every size (C2 6.9 us vs
     // 12.8 us, C3 7.2 vs 7.05 TB/s for the self-service TMA ring), so AUTO picks it; RDV_SCORE_TMA stays selectable
     if (algo == RDV_SCORE_AUTO) algo = RDV_SCORE_LDG;
@@ -460,8 +414,8 @@ static int check_score_args(const char* who, const rdv_tile_desc* d_tiles, int32
     RDV_REQUIRE((d_sims && d_tiles) || total_tiles == 0, RDV_E_INVALID, "%s: null sims / tiles", who);
     RDV_REQUIRE(d >= 4 && d <= 8192 && (d & 3) == 0, RDV_E_INVALID, "%s: d=%d must be a multiple of 4 in [4, 8192]", who, d);
     RDV_REQUIRE(tile_rows >= 1 && tile_rows <= 1024, RDV_E_INVALID, "%s: tile_rows=%d outside [1, 1024]", who, tile_rows);
-    RDV_REQUIRE(algo == RDV_SCORE_LDG || algo == RDV_SCORE_TMA || algo == RDV_SCORE_LDG_FUSED, RDV_E_INVALID,
-                "%s: algo must be RDV_SCORE_LDG, RDV_SCORE_TMA or RDV_SCORE_LDG_FUSED (resolve AUTO with rdv_score_plan)", who);
+    RDV_REQUIRE(algo == RDV_SCORE_LDG || algo == RDV_SCORE_TMA, RDV_E_INVALID,
+                "%s: algo must be RDV_SCORE_LDG or RDV_SCORE_TMA (resolve AUTO with rdv_score_plan)", who);
     RDV_REQUIRE(aligned16(d_q) && aligned16(d_tiles), RDV_E_ALIGN, "%s: q / tiles not 16-byte aligned", who);
     return RDV_OK;
 }
@@ -470,41 +424,33 @@ extern "C" int rdv_score_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, 
                              const float* d_q, int32_t B, int32_t d, float* d_sims, void* stream) {
     int rc = check_score_args("score_f32", d_tiles, total_tiles, tile_rows, algo, d_q, B, d, d_sims);
     if (rc) return rc;
-    RDV_REQUIRE(algo != RDV_SCORE_LDG_FUSED, RDV_E_INVALID, "score_f32: the fused kernel needs rdv_score_topk_f32");
     if (B == 0 || total_tiles == 0) return RDV_OK;
     ScoreParams p = {};
     p.tiles = d_tiles; p.q = d_q; p.B = B; p.d = d; p.total_tiles = total_tiles; p.tile_rows = tile_rows;
-    p.fused = 0; p.sims = d_sims;
+    p.sims = d_sims;
     return launch_stream(p, algo, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_tiles, int32_t tile_rows, int32_t algo,
                                   const int64_t* d_row_off, const float* d_q, int32_t B, int32_t d, int32_t k,
                                   int32_t max_rows, float* d_sims, int32_t* d_topk_idx, float* d_topk_val,
-                                  int32_t* d_topk_cnt, int32_t* d_doc_done, void* stream) {
+                                  int32_t* d_topk_cnt, void* stream) {
     int rc = check_score_args("score_topk_f32", d_tiles, total_tiles, tile_rows, algo, d_q, B, d, d_sims);
     if (rc) return rc;
     RDV_REQUIRE(max_rows >= 0, RDV_E_INVALID, "score_topk_f32: negative size");
     if (B == 0) return RDV_OK;
-    RDV_REQUIRE(d_row_off && d_topk_idx && d_topk_val && d_topk_cnt && d_doc_done, RDV_E_INVALID,
-                "score_topk_f32: null pointer");
+    RDV_REQUIRE(d_row_off && d_topk_idx && d_topk_val && d_topk_cnt, RDV_E_INVALID, "score_topk_f32: null pointer");
     RDV_REQUIRE(k >= 1 && k <= 1024, RDV_E_LIMIT, "score_topk_f32: k=%d outside [1, 1024]", k);
     ScoreParams p = {};
     p.tiles = d_tiles; p.row_off = d_row_off; p.q = d_q;
     p.B = B; p.d = d; p.total_tiles = total_tiles; p.tile_rows = tile_rows; p.sims = d_sims;
     p.sel.k = k;
-    p.sel.cache_floats = cache_floats_for(max_rows, k, (algo == RDV_SCORE_LDG_FUSED ? 16 : 40) * kScoreThreads);
-    p.sel.topk_idx = d_topk_idx; p.sel.topk_val = d_topk_val; p.sel.topk_cnt = d_topk_cnt; p.sel.doc_done = d_doc_done;
+    p.sel.cache_floats = cache_floats_for(max_rows, k, 40 * kScoreThreads);
+    p.sel.topk_idx = d_topk_idx; p.sel.topk_val = d_topk_val; p.sel.topk_cnt = d_topk_cnt; p.sel.doc_done = nullptr;
     p.sel.smem_idx = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (algo == RDV_SCORE_LDG_FUSED) {
-        p.fused = 1;
-        return launch_stream(p, RDV_SCORE_LDG, s);
-    }
-    p.fused = 0;
     rc = launch_stream(p, algo, s);
     if (rc) return rc;
-    p.sel.doc_done = nullptr;            // the split path needs no counters
     return launch_segments(d_sims, d_row_off, B, p.sel, s);
 }
 

@@ -73,6 +73,11 @@ class DocStore:
         self.n_words = int(arrays["chunk_word_off"][-1])
         self.n_tokens = int(arrays["word_tok_off"][-1])
 
+    def same_chunks_as(self, sizes) -> bool:
+        """True when a batch of embeddings with `sizes` rows per document describes exactly this store's chunks."""
+        sizes = np.asarray(sizes, dtype=np.int64)
+        return len(sizes) == self.B and bool(np.array_equal(np.diff(self.host["chunk_off"]), sizes))
+
     @classmethod
     def from_lists(cls, words_text_chunks, words_box_chunks, layout_labels_chunks, page_indices,
                    tokenize: Callable[[str], Sequence[int]], device, images=None, derived: bool = True) -> "DocStore":
@@ -267,6 +272,9 @@ class DocStore:
         if sims is not None:
             if topk_val is None:
                 raise ValueError("fused selection needs topk_val")
+            if sims.numel() != self.n_chunks:
+                raise ValueError("gather: %d similarities for a store of %d chunks (the embeddings and the store must "
+                                 "describe the same chunks)" % (sims.numel(), self.n_chunks))
             t["sims"], t["topk_val"] = sims, topk_val
             a.sims = sims.data_ptr(); a.topk_val = topk_val.data_ptr(); a.max_rows = int(max_rows)
         plan = GatherPlan(self, a, t, max_len, max_seg)
@@ -311,6 +319,27 @@ class GatherPlan:
         dev = self.store.device
         rc = _lib.lib.rdv_gather_vt5_inputs(self._ds_ref, self._args_ref,
                                             _stream_ptr(dev) if stream is None else stream)
+        if rc:
+            _lib.check(rc)
+
+    def can_retrieve_in_one_launch(self, table) -> bool:
+        """rdv_retrieve_vt5_f32's requirements (include/rdv.h): the cluster kernel's limits, no neighbour windows, no
+        reranked re-emission, and a store that describes the same chunks as the embeddings."""
+        a = self.args
+        return (a.include_surroundings == 0 and not a.emit_order and table.B == self.store.B and "topk_val" in self.t
+                and table.cluster_fits(a.k) and self.store.same_chunks_as(table.sizes))
+
+    def prefers_one_launch(self, table) -> bool:
+        """... and rdv_retrieve_plan picks it over the streaming kernel + the select / gather kernel."""
+        return self.can_retrieve_in_one_launch(table) and table.use_cluster(self.args.k)
+
+    def launch_retrieve(self, table, questions: torch.Tensor, sims: torch.Tensor, stream: Optional[int] = None) -> None:
+        """The whole step in ONE launch (rdv_retrieve_vt5_f32): cosine scores of `table` against `questions` into `sims`,
+        per-document top-k into this plan's topk_idx / topk_val / topk_cnt, and the gather of the hits."""
+        dev = self.store.device
+        d_ctas, n_ctas, cluster = table.cluster_pointers()
+        rc = _lib.lib.rdv_retrieve_vt5_f32(d_ctas, n_ctas, cluster, questions.data_ptr(), table.d, table.max_rows, sims.data_ptr(),
+                                           self._ds_ref, self._args_ref, _stream_ptr(dev) if stream is None else stream)
         if rc:
             _lib.check(rc)
 

@@ -62,12 +62,14 @@ class ScoreTopK(NamedTuple):
 
 TILE_DTYPE = np.dtype([("src", "<u8"), ("sims_off", "<i8"), ("rows", "<i4"), ("doc", "<i4"),
                        ("doc_rows", "<i4"), ("reserved", "<i4")])      # rdv_tile_desc, 32 bytes
+CTA_DTYPE = np.dtype([("src", "<u8"), ("sims_off", "<i4"), ("doc_rows", "<i4"), ("doc", "<i4"), ("part", "<i2"),
+                      ("nparts", "<i2"), ("r0", "<i4"), ("r1", "<i4")])  # rdv_cta_desc, 32 bytes
 
 
 class DocTable(NamedTuple):
-    """Device-side description of a ragged batch of documents (see rdv_score_topk_f32)."""
-    desc: torch.Tensor     # uint8 blob on device: row_off[B+1] i64 | pad | tiles[T] rdv_tile_desc
-    keepalive: tuple       # tensors whose storage the tile descriptors point into
+    """Device-side description of a ragged batch of documents (see rdv_score_topk_f32 / rdv_score_topk_cluster_f32)."""
+    desc: torch.Tensor     # uint8 blob on device: row_off[B+1] i64 | pad | tiles[T] rdv_tile_desc | ctas[n_ctas] rdv_cta_desc
+    keepalive: tuple       # tensors whose storage the descriptors point into
     B: int
     d: int
     sizes: List[int]
@@ -77,11 +79,30 @@ class DocTable(NamedTuple):
     max_rows: int
     algo: int
     tiles_offset: int
+    ctas_offset: int
+    n_ctas: int            # descriptors of the cluster kernels (0: the batch is outside their limits)
+    cluster: int           # ... and the cluster size they were packed for
 
     def pointers(self):
         """(d_tiles, d_row_off)"""
         base = self.desc.data_ptr()
         return base + self.tiles_offset, base
+
+    def cluster_pointers(self):
+        """(d_ctas, n_ctas, cluster) for the cluster kernels"""
+        return self.desc.data_ptr() + self.ctas_offset, self.n_ctas, self.cluster
+
+    def cluster_fits(self, k: int) -> bool:
+        """Do the one-launch cluster kernels apply to this batch (their limits; a cluster table was built)?"""
+        return bool(self.B and self.n_ctas and self.algo != _lib.SCORE_TMA and 1 <= int(k) <= int(_lib_fn.rdv_cluster_max_k()))
+
+    def use_cluster(self, k: int) -> bool:
+        """rdv_retrieve_plan: ... and are they the better choice?  (Measured in round 2: no -- see csrc/retrieve_cluster.cu.)"""
+        if not self.cluster_fits(k):
+            return False
+        out = ctypes.c_int32()
+        _lib.check(_lib_fn.rdv_retrieve_plan(self.total_rows, self.max_rows, self.B, self.d, int(k), ctypes.byref(out)))
+        return bool(out.value)
 
 
 def plan_score(total_rows: int, d: int, algo: int = _lib.SCORE_AUTO):
@@ -90,7 +111,8 @@ def plan_score(total_rows: int, d: int, algo: int = _lib.SCORE_AUTO):
     return algo_out.value, tile_rows.value
 
 
-def _table_from_pointers(ptrs: np.ndarray, sizes: np.ndarray, keep, d: int, device, tile_rows: int, algo: int) -> DocTable:
+def _table_from_pointers(ptrs: np.ndarray, sizes: np.ndarray, keep, d: int, device, tile_rows: int, algo: int,
+                         plan_k: int = 8) -> DocTable:
     """rdv_build_doc_table into a pinned blob (row_off | pad | tiles) + ONE H2D copy."""
     B = len(sizes)
     total_rows = int(sizes.sum()) if B else 0
@@ -102,16 +124,30 @@ def _table_from_pointers(ptrs: np.ndarray, sizes: np.ndarray, keep, d: int, devi
     if T < 0 or T >= 2 ** 31 - 1:
         raise ValueError("bad document sizes / too many tiles for one launch")
     tiles_offset = (8 * (B + 1) + 31) // 32 * 32
-    host = torch.empty(tiles_offset + 32 * max(T, 1), dtype=torch.uint8, pin_memory=True)
+    ctas_offset = tiles_offset + 32 * max(T, 1)
+    # the cluster kernels' view (tiles packed into clusters, a document never straddling one) where their limits allow
+    n_ctas, cluster, slice_rows = 0, 0, 0
+    if B and total_rows < 2 ** 31 and algo != _lib.SCORE_TMA and int(sizes.max()) <= int(_lib_fn.rdv_cluster_max_rows(16)):
+        c_cluster, c_slice, c_n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        with torch.cuda.device(device):      # asked for the variant that also gathers with k <= 8 (the common one, and the
+            # one with the least room: a plan that fits it fits the score + top-k variant as well)
+            _lib.check(_lib_fn.rdv_cluster_plan(p_sizes, B, d, plan_k, 1, ctypes.byref(c_cluster), ctypes.byref(c_slice),
+                                                ctypes.byref(c_n)))
+        cluster, slice_rows, n_ctas = c_cluster.value, c_slice.value, int(c_n.value)
+    host = torch.empty(ctas_offset + 32 * max(n_ctas, 1), dtype=torch.uint8, pin_memory=True)
     base = host.data_ptr()
     max_rows = ctypes.c_int32(0)
     if B:
         _lib.check(_lib_fn.rdv_build_doc_table(ptrs.ctypes.data, p_sizes, B, d, tile_rows, base, base + tiles_offset, T,
                                                ctypes.byref(max_rows)))
+        if n_ctas:
+            _lib.check(_lib_fn.rdv_build_cluster_table(ptrs.ctypes.data, p_sizes, B, d, cluster, slice_rows, base + ctas_offset,
+                                                       n_ctas))
     else:
         host[:8] = 0
     desc = host.to(device, non_blocking=True)
-    return DocTable(desc, keep, B, d, sizes.tolist(), total_rows, T, tile_rows, int(max_rows.value), algo, tiles_offset)
+    return DocTable(desc, keep, B, d, sizes.tolist(), total_rows, T, tile_rows, int(max_rows.value), algo, tiles_offset,
+                    ctas_offset, n_ctas, cluster)
 
 
 def build_doc_table(docs: Sequence[torch.Tensor], d: int, device, tile_rows: int = 0,
@@ -177,28 +213,35 @@ def upload_doc_table(host_docs: Sequence[torch.Tensor], d: int, device, tile_row
     return _table_from_pointers(dptrs, sizes, (packed, tuple(docs)), d, device, tile_rows, algo)
 
 
-def score_topk_table(table: DocTable, questions: torch.Tensor, k: int) -> ScoreTopK:
-    """Launches the fused score + top-k kernel on an uploaded DocTable."""
+def score_topk_table(table: DocTable, questions: torch.Tensor, k: int, cluster=None) -> ScoreTopK:
+    """Score + per-document top-k on an uploaded DocTable: ONE launch (a thread-block cluster per document,
+    rdv_score_topk_cluster_f32) for batches of short documents, else the streaming kernel + the selection kernel
+    (rdv_score_topk_f32).  `cluster`: None = rdv_retrieve_plan decides, True / False = forced."""
     device = questions.device
     B, d = table.B, table.d
     q = _f32_contig_aligned(questions)
-    sims = torch.empty(table.total_rows, dtype=torch.float32, device=device)
+    sims_base = torch.empty(max(table.total_rows, 1), dtype=torch.float32, device=device)    # never a null pointer
+    sims = sims_base[:table.total_rows]
     topk_idx = torch.empty((B, k), dtype=torch.int32, device=device)
     topk_val = torch.empty((B, k), dtype=torch.float32, device=device)
     topk_cnt = torch.empty((B,), dtype=torch.int32, device=device)
-    if B:
-        done = _Workspace.zeros_i32(device, B)
+    if B and (table.use_cluster(k) if cluster is None else cluster):
+        d_ctas, n_ctas, cluster_size = table.cluster_pointers()
+        _lib.check(_lib_fn.rdv_score_topk_cluster_f32(
+            d_ctas, n_ctas, cluster_size, q.data_ptr(), B, d, k, table.max_rows, sims_base.data_ptr(), topk_idx.data_ptr(),
+            topk_val.data_ptr(), topk_cnt.data_ptr(), _stream_ptr(device)))
+    elif B:
         p_tiles, p_row = table.pointers()
         _lib.check(_lib_fn.rdv_score_topk_f32(
             p_tiles, table.total_tiles, table.tile_rows, table.algo, p_row, q.data_ptr(), B, d, k,
-            table.max_rows, sims.data_ptr(), topk_idx.data_ptr(), topk_val.data_ptr(),
-            topk_cnt.data_ptr(), done.data_ptr(), _stream_ptr(device)))
+            table.max_rows, sims_base.data_ptr(), topk_idx.data_ptr(), topk_val.data_ptr(),
+            topk_cnt.data_ptr(), _stream_ptr(device)))
     views = list(torch.split(sims, table.sizes)) if B else []
     return ScoreTopK(views, sims, topk_idx, topk_val, topk_cnt, table.sizes)
 
 
 def score_topk(text_embeddings: Sequence[torch.Tensor], question_embeddings: torch.Tensor, k: int,
-               tile_rows: int = 0, algo: int = _lib.SCORE_AUTO) -> ScoreTopK:
+               tile_rows: int = 0, algo: int = _lib.SCORE_AUTO, cluster=None) -> ScoreTopK:
     """Cosine score of question b against every chunk of document b + per-document top-k.
 
     Replaces Retriever._get_similarities + torch.topk (reference src/_modules.py:1978-1997, 2015-2016).
@@ -212,7 +255,7 @@ def score_topk(text_embeddings: Sequence[torch.Tensor], question_embeddings: tor
     d = question_embeddings.shape[1]
     with torch.cuda.device(question_embeddings.device):
         table = build_doc_table(text_embeddings, d, question_embeddings.device, tile_rows, algo)
-        return score_topk_table(table, question_embeddings, k)
+        return score_topk_table(table, question_embeddings, k, cluster=cluster)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -422,15 +465,14 @@ def late_interaction_bf16(query: torch.Tensor, patches: torch.Tensor) -> torch.T
     return out
 
 
-def score_table(table: DocTable, questions: torch.Tensor) -> torch.Tensor:
+def score_table(table: DocTable, questions: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """Scores only (rdv_score_f32): every similarity of the batch, (N,) fp32.  The selection then runs in
     topk_segments or inside the gather kernel (DocStore.prepare_gather(..., sims=...))."""
     device = questions.device
     q = _f32_contig_aligned(questions)
-    sims = torch.empty(table.total_rows, dtype=torch.float32, device=device)
-    algo = _lib.SCORE_LDG if table.algo == _lib.SCORE_LDG_FUSED else table.algo
+    sims = out if out is not None else torch.empty(table.total_rows, dtype=torch.float32, device=device)
     if table.B and table.total_tiles:
         p_tiles, _ = table.pointers()
-        _lib.check(_lib_fn.rdv_score_f32(p_tiles, table.total_tiles, table.tile_rows, algo, q.data_ptr(), table.B,
+        _lib.check(_lib_fn.rdv_score_f32(p_tiles, table.total_tiles, table.tile_rows, table.algo, q.data_ptr(), table.B,
                                          table.d, sims.data_ptr(), _stream_ptr(device)))
     return sims

@@ -354,8 +354,7 @@ class Retriever(StatComponent):
             bufs = (torch.empty(c_in, dtype=torch.uint8, pin_memory=True),
                     torch.empty(c_in, dtype=torch.uint8, device=dev),
                     torch.empty(c_dev, dtype=torch.uint8, device=dev),
-                    torch.empty(c_host, dtype=torch.uint8, pin_memory=True),
-                    torch.zeros(4096, dtype=torch.int32, device=dev))          # doc_done: the kernel leaves it zeroed
+                    torch.empty(c_host, dtype=torch.uint8, pin_memory=True))
             torch.cuda.current_stream(dev).synchronize()
         bufs = bufs + tuple(t.data_ptr() for t in bufs) + (bufs[3].numpy(),)
         self._small_bufs[dev.index] = bufs
@@ -366,7 +365,7 @@ class Retriever(StatComponent):
         """Host inputs of at most a megabyte (C1: one page of 30 chunks, the reference's own CPU-runnable case): a 46 KB
         problem is all fixed cost, so the device round trip is ONE C call (rdv_retrieve_small_f32): row offsets, tile
         descriptors, questions and embedding rows packed into one pinned blob, one upload, one launch (fused score +
-        top-k), one read-back of similarities, hits and counts, one synchronise.  Measured on B200 at C1: 0.164 ms per
+        top-k: a cluster per document), one read-back of similarities, hits and counts, one synchronise.  Measured on B200 at C1: 0.164 ms per
         call through the general path (7 transfers, 2 launches) -> 0.124 ms with one blob each way driven from Python."""
         dev = self.device
         B, d, k = len(text_embeddings), int(question_embeddings.shape[1]), int(self.k)
@@ -385,15 +384,14 @@ class Retriever(StatComponent):
         stream = torch.cuda.current_stream(dev).cuda_stream
         call = F._lib_fn.rdv_retrieve_small_f32
         while True:
-            host, blob, out, out_h, done, p_host, p_blob, p_out, p_out_h, p_done, res = bufs
+            host, blob, out, out_h, p_host, p_blob, p_out, p_out_h, res = bufs
             with torch.cuda.device(dev):
                 rc = call(h_docs, rows, B, d, k, q.data_ptr(), p_host, p_blob, host.numel(), p_out, out.numel(), p_out_h,
-                          out_h.numel(), p_done, ctypes.addressof(lay), stream)
+                          out_h.numel(), ctypes.addressof(lay), stream)
             if rc != F._lib.SMALL_GROW:
                 break
             bufs = self._small_buffers(dev, lay.in_bytes, lay.out_bytes, lay.read_bytes)
         if rc:
-            self._small_bufs.pop(dev.index, None)          # doc_done may be dirty after a failed launch
             F._lib.check(rc)
         o_idx, o_cnt = lay.o_idx, lay.o_cnt
         idx = res[o_idx:o_cnt].view(np.int32).reshape(B, k)
@@ -433,7 +431,7 @@ class Retriever(StatComponent):
             cnt_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
             sims_h = torch.empty((total,), dtype=torch.float32, pin_memory=True)
             p_tiles, p_row = table.pointers()
-            algo = F._lib.SCORE_LDG if table.algo == F._lib.SCORE_LDG_FUSED else table.algo
+            algo = table.algo
             events = []
             for lo, hi in zip(bounds[:-1], bounds[1:]):
                 t_lo, t_hi, r_lo, r_hi = int(tile_off[lo]), int(tile_off[hi]), int(row_off[lo]), int(row_off[hi])
@@ -478,13 +476,13 @@ class Retriever(StatComponent):
         q = _to_device(question_embeddings, dev)
         k = int(self.k)
         with torch.cuda.device(dev):
-            # two launches: streaming score kernel, then ONE block per document selects its top-k and gathers
             if len(text_embeddings) and not any(e.is_cuda for e in text_embeddings):
                 table = F.upload_doc_table(text_embeddings, q.shape[1], dev)
             else:
                 table = F.build_doc_table(emb, q.shape[1], dev)
-            sims = F.score_table(table, q)
             B = table.B
+            q = F._f32_contig_aligned(q)
+            sims = torch.empty(table.total_rows, dtype=torch.float32, device=dev)
             topk_idx = torch.empty((B, k), dtype=torch.int32, device=dev)
             topk_val = torch.empty((B, k), dtype=torch.float32, device=dev)
             topk_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -493,7 +491,13 @@ class Retriever(StatComponent):
                                         pad_id=pad_id, max_len=max_source_length,
                                         with_layout_labels=with_layout_labels, sims=sims, topk_val=topk_val,
                                         max_rows=table.max_rows)
-            plan.launch()
+            if plan.prefers_one_launch(table):
+                # ONE launch (thread-block clusters; csrc/retrieve_cluster.cu): only where rdv_retrieve_plan picks it
+                plan.launch_retrieve(table, q, sims)
+            else:
+                # two launches: streaming score kernel, then one block per document selects its top-k and gathers
+                F.score_table(table, q, out=sims)
+                plan.launch()
             visual = None
             if pages is not None:
                 visual = pages.pack(plan.t["hit_i"][1], plan.t["hit_rect"], topk_cnt, out_size=image_size, resample=resample,

@@ -75,8 +75,10 @@ class CorpusShard:
             raise ValueError("CorpusShard: expected a contiguous (n, d) bf16 matrix")
         self.rows = rows_bf16
         self.id_offset = int(id_offset)
-        self.inv_norm = inv_norm if inv_norm is not None else F.bf16_inv_norm(rows_bf16)
         self.n, self.d = rows_bf16.shape
+        if inv_norm is None:                                  # a rank may own no rows (N < world): nothing to norm
+            inv_norm = F.bf16_inv_norm(rows_bf16) if self.n else torch.empty((0,), dtype=torch.float32, device=rows_bf16.device)
+        self.inv_norm = inv_norm
 
     @classmethod
     def from_f32(cls, rows_f32: torch.Tensor, id_offset: int = 0) -> "CorpusShard":
@@ -87,6 +89,10 @@ class CorpusShard:
         """Local scoring: (Q, groups*16) candidate values / global ids (id -1 = empty)."""
         dev = self.rows.device
         Qn = questions.shape[0]
+        if self.n == 0:                                       # an empty shard still answers: no candidates (id -1)
+            per = int(_fn.rdv_tc_candidates_per_group())
+            return (torch.full((Qn, per), float("-inf"), dtype=torch.float32, device=dev),
+                    torch.full((Qn, per), -1, dtype=torch.int64, device=dev))
         q_bf16, q_inv = F.rows_to_bf16(questions, normalise=False, return_inv_norm=True)
         groups = int(_fn.rdv_corpus_groups(self.n, Qn))
         tile_m, per = int(_fn.rdv_tc_tile_m()), int(_fn.rdv_tc_candidates_per_group())
@@ -152,24 +158,27 @@ class CorpusIndex:
     def load_shard(self, device, rank: int = 0, world: int = 1, chunk_rows: int = 1 << 18) -> CorpusShard:
         """Rows [lo, hi) of this rank on `device`, global ids starting at lo."""
         lo, hi = shard_bounds(self.n, world, rank)
-        rows = torch.empty((hi - lo, self.d), dtype=torch.bfloat16, device=device)
-        stage = [torch.empty((min(chunk_rows, max(hi - lo, 1)), self.d), dtype=torch.int16, pin_memory=True) for _ in range(2)]
-        done = [None, None]
-        for i, a in enumerate(range(lo, hi, chunk_rows)):
-            b = min(hi, a + chunk_rows)
-            buf = stage[i & 1]
-            if done[i & 1] is not None:
-                done[i & 1].synchronize()                      # the previous copy out of this staging buffer
-            buf[:b - a].numpy()[...] = self.rows[a:b]
-            rows[a - lo:b - lo].view(torch.int16).copy_(buf[:b - a], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            done[i & 1] = ev
-        inv = None
-        if self.inv_norm is not None:
-            inv = torch.from_numpy(np.ascontiguousarray(self.inv_norm[lo:hi])).to(device)
-        torch.cuda.synchronize(device)
-        return CorpusShard(rows, id_offset=lo, inv_norm=inv)
+        device = torch.device(device)
+        with torch.cuda.device(device):                        # copies, events and the norm kernel all on `device`
+            rows = torch.empty((hi - lo, self.d), dtype=torch.bfloat16, device=device)
+            stage = [torch.empty((min(chunk_rows, max(hi - lo, 1)), self.d), dtype=torch.int16, pin_memory=True) for _ in range(2)]
+            done = [None, None]
+            stream = torch.cuda.current_stream(device)
+            for i, a in enumerate(range(lo, hi, chunk_rows)):
+                b = min(hi, a + chunk_rows)
+                buf = stage[i & 1]
+                if done[i & 1] is not None:
+                    done[i & 1].synchronize()                  # the previous copy out of this staging buffer
+                buf[:b - a].numpy()[...] = self.rows[a:b]
+                rows[a - lo:b - lo].view(torch.int16).copy_(buf[:b - a], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)                              # on the stream the copy was enqueued on
+                done[i & 1] = ev
+            inv = None
+            if self.inv_norm is not None:
+                inv = torch.from_numpy(np.ascontiguousarray(self.inv_norm[lo:hi])).to(device)
+            torch.cuda.synchronize(device)
+            return CorpusShard(rows, id_offset=lo, inv_norm=inv)
 
 
 def merge_across_ranks(local_val: torch.Tensor, local_idx: torch.Tensor, k: int, group=None, merge_fn=None):
@@ -199,6 +208,124 @@ def merge_across_ranks(local_val: torch.Tensor, local_idx: torch.Tensor, k: int,
         dist.all_gather(idxs, local_idx.contiguous(), group=group)
         cand_val, cand_idx = torch.cat(vals, dim=1), torch.cat(idxs, dim=1)
     return (merge_fn or merge_candidates)(cand_val, cand_idx, k)
+
+
+class CorpusSearcher:
+    """The corpus-mode query for a fixed (Q, k) with every buffer allocated once and the whole step -- bf16 cast of the
+    questions, tcgen05 score + fused top-k on the local shard (rdv_corpus_score_topk_bf16), local merge written STRAIGHT
+    into the NCCL send buffer, all-gather, final merge reading the receive buffer in NCCL's own rank-major layout
+    (rdv_topk_merge_parts) -- captured into ONE CUDA graph and replayed (`graph=True`).  Same kernels and ordering as
+    search(): sharded == unsharded bit for bit.
+
+    search(questions) copies the (Q, d) fp32 questions into the static input and replays; the returned (Q, k) value / id
+    tensors are the searcher's own output buffers (valid until the next call)."""
+
+    def __init__(self, shard: CorpusShard, n_questions: int, k: int, group=None, graph: bool = True):
+        import torch.distributed as dist
+        self.shard, self.Q, self.k, self.group = shard, int(n_questions), int(k), group
+        dev = self.dev = shard.rows.device
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._dist = dist if self.world > 1 else None
+        Q, d = self.Q, shard.d
+        f32, i32, i64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev), dict(dtype=torch.int64, device=dev)
+        self.q_in = torch.zeros((Q, d), **f32)
+        self.q_bf16 = torch.empty((Q, d), dtype=torch.bfloat16, device=dev)
+        self.q_inv = torch.empty((Q,), **f32)
+        self.groups = int(_fn.rdv_corpus_groups(shard.n, Q)) if shard.n else 0
+        tile_m, per = int(_fn.rdv_tc_tile_m()), int(_fn.rdv_tc_candidates_per_group())
+        rows_padded = (Q + tile_m - 1) // tile_m * tile_m
+        self.part_val = torch.empty((max(self.groups, 1), rows_padded, per), **f32)
+        self.part_idx = torch.empty((max(self.groups, 1), rows_padded, per), **i32)
+        self.cand_val = torch.empty((Q, max(self.groups, 1) * per), **f32)
+        self.cand_idx = torch.empty((Q, max(self.groups, 1) * per), **i64)
+        # one byte buffer per rank: (Q, k) fp32 values | pad to 8 | (Q, k) int64 global ids
+        self.nv = (Q * k * 4 + 7) // 8 * 8
+        self.send = torch.zeros(self.nv + Q * k * 8, dtype=torch.uint8, device=dev)
+        self.send_val = self.send[:Q * k * 4].view(torch.float32).view(Q, k)
+        self.send_idx = self.send[self.nv:].view(torch.int64).view(Q, k)
+        if shard.n == 0:                                      # no rows: the (constant) contribution is "no candidates"
+            self.send_val.fill_(float("-inf"))
+            self.send_idx.fill_(-1)
+        if self.world > 1:
+            self.recv = torch.empty((self.world, self.send.numel()), dtype=torch.uint8, device=dev)
+            self.out_val = torch.empty((Q, k), **f32)
+            self.out_idx = torch.empty((Q, k), **i64)
+        else:
+            self.recv, self.out_val, self.out_idx = None, self.send_val, self.send_idx
+        self.graphed = False
+        self._graph = None
+        if graph:
+            self._capture()
+
+    # -- the three parts of a step, each enqueued on torch's current stream ------------------------------------------
+    def _local(self):
+        sh, s = self.shard, F._stream_ptr(self.dev)
+        if sh.n == 0:
+            return
+        _lib.check(_fn.rdv_rows_to_bf16(self.q_in.data_ptr(), self.Q, sh.d, 0, self.q_bf16.data_ptr(), self.q_inv.data_ptr(), s))
+        _lib.check(_fn.rdv_corpus_score_topk_bf16(
+            sh.rows.data_ptr(), sh.inv_norm.data_ptr(), sh.n, sh.d, self.q_bf16.data_ptr(), self.q_inv.data_ptr(), self.Q,
+            self.k, sh.id_offset, self.groups, self.part_val.data_ptr(), self.part_idx.data_ptr(), self.cand_val.data_ptr(),
+            self.cand_idx.data_ptr(), s))
+        _lib.check(_fn.rdv_topk_merge(self.cand_val.data_ptr(), self.cand_idx.data_ptr(), self.Q, self.cand_val.shape[1],
+                                      self.k, self.send_val.data_ptr(), self.send_idx.data_ptr(), s))
+
+    def _exchange(self):
+        if self.world > 1:
+            self._dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+
+    def _final(self):
+        if self.world > 1:
+            stride = self.send.numel()
+            _lib.check(_fn.rdv_topk_merge_parts(self.recv.data_ptr(), self.recv.data_ptr() + self.nv, self.Q, self.world, self.k,
+                                                stride // 4, stride // 8, self.k, self.out_val.data_ptr(), self.out_idx.data_ptr(),
+                                                F._stream_ptr(self.dev)))
+
+    def _step(self):
+        self._local()
+        self._exchange()
+        self._final()
+
+    def _capture(self):
+        with torch.cuda.device(self.dev):
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):                            # NCCL communicator + kernel attributes set up before capture
+                    self._step()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g, stream=side):
+                    self._step()
+                self._graph, self.graphed = g, True
+            except Exception:                                  # capture not possible here (e.g. a collective that refuses it)
+                self._graph, self.graphed = None, False
+                torch.cuda.synchronize(self.dev)
+
+    def search(self, questions: torch.Tensor):
+        if tuple(questions.shape) != tuple(self.q_in.shape):
+            raise ValueError("CorpusSearcher: expected (%d, %d) questions, got %s" % (self.Q, self.shard.d, tuple(questions.shape)))
+        with torch.cuda.device(self.dev):
+            self.q_in.copy_(questions, non_blocking=True)
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._step()
+        return self.out_val, self.out_idx
+
+    # -- parts alone, for measurement ---------------------------------------------------------------------------------
+    def local_only(self, questions: torch.Tensor):
+        with torch.cuda.device(self.dev):
+            self.q_in.copy_(questions, non_blocking=True)
+            self._local()
+        return self.send_val, self.send_idx
+
+    def exchange_only(self):
+        with torch.cuda.device(self.dev):
+            self._exchange()
+            self._final()
 
 
 def merge_candidates(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):

@@ -265,3 +265,66 @@ def test_packed_inputs_vs_oracle_c2_slice(s, reorder, sep, derived):
             assert rect[b, j].tolist() == ref[6][b][j]
             assert page[b, j] == ref[7][b][j] and label[b, j] == ref[2][b][j]
         assert (page[b, len(ref[1][b]):] == -1).all()
+
+
+@pytest.mark.parametrize("derived", [True, False])
+@pytest.mark.parametrize("reorder,sep,k", [(False, False, 5), (True, True, 5), (True, False, 20)])
+def test_one_launch_step_equals_two_launches(reorder, sep, k, derived):
+    """rdv_retrieve_vt5_f32 (score + top-k + gather in ONE launch, a thread-block cluster per document, the candidates'
+    chunk records handed over through distributed shared memory) against rdv_score_f32 followed by rdv_gather_vt5_inputs
+    with its own selection: every output bit for bit, twice."""
+    from rag_docvqa_b200 import functional as F
+    from rag_docvqa_b200.docstore import DocStore
+    batch = synth.make_text_batch("C2", with_lists=True, docs=24, seed=77, dup_frac=0.1)
+    words, boxes, labels = batch["words_text_chunks"], batch["words_box_chunks"], batch["layout_labels_chunks"]
+    sizes = batch["sizes"]
+    assert 0 in sizes and any(0 < n < 5 for n in sizes) and max(sizes) > 256       # empty, shorter than k, several tiles per CTA
+    table_w = synth.make_tokens_for_words(words, seed=9)
+    dev = torch.device(DEV)
+    store = DocStore.from_lists(words, boxes, labels, batch["page_indices"], lambda w: table_w.get(w, [2]), dev,
+                                images=batch["images"], derived=derived)
+    prompts = prompts_for(["what is item %d about ?" % b for b in range(len(words))])
+    emb = [e.to(dev) for e in batch["text_embeddings"]]
+    q = batch["question_embeddings"].to(dev)
+    table = F.build_doc_table(emb, q.shape[1], dev)
+    B = len(emb)
+
+    def run(one_launch):
+        sims = torch.zeros(table.total_rows, dtype=torch.float32, device=dev)
+        idx = torch.full((B, k), -7, dtype=torch.int32, device=dev)
+        val = torch.zeros((B, k), dtype=torch.float32, device=dev)
+        cnt = torch.full((B,), -7, dtype=torch.int32, device=dev)
+        plan = store.prepare_gather(idx, cnt, prompts, reorder_chunks=reorder, sep_ids=[2, 9] if sep else [], max_len=512,
+                                    with_layout_labels=True, sims=sims, topk_val=val, max_rows=table.max_rows)
+        outs = []
+        for _ in range(2):
+            if one_launch:
+                assert plan.can_retrieve_in_one_launch(table)
+                plan.launch_retrieve(table, q, sims)
+            else:
+                F.score_table(table, q, out=sims)
+                plan.launch()
+            pk = plan.finish()
+            outs.append([t.clone() for t in (sims, idx, val, cnt, pk.input_ids, pk.boxes, pk.attention_mask, pk.layout_labels,
+                                             pk.hit_chunk, pk.hit_page, pk.hit_label, pk.hit_nwords, pk.hit_bbox, pk.hit_rect)])
+        for x, y in zip(*outs):
+            assert torch.equal(x, y)
+        return outs[0]
+
+    for x, y in zip(run(True), run(False)):
+        assert torch.equal(x, y)
+
+
+def test_store_and_embeddings_must_describe_the_same_chunks():
+    from rag_docvqa_b200.docstore import DocStore
+    batch = synth.make_text_batch("C2", with_lists=True, docs=4, seed=3)
+    table_w = synth.make_tokens_for_words(batch["words_text_chunks"], seed=9)
+    dev = torch.device(DEV)
+    store = DocStore.from_lists(batch["words_text_chunks"], batch["words_box_chunks"], batch["layout_labels_chunks"],
+                                batch["page_indices"], lambda w: table_w.get(w, [2]), dev)
+    idx = torch.empty((4, 5), dtype=torch.int32, device=dev)
+    cnt = torch.empty((4,), dtype=torch.int32, device=dev)
+    with pytest.raises(ValueError, match="same chunks"):
+        store.prepare_gather(idx, cnt, [[1]] * 4, sims=torch.zeros(store.n_chunks + 1, device=dev),
+                             topk_val=torch.empty((4, 5), device=dev))
+    assert store.same_chunks_as(batch["sizes"]) and not store.same_chunks_as(batch["sizes"][::-1])

@@ -18,14 +18,22 @@ pytestmark = pytest.mark.gpu
 TEXT_CASES = ["c1", "ragged_norm", "ragged_raw", "k20_d1024"]
 
 
-LDG, TMA, FUSED = 1, 2, 3
-ALGOS = [LDG, TMA, FUSED]
+LDG, TMA, CLUSTER = 1, 2, 3         # CLUSTER = the one-launch kernel (a thread-block cluster per document)
+ALGOS = [LDG, TMA, CLUSTER]
 
 
 def run_case(emb, q, k, tile_rows=0, algo=0):
+    """algo 0: what the product picks (rdv_score_plan + rdv_retrieve_plan); LDG / TMA: the two-launch path with that
+    streaming kernel; CLUSTER: the one-launch cluster kernel where its limits allow (k <= 32, documents <= 2048 rows),
+    else the product's choice."""
+    from rag_docvqa_b200 import _lib
     from rag_docvqa_b200 import functional as F
     dev = torch.device("cuda:0")
-    res = F.score_topk([e.to(dev) for e in emb], q.to(dev), k, tile_rows=tile_rows, algo=algo)
+    cluster = None if algo == 0 else False
+    if algo == CLUSTER:
+        fits = k <= _lib.lib.rdv_cluster_max_k() and max([e.shape[0] for e in emb] + [0]) <= _lib.lib.rdv_cluster_max_rows(8)
+        cluster, algo = (True if fits else None), 0
+    res = F.score_topk([e.to(dev) for e in emb], q.to(dev), k, tile_rows=tile_rows, algo=algo, cluster=cluster)
     torch.cuda.synchronize()
     return res
 
@@ -61,7 +69,7 @@ def test_golden_cases(golden_dir, name, algo):
     check_against_oracle(res, emb, q, k, ref_sims=ref)   # the reference's own frozen outputs
 
 
-@pytest.mark.parametrize("algo,tile_rows", [(LDG, 8), (LDG, 32), (LDG, 128), (FUSED, 8), (FUSED, 32), (FUSED, 200), (TMA, 1), (TMA, 5), (TMA, 8), (TMA, 16)])
+@pytest.mark.parametrize("algo,tile_rows", [(LDG, 8), (LDG, 32), (LDG, 128), (CLUSTER, 0), (TMA, 1), (TMA, 5), (TMA, 8), (TMA, 16)])
 @pytest.mark.parametrize("normalised", [True, False])
 def test_c2_full(algo, tile_rows, normalised):
     batch = synth.make_text_batch("C2", normalised=normalised)
@@ -73,6 +81,8 @@ def test_c2_full(algo, tile_rows, normalised):
 @pytest.mark.parametrize("k", [1, 5, 10, 20, 64])
 def test_k_sweep_with_duplicates(k, algo):
     sizes = [300, 17, 0, 64, 1, 1000, 3000, 4097, 8000]   # register (<=1024, <=4096), cached and L2 selection paths
+    if algo == CLUSTER:
+        sizes = [300, 17, 0, 64, 1, 1000, 1024, 1023, 33, 31, 32, 256, 257, 512, 513, 511]   # slices of <= 32 / 64 / 128 rows, edges
     emb, q = synth.make_embeddings(sizes, 384, 31 + k, dup_frac=0.2)
     res = run_case(emb, q, k, algo=algo)
     check_against_oracle(res, emb, q, k)
@@ -134,8 +144,8 @@ def test_workspace_left_clean_and_repeatable():
     a = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=TMA)
     b = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=TMA)
     c = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=LDG)
-    f1 = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=FUSED)
-    f2 = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=FUSED)   # counters were left zeroed
+    f1 = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=CLUSTER)
+    f2 = run_case(batch["text_embeddings"], batch["question_embeddings"], 5, algo=CLUSTER)
     assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_idx, c.topk_idx)
     assert torch.equal(a.topk_idx, f1.topk_idx) and torch.equal(f1.topk_idx, f2.topk_idx)
     assert torch.equal(a.sims, b.sims)          # deterministic: fixed summation order
@@ -156,6 +166,36 @@ def test_c3_slice_large_docs(algo):
     emb, q = synth.make_embeddings(sizes, 768, 5, dup_frac=0.01)
     res = run_case(emb, q, 10, algo=algo)
     check_against_oracle(res, emb, q, 10)
+
+
+@pytest.mark.parametrize("B", [1, 3, 97, 300])
+def test_cluster_kernel_equals_two_launches(B):
+    """Tiles packed into clusters (documents of 0 .. 2048 rows: padding CTAs, one tile per CTA, several tiles per CTA):
+    same answers as the two-launch path, bit for bit."""
+    sizes = [int(x) for x in np.random.RandomState(B).randint(0, 200, size=B)]
+    sizes[0] = 70
+    if B > 2:
+        sizes[1], sizes[2] = 1024, 513
+    emb, q = synth.make_embeddings(sizes, 256, 5 + B, dup_frac=0.1)
+    a = run_case(emb, q, 7, algo=CLUSTER)
+    b = run_case(emb, q, 7, algo=LDG)
+    check_against_oracle(a, emb, q, 7)
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_cnt, b.topk_cnt)
+    assert torch.equal(a.sims, b.sims) and torch.equal(a.topk_val, b.topk_val)
+
+
+def test_cluster_kernel_limits():
+    from rag_docvqa_b200 import _lib
+    from rag_docvqa_b200 import functional as F
+    dev = torch.device("cuda:0")
+    emb, q = synth.make_embeddings([3000, 10], 128, 3)
+    with pytest.raises(_lib.RdvError):              # a document above rdv_cluster_max_rows(): no cluster table was built
+        F.score_topk([e.to(dev) for e in emb], q.to(dev), 5, cluster=True)
+    emb, q = synth.make_embeddings([100, 10], 128, 3)
+    with pytest.raises(_lib.RdvError):              # k above rdv_cluster_max_k()
+        F.score_topk([e.to(dev) for e in emb], q.to(dev), 40, cluster=True)
+    res = F.score_topk([e.to(dev) for e in emb], q.to(dev), 40)      # the product's own choice falls back to two launches
+    check_against_oracle(res, emb, q, 40)
 
 
 def test_rejects_cpu_tensors():

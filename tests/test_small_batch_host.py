@@ -9,7 +9,7 @@ import torch
 
 from oracle import ref_restated as R
 from rag_docvqa_b200 import _lib, synth
-from rag_docvqa_b200.functional import TILE_DTYPE
+from rag_docvqa_b200.functional import CTA_DTYPE, TILE_DTYPE
 
 CASES = [([30], 384, 5), ([45, 0, 3], 384, 5), ([60, 0, 3, 150, 1, 90, 31], 768, 10), ([0, 0], 8, 1), ([700], 128, 40)]
 
@@ -29,16 +29,69 @@ def pack(sizes, d, k, seed=3):
     return emb, q, lay, h_blob[off:off + lay.in_bytes], fake_dev
 
 
+def check_cluster_table(ctas, sizes, row_off, srcs, cs, slice_rows=32):
+    """rdv_build_cluster_table: every document owns min(max(ceil(n / slice_rows), 1), cluster size) CONSECUTIVE CTAs of ONE
+    cluster, parts numbered from 0; everything else is padding (nparts == 0)."""
+    seen = {}
+    for i, c in enumerate(ctas):
+        if int(c["nparts"]) == 0:
+            continue
+        b = int(c["doc"])
+        seen.setdefault(b, []).append(i)
+        assert int(c["doc_rows"]) == sizes[b] and int(c["sims_off"]) == row_off[b] and int(c["src"]) == srcs[b]
+    assert sorted(seen) == [b for b in range(len(sizes))]
+    for b, where in seen.items():
+        want = min(max(-(-sizes[b] // slice_rows), 1), cs)
+        assert len(where) == want and where == list(range(where[0], where[0] + want))          # consecutive
+        assert where[0] // cs == where[-1] // cs                                                # one cluster
+        assert [int(ctas[i]["part"]) for i in where] == list(range(want))
+        assert all(int(ctas[i]["nparts"]) == want for i in where)
+
+
+@pytest.mark.parametrize("slice_rows", [32, 40, 64])
+@pytest.mark.parametrize("cs", [8, 16])
+def test_cluster_table_packing(cs, slice_rows):
+    rng = np.random.RandomState(4)
+    assert _lib.lib.rdv_cluster_max_rows(cs) == 4 * 32 * cs
+    for B in (1, 2, 7, 64, 300):
+        sizes = rng.randint(0, _lib.lib.rdv_cluster_max_rows(cs) + 1, size=B).astype(np.int64)
+        sizes[0] = 0
+        if B > 2:
+            sizes[1] = 600
+            sizes[2] = 32 * cs
+        n = _lib.lib.rdv_cluster_table_size(sizes.ctypes.data, B, cs, slice_rows)
+        assert n > 0 and n % cs == 0
+        slots = int(np.minimum(np.maximum(-(-sizes // slice_rows), 1), cs).sum())
+        assert n >= slots and n - slots < max(cs, 0.25 * slots + cs)          # best-fit decreasing wastes little
+        ctas = np.zeros(n, dtype=CTA_DTYPE)
+        srcs = [(0x10000 + 16 * b) if sizes[b] else 0 for b in range(B)]
+        ptrs = np.asarray(srcs, dtype=np.uint64)
+        _lib.check(_lib.lib.rdv_build_cluster_table(ptrs.ctypes.data, sizes.ctypes.data, B, 64, cs, slice_rows, ctas.ctypes.data, n))
+        row_off = np.concatenate([[0], np.cumsum(sizes)])
+        check_cluster_table(ctas, sizes.tolist(), row_off, srcs, cs, slice_rows)
+    big = np.asarray([_lib.lib.rdv_cluster_max_rows(cs) + 1], dtype=np.int64)
+    ptrs = np.asarray([0x10000], dtype=np.uint64)
+    ctas = np.zeros(cs, dtype=CTA_DTYPE)
+    assert _lib.lib.rdv_build_cluster_table(ptrs.ctypes.data, big.ctypes.data, 1, 64, cs, slice_rows, ctas.ctypes.data, cs) == _lib.E_LIMIT
+    assert _lib.lib.rdv_cluster_table_size(big.ctypes.data, 1, 12, 32) == -1                  # only clusters of 8 and 16 exist
+    assert _lib.lib.rdv_cluster_table_size(big.ctypes.data, 1, cs, 36) == -1                  # slices: multiples of 8 in [32, 64]
+
+
 @pytest.mark.parametrize("sizes,d,k", CASES)
 def test_layout_and_pack(sizes, d, k):
     emb, q, lay, blob, dev = pack(sizes, d, k)
     B, total = len(sizes), sum(sizes)
     assert lay.total_rows == total and lay.max_rows == max(sizes)
-    assert lay.algo == _lib.SCORE_LDG_FUSED and 1 <= lay.tile_rows <= 1024
+    cs, slice_rows = 8, 32                                                         # rdv_cluster_plan without a device
+    cluster = (max(sizes) <= _lib.lib.rdv_cluster_max_rows(8) and k <= _lib.lib.rdv_cluster_max_k()
+               and (total + B) * d * 4 <= (1 << 20))                                # rdv_retrieve_plan
+    assert lay.algo == (_lib.SMALL_CLUSTER if cluster else _lib.SCORE_LDG) and 1 <= lay.tile_rows <= 1024
     assert lay.n_tiles == sum(-(-n // lay.tile_rows) for n in sizes)
     # every part 16-byte aligned, parts in order and not overlapping
     assert lay.o_tiles % 32 == 0 and lay.o_q % 16 == 0 and lay.o_emb % 16 == 0
-    assert 8 * (B + 1) <= lay.o_tiles and lay.o_tiles + 32 * lay.n_tiles <= lay.o_q
+    assert 8 * (B + 1) <= lay.o_tiles and lay.o_tiles + 32 * lay.n_tiles <= lay.o_ctas and lay.o_ctas + 32 * lay.n_ctas == lay.o_q
+    assert (lay.n_ctas > 0) == cluster and lay.n_ctas % cs == 0
+    assert (lay.cluster, lay.slice_rows) == ((cs, slice_rows) if cluster else (0, 0))
     assert lay.o_q + B * d * 4 == lay.o_emb and lay.o_emb + total * d * 4 == lay.in_bytes
     assert lay.o_idx == total * 4 and lay.o_cnt == lay.o_idx + B * k * 4 and lay.read_bytes == lay.o_cnt + B * 4
     assert lay.o_val >= lay.read_bytes and lay.out_bytes == lay.o_val + B * k * 4
@@ -47,6 +100,9 @@ def test_layout_and_pack(sizes, d, k):
     assert np.array_equal(blob[lay.o_q:lay.o_emb].view(np.float32).reshape(B, d), q.numpy())
     rows = blob[lay.o_emb:].view(np.float32).reshape(total, d)
     tiles = blob[lay.o_tiles:lay.o_tiles + 32 * lay.n_tiles].view(TILE_DTYPE)
+    if cluster:
+        check_cluster_table(blob[lay.o_ctas:lay.o_ctas + 32 * lay.n_ctas].view(CTA_DTYPE), sizes, row_off,
+                            [dev + lay.o_emb + int(row_off[b_]) * d * 4 if sizes[b_] else 0 for b_ in range(B)], cs)
     seen = np.zeros(total, dtype=bool)
     prev = (-1, -1)
     for t in tiles:
@@ -84,7 +140,7 @@ def test_small_batch_argument_errors():
     # buffers smaller than the layout: RDV_SMALL_GROW before anything is touched (no CUDA call on this path)
     q = np.zeros((2, 384), dtype=np.float32)
     docs = (ctypes.c_void_p * 2)(q.ctypes.data, q.ctypes.data)
-    rc = lib.rdv_retrieve_small_f32(docs, rows, 2, 384, 5, q.ctypes.data, None, None, 0, None, 0, None, 0, None,
+    rc = lib.rdv_retrieve_small_f32(docs, rows, 2, 384, 5, q.ctypes.data, None, None, 0, None, 0, None, 0,
                                     ctypes.addressof(lay), None)
     assert rc == _lib.SMALL_GROW and lay.in_bytes > 0 and lay.out_bytes > lay.read_bytes > 0
     assert lib.rdv_small_batch_pack(docs, rows, 2, 384, q.ctypes.data, ctypes.addressof(lay), None, None) == _lib.E_INVALID
@@ -114,8 +170,7 @@ def test_retriever_small_path_host_logic_with_emulated_device(monkeypatch):
         grown.append((n_in, n_dev, n_host))
         c_in, c_dev, c_host = (max(2 * n, 1 << 12) for n in (n_in, n_dev, n_host))      # small start: the grow loop runs
         bufs = (torch.empty(c_in, dtype=torch.uint8), torch.empty(c_in, dtype=torch.uint8),
-                torch.empty(c_dev, dtype=torch.uint8), torch.empty(c_host, dtype=torch.uint8),
-                torch.zeros(4096, dtype=torch.int32))
+                torch.empty(c_dev, dtype=torch.uint8), torch.empty(c_host, dtype=torch.uint8))
         bufs = bufs + tuple(t.data_ptr() for t in bufs) + (bufs[3].numpy(),)
         self._small_bufs[dev.index] = bufs
         return bufs
@@ -132,7 +187,7 @@ def test_retriever_small_path_host_logic_with_emulated_device(monkeypatch):
             return getattr(real, name)
 
         def rdv_retrieve_small_f32(self, h_docs, rows, B, d, k, h_q, h_blob, d_blob, blob_bytes, d_out, d_out_bytes, h_out,
-                                   h_out_bytes, d_done, lay_p, stream):
+                                   h_out_bytes, lay_p, stream):
             lay = _lib.SmallLayoutStruct.from_address(lay_p)
             rc = real.rdv_small_batch_layout(rows, B, d, k, lay_p)
             if rc:

@@ -99,3 +99,48 @@ def test_maxsim_bf16_tc(n, Lq, Lp, d):
     np.testing.assert_allclose(got, ref, rtol=5e-3)
     fp32 = F.late_interaction(q.to(DEV), p.to(DEV)).cpu().numpy()
     assert (np.argsort(-got)[:1] == np.argsort(-fp32)[:1]).all() or n < 2
+
+
+def test_corpus_searcher_graph_equals_search_local():
+    """CorpusSearcher (static buffers, the step captured into one CUDA graph) returns exactly what the eager calls do,
+    call after call, and its merge over the receive layout (rdv_topk_merge_parts) equals the unsharded answer."""
+    from rag_docvqa_b200 import _lib, sharded
+    g = torch.Generator().manual_seed(9)
+    n, d, Qn, k, world = 9000, 256, 130, 10, 4
+    E = torch.randn(n, d, generator=g)
+    E[8000] = E[10]                                   # a cross-shard exact tie
+    full = sharded.CorpusShard.from_f32(E.to(DEV))
+    searcher = sharded.CorpusSearcher(full, Qn, k, graph=True)
+    assert searcher.graphed
+    for seed in (1, 2, 3):
+        Q = torch.randn(Qn, d, generator=torch.Generator().manual_seed(seed)).to(DEV)
+        v_ref, i_ref = full.search_local(Q, k)
+        v, i = searcher.search(Q)
+        assert torch.equal(i, i_ref) and torch.equal(v, v_ref)
+    # ranks emulated as slices on one GPU: each rank's searcher fills its send buffer; the receive buffer is their
+    # concatenation in rank order, exactly what ncclAllGather writes
+    sends = []
+    for r in range(world):
+        lo, hi = sharded.shard_bounds(n, world, r)
+        s_r = sharded.CorpusSearcher(sharded.CorpusShard.from_f32(E[lo:hi].to(DEV), id_offset=lo), Qn, k, graph=(r % 2 == 0))
+        s_r.local_only(Q)
+        sends.append(s_r.send.clone())
+        nv, stride = s_r.nv, s_r.send.numel()
+    recv = torch.stack(sends).contiguous()
+    out_v = torch.empty((Qn, k), dtype=torch.float32, device=DEV)
+    out_i = torch.empty((Qn, k), dtype=torch.int64, device=DEV)
+    _lib.check(_lib.lib.rdv_topk_merge_parts(recv.data_ptr(), recv.data_ptr() + nv, Qn, world, k, stride // 4, stride // 8, k,
+                                             out_v.data_ptr(), out_i.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(out_i, i_ref) and torch.equal(out_v, v_ref)
+
+
+def test_corpus_searcher_empty_shard():
+    """A rank that owns no rows (N < world) still takes part: its contribution is 'no candidates'."""
+    from rag_docvqa_b200 import sharded
+    empty = sharded.CorpusShard(torch.empty((0, 64), dtype=torch.bfloat16, device=DEV), id_offset=5)
+    s = sharded.CorpusSearcher(empty, 7, 3, graph=True)
+    v, i = s.search(torch.randn(7, 64, device=DEV))
+    assert (i == -1).all() and torch.isneginf(v).all()
+    v2, i2 = empty.search_local(torch.randn(7, 64, device=DEV), 3)
+    assert (i2 == -1).all() and torch.isneginf(v2).all()
