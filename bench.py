@@ -174,6 +174,8 @@ def run_reference(args):
         return run_reference_corpus(args)
     if args.workload == "C4":
         return run_reference_visual(args)
+    if args.workload == "C4p":
+        return run_reference_pooled(args)
     w = synth.WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -229,6 +231,36 @@ def run_reference_corpus(args):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": "oracle corpus_scores + torch.topk on a 1/64 row slice (%d rows) per step, time x64" % n_cpu},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_reference_pooled(args):
+    """CPU arm of C4p: the oracle's pooled-patch scores (the reference's mean_pooling + cosine, torch CPU ops) + torch.topk,
+    one document per step."""
+    from oracle import ref_restated as R
+    from rag_docvqa_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    strips, L, d, k = 50, 2048, 768, 5
+    patches, q = synth.make_strip_batch(1, [strips], L, d, synth_seed(4))
+
+    def step():
+        sims, strip_scores, _ = R.pooled_patch_scores(patches, q)
+        return torch.topk(sims[0], k), torch.topk(strip_scores[0], k)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": 1.0 / dt, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": pooled_config(args.visual_docs, strips, L, d, k),
+        "cpu_baseline": {"value": 1.0 / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": "oracle pooled_patch_scores + torch.topk on one document per step"},
+        "e2e": {"value": 1.0 / dt, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
@@ -1176,6 +1208,105 @@ def run_visual(args):
         dist.destroy_process_group()
 
 
+def pooled_config(B, strips, L, d, k):
+    return {"workload": "C4p: %d questions x %d strips x %d patch vectors x %d-d, pooled question, cosine of every patch "
+                        "vector, top-k=%d patches and strips" % (B, strips, L, d, k),
+            "l2": "inputs larger than L2 (%.0f MB of patch vectors per document)" % (strips * L * d * 4 / 1e6),
+            "parallelism": CONFIG_PAR}
+
+
+def run_pooled(args):
+    """C4p (north_star's wording of configs[3]): every patch vector of 50 strips (102 400 x 768 fp32 = 315 MB per
+    document) scored against the mean-pooled question, top-k patches, strips ranked by their best patch.  A step = one batch
+    of B questions through functional.pooled_patch_topk (pool, streaming score, group max, two segmented top-k)."""
+    from rag_docvqa_b200 import functional as F
+    from rag_docvqa_b200 import synth
+    ctx = Ctx()
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    hbm_peak, _, peak_kind = measured_peaks()
+    B, strips, L, d, k = args.visual_docs, 50, 2048, 768, 5
+    patches, q = synth.make_strip_batch(B, [strips] * B, L, d, synth_seed(4) + 1000 * rank, device=dev)
+    torch.cuda.synchronize()
+
+    def step(i):
+        return F.pooled_patch_topk(patches, q, k)
+    flat = [p.reshape(-1, d) for p in patches]
+    table = F.build_doc_table(flat, d, dev)
+    q_pooled = step(0).question
+    sims = torch.empty(table.total_rows, dtype=torch.float32, device=dev)
+    warmup = max(3, args.warmup)
+    steps = max(1, min(args.steps, 20))
+    for i in range(warmup):
+        step(i)
+        F.score_table(table, q_pooled, out=sims)
+    with ClockSampler(ctx.local) as clocks:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ctx.barrier()
+        ev[0].record()
+        for i in range(steps):
+            step(i)
+            ev[i + 1].record()
+        ctx.barrier()
+        per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
+        ms_kernel = timed_loop(lambda i: F.score_table(table, q_pooled, out=sims), steps, ctx.barrier) / steps
+    per_rank = ctx.all_ranks(float(np.median(per)))
+    ms_per_step = max(per_rank)
+    ms_kernel = ctx.maxr(ms_kernel)
+    n_rows = B * strips * L
+    kernel_bytes = n_rows * d * 4 + B * d * 4 + n_rows * 4
+    step_bytes_total = kernel_bytes + B * L * d * 4 + B * L * 8
+
+    host_p = [x.cpu().pin_memory() for x in patches[:2]]
+    host_q = q[:2].cpu().pin_memory()
+
+    def e2e_step():
+        res = F.pooled_patch_topk([x.to(dev, non_blocking=True) for x in host_p], host_q.to(dev, non_blocking=True), k)
+        return res.patch_idx.cpu(), res.strip_idx.cpu()
+    e2e_step()
+    ctx.barrier()
+    e2e_steps = 3
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = ctx.maxr(time.perf_counter() - t0)
+    line = {
+        "metric": METRIC, "value": B * world / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": pooled_config(B, strips, L, d, k),
+        "timing": {"what": "a step = one batch of %d questions through functional.pooled_patch_topk: mean pooling of the question "
+                           "tokens, streaming cosine of every patch vector, top-k patches, best patch per strip, top-k strips "
+                           "(5 launches); CUDA events around every step, median, max over ranks" % B,
+                   "per_rank_ms_per_step": per_rank},
+        "roofline": {"bound": "hbm", "achieved": kernel_bytes / (ms_kernel * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": kernel_bytes / (ms_kernel * 1e-3) / 1e9 / hbm_peak, "peak_kind": peak_kind, "traffic": None,
+                     "kernel": "score_ldg_kernel (rdv_score_f32)", "algorithmic_bytes_per_launch": kernel_bytes,
+                     "ms_per_launch": ms_kernel,
+                     "how": "the streaming kernel alone, back-to-back launches, CUDA events, max over ranks",
+                     "step_frac_hbm": step_bytes_total / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
+        "e2e": {"value": 2 * world * e2e_steps / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": sum(x.numel() * 4 for x in host_p) + host_q.numel() * 4,
+                "d2h_bytes_per_step": 2 * 2 * k * 4, "ms_per_step": e2e_dt / e2e_steps * 1e3,
+                "api": "rag_docvqa_b200.functional.pooled_patch_topk (pinned host token matrices of 2 documents in, hit indices out)"},
+        "gpu_launches": steps * 5, "clocks": clocks.summary(),
+    }
+    if rank == 0 and world == 1:
+        from oracle import ref_restated as R
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        pc, qc = [patches[0].cpu()], q[0:1].cpu()
+
+        def cpu_fn():
+            sims_c, strips_c, _ = R.pooled_patch_scores(pc, qc)
+            return torch.topk(sims_c[0], k), torch.topk(strips_c[0], k)
+        best, reps = time_cpu(cpu_fn, min(args.cpu_seconds, 10.0), min_reps=1)
+        line["cpu_baseline"] = {"value": 1.0 / best, "unit": "queries/s", "cores": threads, "kind": "port",
+                                "sample": "oracle pooled_patch_scores (torch CPU: mean pooling + cosine of 102 400 patch vectors + "
+                                          "strip max) + torch.topk on ONE document, best of %d reps" % reps}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+
+
 def visual_config(B, strips, L, d, k):
     return {"workload": "C4: %d questions x %d strips x (%d x %d) tokens, MaxSim late interaction, top-k=%d" % (B, strips, L, d, k),
             "l2": "inputs larger than L2 (%.0f MB of strip tokens per document)" % (strips * L * d * 4 / 1e6),
@@ -1193,7 +1324,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C4p", "C5"])
     ap.add_argument("--visual-docs", type=int, default=8)
     ap.add_argument("--corpus-rows", type=int, default=10_000_000)
     ap.add_argument("--corpus-queries", type=int, default=1024)
@@ -1218,6 +1349,8 @@ def main():
         run_corpus(args)
     elif args.workload == "C4":
         run_visual(args)
+    elif args.workload == "C4p":
+        run_pooled(args)
     else:
         run_ours(args)
 

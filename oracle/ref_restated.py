@@ -194,6 +194,26 @@ def mean_pooling(embs: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tens
 # --------------------------------------------------------------------------------------
 # a5: MaxSim late interaction   reference: src/utils.py:442-458, src/_modules.py:2191-2205
 # --------------------------------------------------------------------------------------
+def pooled_patch_scores(patch_embeddings: Sequence[torch.Tensor], question_embeddings: torch.Tensor,
+                        question_mask: torch.Tensor = None):
+    """Pooled-patch visual retrieval, composed from the reference's own functions: the question tokens through
+    mean_pooling (src/_model_utils.py:49-61), every patch vector of every strip through Retriever._get_similarities
+    (src/_modules.py:1978-1997), a strip scored by torch.max over its patches.  Returns (per-document patch similarities
+    (n_b * L,), per-document strip scores (n_b,), pooled questions (B, d))."""
+    B = len(patch_embeddings)
+    if question_mask is None:
+        question_mask = torch.ones(question_embeddings.shape[:2], dtype=torch.int64)
+    q = mean_pooling(question_embeddings, question_mask)
+    d = question_embeddings.shape[2]
+    flat = [p.reshape(-1, d) for p in patch_embeddings]
+    sims = score(flat, q)
+    strips = []
+    for b in range(B):
+        n = patch_embeddings[b].shape[0]
+        strips.append(sims[b].reshape(n, -1).max(dim=1).values if n else torch.empty(0))
+    return sims, strips, q
+
+
 def late_interaction(query: torch.Tensor, patches: torch.Tensor) -> torch.Tensor:
     qn = F.normalize(query, p=2, dim=-1)                                # :445
     pn = F.normalize(patches, p=2, dim=-1)                              # :446

@@ -67,6 +67,19 @@ class Chunker(StatComponent):
         assert self.overlap < self.chunk_size, "overlap should be less than chunk_size."
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def compact_chunks(words_text_chunks: list, words_boxes_chunks: list) -> tuple:
+        """Static on the class, as in the reference (src/_modules.py:1102-1132): src/RAGVT5.py:224 calls
+        `Chunker.compact_chunks(...)` on the NAME, so a drop-in class must carry it.  [B][n][w] words / boxes ->
+        [B][n] joined text and [B][n][4] bounding box ([0, 0, 1, 1] for a chunk without words)."""
+        from .retriever import compact_chunk
+        text_chunks, boxes_chunks = [], []
+        for doc_words, doc_boxes in zip(words_text_chunks, words_boxes_chunks):
+            pairs = [compact_chunk(w, bx) for w, bx in zip(doc_words, doc_boxes)]
+            text_chunks.append([t for t, _ in pairs])
+            boxes_chunks.append([bb for _, bb in pairs])
+        return text_chunks, boxes_chunks
+
     def assign_words_to_layouts(self, page_boxes: List[np.ndarray], layout_boxes: List[np.ndarray],
                                 layout_labels: List[np.ndarray], default_label: int = -1):
         """One launch for a list of pages.  page_boxes[i] (n_i,4) float64 word boxes, layout_boxes[i] (l_i,4) float64 in

@@ -290,6 +290,65 @@ def mean_pooling(embs: torch.Tensor, attention_mask: torch.Tensor, normalise: bo
 
 
 # ------------------------------------------------------------------------------------------------
+# pooled-patch visual retrieval (north_star's wording of BASELINE.json configs[3])
+# ------------------------------------------------------------------------------------------------
+class PooledPatchTopK(NamedTuple):
+    similarities: List[torch.Tensor]   # List[B] of (n_b * L,) fp32: cosine of every patch vector, strip-major
+    patch_idx: torch.Tensor            # (B, k) int32 flat patch index (strip * L + patch), -1 padded, rank order
+    patch_val: torch.Tensor            # (B, k) fp32
+    patch_cnt: torch.Tensor            # (B,) int32
+    strip_scores: List[torch.Tensor]   # List[B] of (n_b,) fp32: best patch of every strip
+    strip_idx: torch.Tensor            # (B, k_strips) int32 strip index, -1 padded, rank order
+    strip_val: torch.Tensor
+    strip_cnt: torch.Tensor
+    question: torch.Tensor             # (B, d) fp32 pooled question vectors
+
+
+def pooled_patch_topk(patch_embeddings: Sequence[torch.Tensor], question_embeddings: torch.Tensor, k: int,
+                      question_mask: torch.Tensor = None, k_strips: int = None) -> PooledPatchTopK:
+    """Pooled-patch retrieval over page strips: the question's encoder tokens are mean-pooled (mean_pooling,
+    src/_model_utils.py:49-61; all tokens when no mask is given), EVERY patch vector of every strip -- the (n_b, L, d)
+    encoder outputs ImageEncoder returns (src/_modules.py:1627-1666), 102 400 vectors for 50 strips -- is scored against it with
+    Retriever._get_similarities' cosine (src/_modules.py:1990-1993: eps on the product of the norms), the k best patches per
+    document are selected, a strip is scored by its best patch and the k_strips best strips are selected (torch.topk,
+    src/_modules.py:2408; lowest index first on ties).  One pooling launch, the streaming score kernel over all documents,
+    two segmented top-k launches and one group-max launch; every patch vector is read from HBM exactly once."""
+    _require_cuda(question_embeddings, "question_embeddings")
+    device = question_embeddings.device
+    B = len(patch_embeddings)
+    if question_embeddings.dim() != 3 or question_embeddings.shape[0] != B:
+        raise ValueError("pooled_patch_topk: question_embeddings must be (B, Lq, d) with B == len(patch_embeddings)")
+    d = question_embeddings.shape[2]
+    if question_mask is None:
+        question_mask = torch.ones(question_embeddings.shape[:2], dtype=torch.int64, device=device)
+    k_strips = int(k if k_strips is None else k_strips)
+    with torch.cuda.device(device):
+        q = mean_pooling(question_embeddings, question_mask)                       # (B, d)
+        L = None
+        flat, n_strips = [], []
+        for b, p in enumerate(patch_embeddings):
+            if p.dim() != 3 or p.shape[2] != d:
+                raise ValueError("pooled_patch_topk: document %d: expected (n, L, %d) patch embeddings, got %s" % (b, d, tuple(p.shape)))
+            if p.shape[0]:
+                _require_cuda(p, "patch_embeddings[%d]" % b)
+                if L is None:
+                    L = int(p.shape[1])
+                elif int(p.shape[1]) != L:
+                    raise ValueError("pooled_patch_topk: strips of %d and %d patches in one batch" % (L, int(p.shape[1])))
+            n_strips.append(int(p.shape[0]))
+            flat.append(_f32_contig_aligned(p).reshape(-1, d))                     # a view: nothing is copied
+        L = L or 1
+        res = score_topk(flat, q, int(k), cluster=False)
+        total_strips = sum(n_strips)
+        strip_flat = torch.empty(max(total_strips, 1), dtype=torch.float32, device=device)
+        if total_strips:
+            _lib.check(_lib_fn.rdv_group_max_f32(res.sims.data_ptr(), total_strips, L, strip_flat.data_ptr(), _stream_ptr(device)))
+        strip_scores = list(torch.split(strip_flat[:total_strips], n_strips))
+        s_idx, s_val, s_cnt = topk_segments(strip_scores, k_strips) if B else (None, None, None)
+    return PooledPatchTopK(res.similarities, res.topk_idx, res.topk_val, res.topk_cnt, strip_scores, s_idx, s_val, s_cnt, q)
+
+
+# ------------------------------------------------------------------------------------------------
 # MaxSim late interaction (a5)
 # ------------------------------------------------------------------------------------------------
 def split_tf32(x: torch.Tensor, normalise: bool = False):

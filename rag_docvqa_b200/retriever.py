@@ -560,12 +560,17 @@ def _merge_rectangles(rects: List[Sequence[float]]) -> List[List[float]]:
 
 
 class VisualRetriever:
-    def __init__(self, config: dict):
+    def __init__(self, config: dict, score: Optional[str] = None):
         self.k = config.get("chunk_num", 10)
         self.include_surroundings = config.get("include_surroundings", 0)
         self.mode = config.get("chunk_mode", "horizontal")
         self.layout_map = get_layout_model_map(config)
         self.device = _device_of(config)
+        # optional key / argument (the default is the reference's MaxSim late interaction): "pooled" scores a strip by the
+        # best cosine of its patch vectors against the mean-pooled question (functional.pooled_patch_topk)
+        self.score = score or config.get("visual_score", "maxsim")
+        if self.score not in ("maxsim", "pooled"):
+            raise ValueError("VisualRetriever: visual_score must be 'maxsim' or 'pooled', got %r" % (self.score,))
 
     def _get_similarities(self, patch_embeddings: List[torch.Tensor], question_embeddings: torch.Tensor):
         """MaxSim of question i against the strips of document i (src/_modules.py:2191-2205).  Documents alternate
@@ -574,6 +579,8 @@ class VisualRetriever:
         dev = question_embeddings.device if question_embeddings.is_cuda else self.device
         q = _to_device(question_embeddings, dev)
         n_docs = len(patch_embeddings)
+        if self.score == "pooled":
+            return F.pooled_patch_topk([_to_device(p, dev) for p in patch_embeddings], q, int(self.k)).strip_scores
         if n_docs < 2:
             return [F.late_interaction(q[i].unsqueeze(0), _to_device(patch_embeddings[i], dev)) for i in range(n_docs)]
         if getattr(self, "_side_streams", None) is None or self._side_streams[0].device != dev:

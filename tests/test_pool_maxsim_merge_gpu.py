@@ -139,3 +139,68 @@ def test_topk_merge_equals_unsharded(world, k):
     np.testing.assert_array_equal(out_v.cpu().numpy(), ref_v)
     for qi in range(1, Q):                                      # equals the unsharded selection
         np.testing.assert_array_equal(out_i[qi].cpu().numpy(), R.topk_lowest_index(scores[qi], k))
+
+
+def test_pooled_patch_golden(golden_dir):
+    """pooled_patch_topk (pool -> cosine of every patch vector -> top-k patches, strip max -> top-k strips) against what the
+    reference's own mean_pooling + Retriever._get_similarities + torch.max / torch.topk produced."""
+    from rag_docvqa_b200 import functional as F
+    z = np.load(os.path.join(golden_dir, "pooled_patch.npz"))
+    n_docs, k = int(z["n_docs"]), int(z["k"])
+    patches = [torch.from_numpy(z["patches_%d" % b]).to(DEV) for b in range(n_docs)]
+    q, mask = torch.from_numpy(z["q"]).to(DEV), torch.from_numpy(z["mask"]).to(DEV)
+    res = F.pooled_patch_topk(patches, q, k, question_mask=mask)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(res.question.cpu().numpy(), z["pooled"], rtol=1e-5, atol=1e-6)
+    p_idx, p_cnt = res.patch_idx.cpu().numpy(), res.patch_cnt.cpu().numpy()
+    s_idx, s_cnt = res.strip_idx.cpu().numpy(), res.strip_cnt.cpu().numpy()
+    for b in range(n_docs):
+        ref, own = z["sims_%d" % b], res.similarities[b].cpu().numpy()
+        compare.assert_scores_close(own, ref, what="doc %d patch sims" % b)
+        kb = min(k, len(ref))
+        assert p_cnt[b] == kb and (p_idx[b, kb:] == -1).all()
+        compare.assert_topk_matches(p_idx[b, :kb], own, ref, k, what="doc %d patches" % b)
+        sref, sown = z["strip_%d" % b], res.strip_scores[b].cpu().numpy()
+        compare.assert_scores_close(sown, sref, what="doc %d strip scores" % b)
+        n = len(sref)
+        if n:
+            np.testing.assert_array_equal(sown, own.reshape(n, -1).max(axis=1))          # exactly the best patch of the strip
+        ks = min(k, n)
+        assert s_cnt[b] == ks and (s_idx[b, ks:] == -1).all()
+        compare.assert_topk_matches(s_idx[b, :ks], sown, sref, k, what="doc %d strips" % b)
+
+
+def test_pooled_patch_c4_shape_and_nan():
+    """One document at C4 strip shape (8 strips x 2048 patches x 768) against the oracle; a NaN patch makes its strip NaN
+    (torch.max) and therefore the best strip (torch.topk: NaN greatest)."""
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(4)
+    patches = [torch.randn(8, 2048, 768, generator=g), torch.randn(3, 2048, 768, generator=g)]
+    patches[1][2, 100, 5] = float("nan")
+    q = torch.randn(2, 2048, 768, generator=g)
+    sims, strips, _ = R.pooled_patch_scores(patches, q)
+    res = F.pooled_patch_topk([p.to(DEV) for p in patches], q.to(DEV), 5, k_strips=2)
+    for b in range(2):
+        own = res.similarities[b].cpu().numpy()
+        compare.assert_scores_close(own, sims[b].numpy())
+        compare.assert_topk_matches(res.patch_idx[b].cpu().numpy()[:5], own, sims[b].numpy(), 5)
+    assert np.isnan(res.strip_scores[1].cpu().numpy()[2]) and res.strip_idx.cpu().numpy()[1, 0] == 2
+    compare.assert_scores_close(res.strip_scores[0].cpu().numpy(), strips[0].numpy())
+    assert res.strip_idx.shape == (2, 2)
+
+
+def test_visual_retriever_pooled_score():
+    """VisualRetriever(config, score='pooled'): the strips the decode receives are ranked by the pooled-patch score."""
+    from PIL import Image
+    from rag_docvqa_b200.retriever import VisualRetriever
+    g = torch.Generator().manual_seed(9)
+    n, L, d = 6, 64, 32
+    patches = [torch.randn(n, L, d, generator=g)]
+    q = torch.randn(1, 16, d, generator=g)
+    _, strips, _ = R.pooled_patch_scores(patches, q)
+    want = sorted(R.topk_lowest_index(strips[0], 2).tolist())
+    pages = [[Image.new("RGB", (40, 30), (i, 0, 0)) for i in range(n)]]
+    vr = VisualRetriever({"chunk_num": 2, "include_surroundings": 0, "chunk_mode": "horizontal", "device": DEV}, score="pooled")
+    crops, page_ids = vr.retrieve([p.to(DEV) for p in patches], q.to(DEV), [np.arange(n)], [[[[pages[0][i]]] for i in range(n)]],
+                                  [[[[0, 0, 40, 30]] for i in range(n)]], pages)
+    assert page_ids[0] == want and len(crops[0]) == 2

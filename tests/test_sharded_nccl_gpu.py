@@ -25,20 +25,26 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
-for N, d, Q, k in ((200_000, 256, 300, 10), (3, 64, 9, 5)):          # the second corpus leaves ranks without rows
+def say(*a):
+    print("[rank %d]" % rank, *a, flush=True)
+# scenario 1: rows sharded evenly; scenario 2: rank 0 owns every row, the other ranks own EMPTY shards (N < world in miniature)
+for scenario, (N, d, Q, k) in enumerate(((200_000, 256, 300, 10), (5_000, 64, 9, 5))):
     g = torch.Generator(device="cpu").manual_seed(5)
     E = (torch.randn(N, d, generator=g) + 0.3).to(torch.bfloat16)
-    if N > 100:
-        E[N - 7] = E[11]                                             # a cross-shard exact tie
-    lo, hi = sharded.shard_bounds(N, world, rank)
+    E[N - 7] = E[11]                                                 # an exact tie (across shards in scenario 1)
+    lo, hi = sharded.shard_bounds(N, world, rank) if scenario == 0 else ((0, N) if rank == 0 else (N, N))
     shard = sharded.CorpusShard(E[lo:hi].to(dev).contiguous(), id_offset=lo)
     whole = sharded.CorpusShard(E.to(dev).contiguous())
+    say("scenario", scenario, "rows", lo, hi)
     searcher = sharded.CorpusSearcher(shard, Q, k, graph=True)
+    say("searcher built, graphed =", searcher.graphed)
     for seed in (1, 2):
         Qs = torch.randn(Q, d, generator=torch.Generator(device="cpu").manual_seed(seed)).to(dev)
         ref_v, ref_i = whole.search_local(Qs, k)
         v1, i1 = sharded.search(shard, Qs, k)
         v2, i2 = searcher.search(Qs)
+        torch.cuda.synchronize()
+        say("seed", seed, "done")
         ok = ok and torch.equal(i1, ref_i) and torch.equal(v1, ref_v) and torch.equal(i2, ref_i) and torch.equal(v2, ref_v)
     ok = ok and (searcher.graphed or world == 1)
 flag = torch.tensor([1 if ok else 0], device=dev)
@@ -62,6 +68,11 @@ def test_sharded_search_over_nccl_equals_unsharded(tmp_path):
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(port), str(script)]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    try:
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240,
+                             env={**os.environ, "NCCL_DEBUG": "WARN"})
+    except subprocess.TimeoutExpired as exc:                          # a hang: show how far the ranks got
+        out = exc.stdout.decode("utf-8", "replace") if isinstance(exc.stdout, bytes) else (exc.stdout or "")
+        pytest.fail("the NCCL workers did not finish in 240 s; their output so far:\n" + out[-4000:])
     assert res.returncode == 0, res.stdout[-3000:]
     assert "sharded == unsharded on %d ranks: True" % world in res.stdout

@@ -150,74 +150,9 @@ def test_retriever_small_path_host_logic_with_emulated_device(monkeypatch):
     """The Python half of Retriever._retrieve_host_small without a GPU: buffers are host tensors, the device round trip of
     rdv_retrieve_small_f32 is emulated (real layout + pack, a memmove for each copy, the oracle in place of the kernel),
     so the pointer bookkeeping, the RDV_SMALL_GROW loop, the result offsets and the list building are exercised on CPU."""
-    import contextlib
-
-    from rag_docvqa_b200 import functional as F
-    from rag_docvqa_b200 import retriever as RM
     from rag_docvqa_b200.retriever import Retriever
-
-    class Stream:
-        cuda_stream = 0
-
-        def synchronize(self):
-            pass
-
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: Stream())
-    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
-    grown = []
-
-    def host_buffers(self, dev, n_in, n_dev, n_host):
-        grown.append((n_in, n_dev, n_host))
-        c_in, c_dev, c_host = (max(2 * n, 1 << 12) for n in (n_in, n_dev, n_host))      # small start: the grow loop runs
-        bufs = (torch.empty(c_in, dtype=torch.uint8), torch.empty(c_in, dtype=torch.uint8),
-                torch.empty(c_dev, dtype=torch.uint8), torch.empty(c_host, dtype=torch.uint8))
-        bufs = bufs + tuple(t.data_ptr() for t in bufs) + (bufs[3].numpy(),)
-        self._small_bufs[dev.index] = bufs
-        return bufs
-
-    monkeypatch.setattr(Retriever, "_small_buffers", host_buffers)
-
-    def view(ptr, n, dt):
-        return np.frombuffer((ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt)
-
-    real = _lib.lib
-
-    class EmulatedLib:
-        def __getattr__(self, name):
-            return getattr(real, name)
-
-        def rdv_retrieve_small_f32(self, h_docs, rows, B, d, k, h_q, h_blob, d_blob, blob_bytes, d_out, d_out_bytes, h_out,
-                                   h_out_bytes, lay_p, stream):
-            lay = _lib.SmallLayoutStruct.from_address(lay_p)
-            rc = real.rdv_small_batch_layout(rows, B, d, k, lay_p)
-            if rc:
-                return rc
-            if lay.in_bytes > blob_bytes or lay.out_bytes > d_out_bytes or lay.read_bytes > h_out_bytes:
-                return _lib.SMALL_GROW
-            rc = real.rdv_small_batch_pack(h_docs, rows, B, d, h_q, lay_p, h_blob, d_blob)
-            if rc:
-                return rc
-            ctypes.memmove(d_blob, h_blob, lay.in_bytes)                                 # "upload"
-            row = view(d_blob, B + 1, np.int64)
-            q = view(d_blob + lay.o_q, B * d, np.float32).reshape(B, d)
-            tiles = view(d_blob + lay.o_tiles, lay.n_tiles, TILE_DTYPE)
-            sims = view(d_out, max(int(row[-1]), 1), np.float32)
-            idx = view(d_out + lay.o_idx, B * k, np.int32).reshape(B, k)
-            cnt = view(d_out + lay.o_cnt, B, np.int32)
-            for b in range(B):
-                n = int(row[b + 1] - row[b])
-                if n:
-                    first = [t for t in tiles if int(t["doc"]) == b][0]                  # rows of a document are contiguous
-                    e = view(int(first["src"]), n * d, np.float32).reshape(n, d)
-                    sims[row[b]:row[b + 1]] = R.score([torch.from_numpy(e.copy())], torch.from_numpy(q[b:b + 1].copy()))[0].numpy()
-                hits = R.topk_lowest_index(sims[row[b]:row[b + 1]], k)
-                idx[b] = -1
-                idx[b, :len(hits)] = hits
-                cnt[b] = len(hits)
-            ctypes.memmove(h_out, d_out, lay.read_bytes)                                 # "read-back"
-            return 0
-
-    monkeypatch.setattr(F, "_lib_fn", EmulatedLib())
+    import _emulated_device
+    grown = _emulated_device.install(monkeypatch, small_start=True)
     base = {"compute_stats": False, "compute_stats_examples": False, "n_stats_examples": 0, "device": "cuda:0"}
     for sizes in ([30], [45, 0, 3], [60, 0, 3, 150, 1, 90, 31], [0, 0]):
         docs = len(sizes)
