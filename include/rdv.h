@@ -219,12 +219,6 @@ RDV_API int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_of
 
 
 
-/* Maximum of consecutive groups of group_len scores: d_out[g] = max(d_scores[g * group_len .. + group_len)), NaN if the group
- * holds one (torch.max).  The strip score of pooled-patch visual retrieval (BASELINE.json configs[3] in north_star's wording:
- * every patch vector of a strip scored by the cosine of src/_modules.py:1990-1993 against the pooled question, a strip ranked
- * by its best patch, torch.topk over the strips :2408). */
-RDV_API int rdv_group_max_f32(const float* d_scores, int64_t n_groups, int32_t group_len, float* d_out, void* stream);
-
 /* ---------------------------------------------------------------------------------------------
  * Masked mean pooling of encoder token outputs (+ optional fused L2 normalisation / bf16 copy).
  *

@@ -51,6 +51,46 @@ class _Workspace:
         return buf
 
 
+class EmbeddingCache:
+    """Device copies of HOST document embeddings, kept between calls (least recently used first out): MP-DocVQA asks many
+    questions about one document, and a read-once streaming op cannot win across PCIe -- the second question about a
+    document should not cross it again.  A document is recognised by its tensor's storage address, shape, dtype and version
+    counter (in-place torch writes bump it; writes through numpy views do not -- callers that do that must not use the
+    cache)."""
+
+    def __init__(self, budget_bytes: int, device):
+        from collections import OrderedDict
+        self.budget, self.device = int(budget_bytes), torch.device(device)
+        self.entries = OrderedDict()
+        self.bytes = 0
+        self.hits = self.misses = 0
+
+    def resident(self, host_docs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        out = []
+        for e in host_docs:
+            if e.is_cuda or e.shape[0] == 0:
+                out.append(e if e.is_cuda else e.to(self.device))
+                continue
+            key = (e.data_ptr(), tuple(e.shape), e.dtype, e._version)
+            hit = self.entries.get(key)
+            if hit is not None:
+                self.entries.move_to_end(key)
+                self.hits += 1
+                out.append(hit)
+                continue
+            self.misses += 1
+            t = e.to(self.device, non_blocking=True)
+            nbytes = t.numel() * t.element_size()
+            if nbytes <= self.budget:
+                self.entries[key] = t
+                self.bytes += nbytes
+                while self.bytes > self.budget:
+                    _, old = self.entries.popitem(last=False)
+                    self.bytes -= old.numel() * old.element_size()
+            out.append(t)
+        return out
+
+
 class ScoreTopK(NamedTuple):
     similarities: List[torch.Tensor]   # List[B] of (n_b,) fp32 views into `sims`
     sims: torch.Tensor                 # (N,) fp32, all documents back to back
@@ -311,8 +351,9 @@ def pooled_patch_topk(patch_embeddings: Sequence[torch.Tensor], question_embeddi
     encoder outputs ImageEncoder returns (src/_modules.py:1627-1666), 102 400 vectors for 50 strips -- is scored against it with
     Retriever._get_similarities' cosine (src/_modules.py:1990-1993: eps on the product of the norms), the k best patches per
     document are selected, a strip is scored by its best patch and the k_strips best strips are selected (torch.topk,
-    src/_modules.py:2408; lowest index first on ties).  One pooling launch, the streaming score kernel over all documents,
-    two segmented top-k launches and one group-max launch; every patch vector is read from HBM exactly once."""
+    src/_modules.py:2408; lowest index first on ties).  One pooling launch, the streaming score kernel over all documents and
+    three segmented top-k launches (per strip, per document over the strips' candidates, over the strip scores); every
+    patch vector is read from HBM exactly once."""
     _require_cuda(question_embeddings, "question_embeddings")
     device = question_embeddings.device
     B = len(patch_embeddings)
@@ -338,14 +379,51 @@ def pooled_patch_topk(patch_embeddings: Sequence[torch.Tensor], question_embeddi
             n_strips.append(int(p.shape[0]))
             flat.append(_f32_contig_aligned(p).reshape(-1, d))                     # a view: nothing is copied
         L = L or 1
-        res = score_topk(flat, q, int(k), cluster=False)
+        k = int(k)
+        table = build_doc_table(flat, d, device)
+        sims = score_table(table, q)                                               # every patch vector, read once
         total_strips = sum(n_strips)
-        strip_flat = torch.empty(max(total_strips, 1), dtype=torch.float32, device=device)
+        sizes = [n * L for n in n_strips]
+        similarities = list(torch.split(sims, sizes)) if B else []
+        patch_idx = torch.full((B, k), -1, dtype=torch.int32, device=device)
+        patch_val = torch.full((B, k), float("-inf"), dtype=torch.float32, device=device)
+        patch_cnt = torch.zeros((B,), dtype=torch.int32, device=device)
+        strip_scores = [sims.new_empty(0) for _ in range(B)]
+        s_idx = torch.full((B, k_strips), -1, dtype=torch.int32, device=device)
+        s_val = torch.full((B, k_strips), float("-inf"), dtype=torch.float32, device=device)
+        s_cnt = torch.zeros((B,), dtype=torch.int32, device=device)
         if total_strips:
-            _lib.check(_lib_fn.rdv_group_max_f32(res.sims.data_ptr(), total_strips, L, strip_flat.data_ptr(), _stream_ptr(device)))
-        strip_scores = list(torch.split(strip_flat[:total_strips], n_strips))
-        s_idx, s_val, s_cnt = topk_segments(strip_scores, k_strips) if B else (None, None, None)
-    return PooledPatchTopK(res.similarities, res.topk_idx, res.topk_val, res.topk_cnt, strip_scores, s_idx, s_val, s_cnt, q)
+            # two-level selection: a document's 102 400 scores are 50 segments of 2048, so the k best of every STRIP come
+            # first (one block per strip, register-resident: 400 blocks instead of 8), then the k best of a document's
+            # 50 x k candidates; a strip's own score is its rank-0 candidate (torch.max: NaN greatest, as torch.topk ranks it)
+            kk = min(k, L)
+            strip_off = torch.arange(0, (total_strips + 1) * L, L, dtype=torch.int64, device=device)
+            l_idx = torch.empty((total_strips, kk), dtype=torch.int32, device=device)
+            l_val = torch.empty((total_strips, kk), dtype=torch.float32, device=device)
+            l_cnt = torch.empty((total_strips,), dtype=torch.int32, device=device)
+            s = _stream_ptr(device)
+            _lib.check(_lib_fn.rdv_topk_segments_f32(sims.data_ptr(), strip_off.data_ptr(), total_strips, kk, L, l_idx.data_ptr(),
+                                                     l_val.data_ptr(), l_cnt.data_ptr(), s))
+            doc_off = np.zeros(B + 1, dtype=np.int64)
+            np.cumsum(n_strips, out=doc_off[1:])
+            cand_off = torch.from_numpy(doc_off * kk).pin_memory().to(device, non_blocking=True)
+            strip_off_doc = torch.from_numpy(doc_off).pin_memory().to(device, non_blocking=True)
+            pos = torch.empty((B, k), dtype=torch.int32, device=device)
+            _lib.check(_lib_fn.rdv_topk_segments_f32(l_val.data_ptr(), cand_off.data_ptr(), B, k, max(n_strips) * kk, pos.data_ptr(),
+                                                     patch_val.data_ptr(), patch_cnt.data_ptr(), s))
+            # candidate position -> patch index: (strip within the document) * L + (patch within the strip)
+            valid = pos >= 0
+            p64 = pos.clamp(min=0).to(torch.int64)
+            strip_in_doc = p64 // kk
+            where = (cand_off[:B, None] + p64).clamp(max=l_idx.numel() - 1)         # (an empty last document points past the end)
+            local = torch.gather(l_idx.reshape(-1), 0, where.reshape(-1)).reshape(B, k)
+            patch_idx = torch.where(valid, (strip_in_doc * L).to(torch.int32) + local, torch.full_like(pos, -1))
+            best = l_val[:, 0].contiguous()                                        # (total_strips,): best patch of every strip
+            strip_scores = list(torch.split(best, n_strips))
+            _lib.check(_lib_fn.rdv_topk_segments_f32(best.data_ptr(), strip_off_doc.data_ptr(), B, k_strips, max(n_strips),
+                                                     s_idx.data_ptr(), s_val.data_ptr(), s_cnt.data_ptr(), s))
+    return PooledPatchTopK(similarities, patch_idx, patch_val, patch_cnt, strip_scores, s_idx, s_val, s_cnt, q)
+
 
 
 # ------------------------------------------------------------------------------------------------

@@ -109,18 +109,32 @@ def _lazy_crop_class():
         PIL's own file images follow (every PIL operation calls load() before touching the pixels), so it
         behaves exactly like the eager `page.crop(rect)` of reference src/_modules.py:2119."""
 
+        # Only PUBLIC Pillow protocol is used, so the class works with the reference's pinned Pillow 10.3 as well as with
+        # Pillow >= 11: `mode` / `size` are plain attributes up to 10.0 and read-only properties over `_mode` / `_size`
+        # from 10.1; `im` is a plain attribute up to 10.x and a property over `_im` from 11 -- assigning `self.im` is right
+        # for both, and whether the pixels exist yet is this class's own state (`_page`), never Pillow's private field.
+        _MODE_IS_PROPERTY = isinstance(getattr(Image.Image, "mode", None), property)
+        _SIZE_IS_PROPERTY = isinstance(getattr(Image.Image, "size", None), property)
+
         def __init__(self, page, rect):
             super().__init__()                     # Pillow's own field set (it differs between Pillow versions)
-            self._mode = page.mode
-            self._size = (rect[2] - rect[0], rect[3] - rect[1])
+            size = (rect[2] - rect[0], rect[3] - rect[1])
+            if self._MODE_IS_PROPERTY:
+                self._mode = page.mode
+            else:
+                self.mode = page.mode
+            if self._SIZE_IS_PROPERTY:
+                self._size = size
+            else:
+                self.size = size
             if page.info:
                 self.info = dict(page.info)
             self._page, self._rect = page, rect
 
         def load(self):
-            if self._im is None and self._page is not None:
+            if self._page is not None:
                 real = self._page.crop(self._rect)
-                self._im, self.palette = real.im, real.palette
+                self.im, self.palette = real.im, real.palette
                 self._page = None
             return super().load()
     return LazyCrop
@@ -163,8 +177,15 @@ _SMALL_BATCH_BYTES = 1 << 20      # host batches up to this size take the one-up
 class Retriever(StatComponent):
     def __init__(self, config: dict):
         super().__init__(config)
-        # optional key (default preserves the reference's eager crops): cut the patch pixels on first use
+        # optional keys (the defaults preserve the reference's behaviour).  retrieval_lazy_patches: cut the patch pixels
+        # on first use.  retrieval_pause_gc: pause the cyclic garbage collector for the duration of a retrieve() call (a
+        # process-wide switch: leave it off when other threads allocate).  retrieval_embedding_cache_mb: keep up to that
+        # many MB of HOST document embeddings resident on the device, so that further questions about the same documents
+        # do not cross PCIe again (0 = off).
         self.lazy_patches = bool(config.get("retrieval_lazy_patches", False))
+        self.pause_gc = bool(config.get("retrieval_pause_gc", False))
+        self._cache_budget = int(float(config.get("retrieval_embedding_cache_mb", 0)) * (1 << 20))
+        self._cache = None          # functional.EmbeddingCache, built on first use (it needs the device)
         self.k = config.get("chunk_num", 10)
         self.include_surroundings = config.get("include_surroundings", 0)
         self.layout_map = get_layout_model_map(config)
@@ -311,8 +332,12 @@ class Retriever(StatComponent):
         """Retrieve the top-k chunks: 9-tuple, see reference src/_modules.py:2144-2153, 2180."""
         # The call builds ~1500 small acyclic containers next to the caller's millions of live word / box objects;
         # the cyclic collector's generation passes triggered by those allocations were up to 30 % of the call
-        # (scripts/profile_e2e_phases.py).  Nothing created here can be part of a cycle, so collection is paused
-        # for the duration of the call and resumes (with its counters intact) on return.
+        # (scripts/profile_e2e_phases.py).  Nothing created here can be part of a cycle, so with the opt-in key
+        # `retrieval_pause_gc` collection is paused for the duration of the call and resumes (with its counters intact) on
+        # return.  It is a process-wide switch, hence off by default.
+        if not self.pause_gc:
+            return self._retrieve(text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
+                                  layout_labels_chunks, images, page_indices)
         gc_was_enabled = gc.isenabled()
         gc.disable()
         try:
@@ -325,6 +350,15 @@ class Retriever(StatComponent):
     def _retrieve(self, text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,
                   layout_labels_chunks, images, page_indices) -> tuple:
         inputs_on_host = not question_embeddings.is_cuda
+        if self._cache_budget and inputs_on_host and len(text_embeddings) and not any(e.is_cuda for e in text_embeddings):
+            # documents answered from the resident copies; the similarities still go back to the host, where the
+            # caller's embeddings live (src/_modules.py:1990-1995)
+            if self._cache is None:
+                self._cache = F.EmbeddingCache(self._cache_budget, self.device)
+            res = self._score_topk(self._cache.resident(text_embeddings), question_embeddings.to(self.device, non_blocking=True))
+            hits = self._hits_to_host(res.topk_idx, res.topk_cnt)
+            lists = self._hit_lists(hits, words_text_chunks, words_box_chunks, layout_labels_chunks, images, page_indices)
+            return (*lists, list(torch.split(res.sims.cpu(), res.sizes)))
         if (inputs_on_host and len(text_embeddings) >= 8 and not any(e.is_cuda for e in text_embeddings)
                 and question_embeddings.dim() == 2 and question_embeddings.shape[0] == len(text_embeddings)):
             return self._retrieve_host_pipelined(text_embeddings, question_embeddings, words_text_chunks, words_box_chunks,

@@ -73,3 +73,44 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         F.late_interaction(torch.zeros(1, 3, 4), torch.zeros(2, 3, 4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         F.topk_merge(torch.zeros(2, 4), torch.zeros(2, 4, dtype=torch.long), 2)
+
+
+def test_lazy_crop_uses_public_pillow_protocol_only():
+    """The deferred patch must behave like page.crop(rect) with the reference's pinned Pillow 10.3 as well as with the
+    installed one: no private Pillow field (`_im` exists only from Pillow 11) is read or written."""
+    import inspect
+
+    import numpy as np
+    from PIL import Image
+
+    from rag_docvqa_b200 import retriever
+    src = inspect.getsource(retriever._lazy_crop_class)
+    code = "\n".join(line.split("#")[0] for line in src.splitlines())
+    assert "_im" not in code.replace("_image", "")
+    rng = np.random.RandomState(0)
+    page = Image.fromarray(rng.randint(0, 256, (60, 80, 3)).astype(np.uint8), "RGB")
+    page.info["dpi"] = (72, 72)
+    for rect in ((5, 7, 40, 33), (0, 0, 80, 60), (-3, -2, 10, 12), (70, 50, 95, 70)):
+        lazy = retriever.lazy_crop(page, rect)
+        want = page.crop(rect)
+        assert lazy.size == want.size and lazy.mode == want.mode and lazy.info == want.info
+        assert lazy._page is not None                                   # nothing cut yet
+        assert np.array_equal(np.asarray(lazy), np.asarray(want))        # first pixel access cuts
+        assert lazy._page is None
+        assert lazy.resize((8, 8)).size == (8, 8) and lazy.copy().tobytes() == want.tobytes()
+    pal = page.convert("P")
+    assert retriever.lazy_crop(pal, (1, 1, 9, 9)).convert("RGB").tobytes() == pal.crop((1, 1, 9, 9)).convert("RGB").tobytes()
+
+
+def test_gc_pause_is_opt_in(monkeypatch):
+    """Retriever.retrieve leaves the process-wide collector alone unless `retrieval_pause_gc` asks for the pause."""
+    import gc
+
+    from rag_docvqa_b200.retriever import Retriever
+    seen = []
+    base = {"compute_stats": False, "compute_stats_examples": False, "n_stats_examples": 0, "device": "cuda:0"}
+    monkeypatch.setattr(Retriever, "_retrieve", lambda self, *a: seen.append(gc.isenabled()) or "out")
+    assert gc.isenabled()
+    assert Retriever(base).retrieve(None, None, None, None, None, None, None) == "out"
+    assert Retriever({**base, "retrieval_pause_gc": True}).retrieve(None, None, None, None, None, None, None) == "out"
+    assert seen == [True, False] and gc.isenabled()

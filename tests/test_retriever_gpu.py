@@ -328,3 +328,34 @@ def test_store_and_embeddings_must_describe_the_same_chunks():
         store.prepare_gather(idx, cnt, [[1]] * 4, sims=torch.zeros(store.n_chunks + 1, device=dev),
                              topk_val=torch.empty((4, 5), device=dev))
     assert store.same_chunks_as(batch["sizes"]) and not store.same_chunks_as(batch["sizes"][::-1])
+
+
+def test_resident_embedding_cache():
+    """retrieval_embedding_cache_mb: a second question about the same host documents is answered from their device copies --
+    same outputs as without the cache; an in-place change of a document is seen (version counter)."""
+    from rag_docvqa_b200.retriever import Retriever
+    batch = synth.make_text_batch("C2", with_lists=True, docs=10, seed=21)
+    lists = (batch["words_text_chunks"], batch["words_box_chunks"], batch["layout_labels_chunks"], batch["images"],
+             batch["page_indices"])
+    emb = [e.clone().pin_memory() for e in batch["text_embeddings"]]
+    q = batch["question_embeddings"]
+    plain = Retriever({**BASE, "chunk_num": 5})
+    cached = Retriever({**BASE, "chunk_num": 5, "retrieval_embedding_cache_mb": 64})
+    want = plain.retrieve(emb, q, *lists)
+    for rep in range(3):
+        got = cached.retrieve(emb, q, *lists)
+        for i in (0, 1, 2, 3, 4, 5, 7):
+            assert got[i] == want[i]
+        for a, b in zip(got[8], want[8]):
+            assert torch.equal(a, b) and not a.is_cuda
+    n_docs = sum(1 for e in emb if e.shape[0])
+    assert cached._cache.misses == n_docs and cached._cache.hits == 2 * n_docs
+    emb[0].mul_(-1.0)                                                   # in-place torch write: the version counter moves
+    got = cached.retrieve(emb, q, *lists)
+    want2 = plain.retrieve(emb, q, *lists)
+    assert got[0] == want2[0] and torch.equal(got[8][0], want2[8][0]) and cached._cache.misses == n_docs + 1
+    tiny = Retriever({**BASE, "chunk_num": 5, "retrieval_embedding_cache_mb": 0.05})       # 50 KB: eviction, still correct
+    for rep in range(2):
+        got = tiny.retrieve(emb, q, *lists)
+        assert got[0] == want2[0]
+    assert tiny._cache.bytes <= 0.05 * (1 << 20)
