@@ -50,12 +50,18 @@ L2_BYTES = 126 * 1024 * 1024
 METRIC = "retrieval_queries_per_sec"
 
 
-def ncu_traffic(key):
-    """Per-launch DRAM traffic of a kernel from the committed ncu capture (profiles/traffic.json), or None."""
+def ncu_traffic(kernel, grid):
+    """Per-launch DRAM traffic of `kernel` at this grid size from the committed ncu capture (profiles/traffic.json, written
+    by scripts/summarise_ncu.py with the capture file and the commit it was taken at), or None -- never a value of this run."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get(key)
+            doc = json.load(f)
+        e = doc["kernels"].get("%s|grid %s|cold" % (kernel, grid))
+        if e is None:
+            return None
+        return {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "capture": e["capture"], "commit": doc.get("commit"),
+                "ncu_duration_us_cold_serialised": e.get("duration_us")}
     except Exception:
         return None
 
@@ -547,10 +553,12 @@ def text_leg(ctx, args, wl, lanes, compact=False):
         "clocks": clocks.summary(),
     }
     if ctx.rank == 0:
-        traffic = ncu_traffic(("retrieve" if one_launch else "score_topk" if launches_per_step == 1 else "score") + ":" + w.name)
+        short_name = "retrieve_cluster_kernel" if launches_per_step == 1 else kernel.split(" ")[0]
+        grid = tables[0].n_ctas if launches_per_step == 1 else tables[0].total_tiles
+        traffic = ncu_traffic(short_name, grid)
         if traffic:
-            res["roofline"]["traffic"] = traffic.get("dram_bytes_per_launch")
-            res["roofline"]["traffic_from"] = {k: traffic.get(k) for k in ("capture", "commit")}
+            res["roofline"]["traffic"] = traffic["dram_bytes_per_launch"]
+            res["roofline"]["traffic_from"] = {k: traffic.get(k) for k in ("capture", "commit", "ncu_duration_us_cold_serialised")}
     live = dict(w=w, host_batch=host_batch, batches=batches, tables=tables, outs=outs, plans=plans, store=store,
                 prompts=prompts, sizes=sizes, step_bytes=step_bytes, docstore_build_s=docstore_build_s, R=R)
     return res, live

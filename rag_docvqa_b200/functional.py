@@ -332,6 +332,25 @@ def mean_pooling(embs: torch.Tensor, attention_mask: torch.Tensor, normalise: bo
 # ------------------------------------------------------------------------------------------------
 # pooled-patch visual retrieval (north_star's wording of BASELINE.json configs[3])
 # ------------------------------------------------------------------------------------------------
+_POOLED_OFFSETS = {}
+
+
+def _pooled_offsets(n_strips: tuple, L: int, kk: int, device):
+    """Segment offsets of pooled_patch_topk's three selections for a batch shape (kept: they only depend on the shape)."""
+    key = (n_strips, L, kk, device.index)
+    hit = _POOLED_OFFSETS.get(key)
+    if hit is None:
+        if len(_POOLED_OFFSETS) > 64:
+            _POOLED_OFFSETS.clear()
+        doc_off = np.zeros(len(n_strips) + 1, dtype=np.int64)
+        np.cumsum(n_strips, out=doc_off[1:])
+        total = int(doc_off[-1])
+        hit = (torch.arange(0, (total + 1) * L, L, dtype=torch.int64, device=device),
+               torch.from_numpy(doc_off * kk).to(device), torch.from_numpy(doc_off).to(device))
+        _POOLED_OFFSETS[key] = hit
+    return hit
+
+
 class PooledPatchTopK(NamedTuple):
     similarities: List[torch.Tensor]   # List[B] of (n_b * L,) fp32: cosine of every patch vector, strip-major
     patch_idx: torch.Tensor            # (B, k) int32 flat patch index (strip * L + patch), -1 padded, rank order
@@ -397,17 +416,13 @@ def pooled_patch_topk(patch_embeddings: Sequence[torch.Tensor], question_embeddi
             # first (one block per strip, register-resident: 400 blocks instead of 8), then the k best of a document's
             # 50 x k candidates; a strip's own score is its rank-0 candidate (torch.max: NaN greatest, as torch.topk ranks it)
             kk = min(k, L)
-            strip_off = torch.arange(0, (total_strips + 1) * L, L, dtype=torch.int64, device=device)
+            strip_off, cand_off, strip_off_doc = _pooled_offsets(tuple(n_strips), L, kk, device)
             l_idx = torch.empty((total_strips, kk), dtype=torch.int32, device=device)
             l_val = torch.empty((total_strips, kk), dtype=torch.float32, device=device)
             l_cnt = torch.empty((total_strips,), dtype=torch.int32, device=device)
             s = _stream_ptr(device)
             _lib.check(_lib_fn.rdv_topk_segments_f32(sims.data_ptr(), strip_off.data_ptr(), total_strips, kk, L, l_idx.data_ptr(),
                                                      l_val.data_ptr(), l_cnt.data_ptr(), s))
-            doc_off = np.zeros(B + 1, dtype=np.int64)
-            np.cumsum(n_strips, out=doc_off[1:])
-            cand_off = torch.from_numpy(doc_off * kk).pin_memory().to(device, non_blocking=True)
-            strip_off_doc = torch.from_numpy(doc_off).pin_memory().to(device, non_blocking=True)
             pos = torch.empty((B, k), dtype=torch.int32, device=device)
             _lib.check(_lib_fn.rdv_topk_segments_f32(l_val.data_ptr(), cand_off.data_ptr(), B, k, max(n_strips) * kk, pos.data_ptr(),
                                                      patch_val.data_ptr(), patch_cnt.data_ptr(), s))

@@ -204,3 +204,40 @@ def test_visual_retriever_pooled_score():
     crops, page_ids = vr.retrieve([p.to(DEV) for p in patches], q.to(DEV), [np.arange(n)], [[[[pages[0][i]]] for i in range(n)]],
                                   [[[[0, 0, 40, 30]] for i in range(n)]], pages)
     assert page_ids[0] == want and len(crops[0]) == 2
+
+
+def test_late_interaction_auto_at_the_widest_supported_embedding():
+    """mode='auto' picks the 3xTF32 tensor-core kernel up to d = 2048, where its systematic error is largest (about
+    d * 2.1e-9 relative low: 4.4e-6): held to north_star's 1e-5 against float64, at Lq = Lp = 2048."""
+    from rag_docvqa_b200 import functional as F
+    g = torch.Generator().manual_seed(8)
+    q = torch.randn(1, 2048, 2048, generator=g)
+    p = torch.randn(2, 2048, 2048, generator=g)
+    got = F.late_interaction(q.to(DEV), p.to(DEV), mode="auto").cpu().numpy().astype(np.float64)
+    ref = R.late_interaction_f64(q, p).numpy()
+    rel = np.abs(got - ref) / np.abs(ref)
+    assert rel.max() < 1e-5, rel
+    strict = F.late_interaction(q.to(DEV), p.to(DEV), mode="ffma").cpu().numpy().astype(np.float64)
+    assert (np.abs(strict - ref) / np.abs(ref)).max() < 2e-6
+    assert (got <= strict + 1e-3).all()                       # the tensor-core accumulator rounds toward zero: never high
+
+
+def test_mean_pooling_masked_nan_is_not_read():
+    """Documented deviation: a NaN / Inf at a MASKED token position is ignored -- the kernel never
+    reads masked tokens -- where the reference's `embs * mask` turns it into NaN for the whole chunk.  Pinned both ways."""
+    from rag_docvqa_b200 import functional as F
+    embs, mask = synth.make_token_batch(12, 64, 3, mean_len=12.0, std_len=4.0, min_len=3, max_len=20)
+    dirty = embs.clone()
+    row = int((mask.sum(dim=1) < mask.shape[1]).nonzero()[0])           # a chunk that has padding
+    first_pad = int(mask[row].sum())
+    dirty[row, first_pad, 5] = float("nan")
+    dirty[row, -1, 7] = float("inf")
+    ref_clean = R.mean_pooling(embs, mask)
+    ref_dirty = R.mean_pooling(dirty, mask)
+    assert torch.isnan(ref_dirty[row]).any()                             # the reference propagates it ...
+    got = F.mean_pooling(dirty.to(DEV), mask.to(DEV)).cpu()
+    assert torch.isfinite(got).all()                                     # ... the kernel does not read it
+    np.testing.assert_allclose(got.numpy(), ref_clean.numpy(), rtol=1e-5, atol=1e-6)
+    unmasked = dirty.clone()
+    unmasked[row, 0, 5] = float("nan")                                   # an UNMASKED NaN is data: it propagates here too
+    assert torch.isnan(F.mean_pooling(unmasked.to(DEV), mask.to(DEV)).cpu()[row, 5])

@@ -202,3 +202,11 @@ def test_rejects_cpu_tensors():
     from rag_docvqa_b200 import functional as F
     with pytest.raises(RuntimeError):
         F.score_topk([torch.randn(4, 8)], torch.randn(1, 8), 2)
+
+
+def test_c3_slice_32_documents_at_full_length():
+    """32 documents of the full C3 length (10 000 chunks x 768-d each, 983 MB) against the oracle: scores, hits, order."""
+    sizes = [10_000] * 30 + [9_999, 10_000]
+    emb, q = synth.make_embeddings(sizes, 768, 41, dup_frac=0.01)
+    res = run_case(emb, q, 10)
+    check_against_oracle(res, emb, q, 10)
