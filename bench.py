@@ -1063,6 +1063,7 @@ def corpus_leg(ctx, args, compact=False):
         out["cpu_baseline"] = {"value": Qn / (best * 64), "unit": "queries/s", "cores": threads, "kind": "port",
                                "sample": "oracle corpus_scores (torch matmul) + torch.topk on a 1/64 row slice (%d rows), "
                                          "time scaled x64, best of %d reps" % (n_cpu, reps)}
+    searcher.close()                      # before the process group is destroyed
     del searcher, shard, rows
     torch.cuda.empty_cache()
     return out

@@ -6,6 +6,7 @@ a CUDA device: there is no CPU path (use oracle/ for a CPU checker).
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 from typing import List, NamedTuple, Sequence
 
@@ -151,9 +152,28 @@ def plan_score(total_rows: int, d: int, algo: int = _lib.SCORE_AUTO):
     return algo_out.value, tile_rows.value
 
 
+_TABLE_CACHE = collections.OrderedDict()
+
+
 def _table_from_pointers(ptrs: np.ndarray, sizes: np.ndarray, keep, d: int, device, tile_rows: int, algo: int,
                          plan_k: int = 8) -> DocTable:
-    """rdv_build_doc_table into a pinned blob (row_off | pad | tiles) + ONE H2D copy."""
+    """rdv_build_doc_table into a pinned blob (row_off | pad | tiles | cluster descriptors) + ONE H2D copy.
+    The blob is a pure function of (pointers, sizes, d, tile_rows, algo), so the device copies of the last few are kept
+    (per device and stream): a caller that comes back with the same resident documents -- more questions about one
+    document, a serving loop over a fixed index -- pays neither the cutting nor the upload again."""
+    key = (ptrs.tobytes(), sizes.tobytes(), d, tile_rows, algo, plan_k, torch.device(device).index, _stream_ptr(device))
+    hit = _TABLE_CACHE.get(key)
+    if hit is not None:
+        _TABLE_CACHE.move_to_end(key)
+        return hit._replace(keepalive=keep)
+    table = _table_from_pointers_uncached(ptrs, sizes, keep, d, device, tile_rows, algo, plan_k)
+    _TABLE_CACHE[key] = table._replace(keepalive=())          # the cache must not keep the documents alive
+    while len(_TABLE_CACHE) > 32:
+        _TABLE_CACHE.popitem(last=False)
+    return table
+
+
+def _table_from_pointers_uncached(ptrs, sizes, keep, d, device, tile_rows, algo, plan_k) -> DocTable:
     B = len(sizes)
     total_rows = int(sizes.sum()) if B else 0
     algo, planned_rows = plan_score(total_rows, d, algo)

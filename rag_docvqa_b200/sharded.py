@@ -315,6 +315,14 @@ class CorpusSearcher:
                 self._step()
         return self.out_val, self.out_idx
 
+    def close(self):
+        """Releases the captured step.  Call it (or drop the searcher) BEFORE torch.distributed.destroy_process_group():
+        a live CUDA graph that holds NCCL work keeps the communicator busy and the teardown waits for it forever."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.dev)
+            self._graph = None
+            self.graphed = False
+
     # -- parts alone, for measurement ---------------------------------------------------------------------------------
     def local_only(self, questions: torch.Tensor):
         with torch.cuda.device(self.dev):

@@ -26,7 +26,7 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
 def say(*a):
-    print("[rank %d]" % rank, *a, flush=True)
+    print("[rank %%d]" %% rank, *a, flush=True)
 # scenario 1: rows sharded evenly; scenario 2: rank 0 owns every row, the other ranks own EMPTY shards (N < world in miniature)
 for scenario, (N, d, Q, k) in enumerate(((200_000, 256, 300, 10), (5_000, 64, 9, 5))):
     g = torch.Generator(device="cpu").manual_seed(5)
@@ -47,10 +47,13 @@ for scenario, (N, d, Q, k) in enumerate(((200_000, 256, 300, 10), (5_000, 64, 9,
         say("seed", seed, "done")
         ok = ok and torch.equal(i1, ref_i) and torch.equal(v1, ref_v) and torch.equal(i2, ref_i) and torch.equal(v2, ref_v)
     ok = ok and (searcher.graphed or world == 1)
+    searcher.close()          # a captured graph that holds NCCL work must be released before the process group goes away
+    del searcher
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("sharded == unsharded on %%d ranks: %%s" %% (world, bool(flag.item())))
+    print("sharded == unsharded on %%d ranks: %%s" %% (world, bool(flag.item())), flush=True)
+torch.cuda.synchronize()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
 '''
