@@ -219,6 +219,21 @@ RDV_API int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_of
 
 
 
+/* Selection half of pooled-patch visual retrieval (BASELINE.json configs[3] in north_star's wording): d_sims holds the cosine
+ * of EVERY patch vector (rdv_score_f32 on the (strips * L, d) matrices; src/_modules.py:1990-1993), strip s owning
+ * d_sims[d_strip_row_off[s] .. d_strip_row_off[s + 1]) (L scores), document b the strips d_doc_strip_off[b] ..
+ * d_doc_strip_off[b + 1].  Two launches: the min(k, L) best patches of every strip (register-resident, one block per strip),
+ * then per document the k best of its strips' candidates as flat patch indices (strip in the document) * L + patch, a
+ * strip's score = its best patch (torch.max: NaN greatest) and the k_strips best strips (torch.topk, src/_modules.py:2408;
+ * same ordering rules as rdv_score_topk_f32).  Workspaces d_ws_idx / d_ws_val (n_strips, min(k, L)) and d_ws_cnt (n_strips);
+ * outputs d_patch_* (B, k), d_strip_scores [n_strips], d_strip_* (B, k_strips).
+ * Requirements: k, k_strips <= 32, max_strips * min(k, L) <= 4096. */
+RDV_API int rdv_pooled_select_f32(const float* d_sims, const int64_t* d_strip_row_off, int64_t n_strips, int32_t L,
+                                  const int64_t* d_doc_strip_off, int32_t B, int32_t max_strips, int32_t k, int32_t k_strips,
+                                  int32_t* d_ws_idx, float* d_ws_val, int32_t* d_ws_cnt, int32_t* d_patch_idx,
+                                  float* d_patch_val, int32_t* d_patch_cnt, float* d_strip_scores, int32_t* d_strip_idx,
+                                  float* d_strip_val, int32_t* d_strip_cnt, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Masked mean pooling of encoder token outputs (+ optional fused L2 normalisation / bf16 copy).
  *

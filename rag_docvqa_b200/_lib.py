@@ -102,6 +102,9 @@ SIGNATURES = {
     "rdv_score_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "rdv_topk_segments_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
+    "rdv_pooled_select_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
     "rdv_mean_pool_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "rdv_row_inv_norm_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),

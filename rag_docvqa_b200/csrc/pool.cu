@@ -5,7 +5,8 @@
 // The reference materialises embs*mask (a full-size temporary) and reads it again; here every token
 // row is read exactly once and tokens whose mask is 0 are not read at all, so the traffic is
 // n*Lvalid*d*4 instead of 3*n*L*d*4.  HBM-bound: one block per chunk, thread = one float4 column of
-// d, G token-groups per block accumulate in parallel and are folded through shared memory.
+// d, G token-groups per block accumulate in parallel and are folded through shared memory.  When there are few rows of many
+// tokens, a row is split over a thread-block cluster instead (mean_pool_split_kernel below).
 //
 // Deviation, documented: a NaN/Inf sitting at a *masked-out* token position is ignored here, whereas
 // the reference's `embs * 0` would propagate it (finite inputs: bit-for-bit the same sum order per
@@ -153,6 +154,170 @@ __global__ void __launch_bounds__(kPoolThreads, 4) mean_pool_kernel(const PoolPa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Few rows, many tokens (8 rendered questions x 2048 patch vectors x 768: 50 MB that one block per row would pull through 8
+// of the 148 SMs, 284 us measured): one row per thread-block CLUSTER of S CTAs.  CTA r sums the tokens [r * per, (r + 1) * per)
+// of the row exactly as the kernel above does, stores its partial row into the LEADER's shared memory (st.shared::cluster),
+// and after one cluster barrier the leader adds the S partial rows in rank order (deterministic), divides and normalises.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pool_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void pool_remote_store(const void* local, uint32_t rank, float4 v) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(r), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(kPoolThreads) mean_pool_split_kernel(const PoolParams p, const int S) {
+    extern __shared__ float4 s_dyn[];             // [G][cols] group partials | [S][d4] the ranks' partial rows (leader's copy is read)
+    __shared__ float s_mask[kPoolMaxL];
+    __shared__ float s_red[kPoolThreads / 32];
+    __shared__ float s_scalar[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d4 = p.d >> 2;
+    const uint32_t rank = pool_cluster_rank();
+    const int row = blockIdx.x / S;
+    const int64_t* mrow = p.mask + (size_t)row * p.L;
+
+    float cnt = 0.f;                              // the whole mask row in every CTA: the same count, summed in the same order
+    for (int t = tid; t < p.L; t += kPoolThreads) {
+        const float m = (float)mrow[t];
+        s_mask[t] = m;
+        cnt += m;
+    }
+    cnt = warp_sum(cnt);
+    if (lane == 0) s_red[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        float c = 0.f;
+        for (int w = 0; w < kPoolThreads / 32; ++w) c += s_red[w];
+        s_scalar[0] = fmaxf(c, 1e-9f);
+    }
+    __syncthreads();
+    const float denom = s_scalar[0];
+
+    const int cols = d4 < kPoolThreads ? d4 : kPoolThreads;
+    const int G = kPoolThreads / cols;
+    const int g = tid / cols, c0 = tid - g * cols;
+    const bool active = g < G;
+    const int per = (p.L + S - 1) / S;
+    const int t_lo = (int)rank * per, t_hi = min(p.L, t_lo + per);
+    const float4* base = reinterpret_cast<const float4*>(p.embs) + (size_t)row * p.L * d4;
+    float4* s_fold = s_dyn;
+    float4* s_rows = s_dyn + (size_t)G * cols;
+
+    for (int c = c0; c < d4; c += cols) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            int t = t_lo + g;
+            for (; t + (kPoolUnroll - 1) * G < t_hi; t += kPoolUnroll * G) {
+                float m[kPoolUnroll];
+                float4 v[kPoolUnroll];
+#pragma unroll
+                for (int u = 0; u < kPoolUnroll; ++u) {
+                    m[u] = s_mask[t + u * G];
+                    if (m[u] != 0.f) v[u] = ldg_stream(base + (size_t)(t + u * G) * d4 + c);
+                }
+#pragma unroll
+                for (int u = 0; u < kPoolUnroll; ++u) {
+                    if (m[u] != 0.f) {
+                        acc.x = fmaf(v[u].x, m[u], acc.x); acc.y = fmaf(v[u].y, m[u], acc.y);
+                        acc.z = fmaf(v[u].z, m[u], acc.z); acc.w = fmaf(v[u].w, m[u], acc.w);
+                    }
+                }
+            }
+            for (; t < t_hi; t += G) {
+                const float m = s_mask[t];
+                if (m != 0.f) {
+                    const float4 v = ldg_stream(base + (size_t)t * d4 + c);
+                    acc.x = fmaf(v.x, m, acc.x); acc.y = fmaf(v.y, m, acc.y);
+                    acc.z = fmaf(v.z, m, acc.z); acc.w = fmaf(v.w, m, acc.w);
+                }
+            }
+        }
+        if (G > 1) {
+            if (active) s_fold[g * cols + c0] = acc;
+            __syncthreads();
+            if (g == 0) {
+                for (int gg = 1; gg < G; ++gg) {
+                    const float4 o = s_fold[gg * cols + c0];
+                    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                }
+            }
+        }
+        if (g == 0) pool_remote_store(s_rows + (size_t)rank * d4 + c, 0, acc);      // into the leader's copy of s_rows
+        if (G > 1) __syncthreads();
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (rank != 0) return;
+
+    float ss_local = 0.f;
+    for (int c = tid; c < d4; c += kPoolThreads) {
+        float4 acc = s_rows[c];
+        for (int r = 1; r < S; ++r) {
+            const float4 o = s_rows[(size_t)r * d4 + c];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        acc.x = __fdiv_rn(acc.x, denom); acc.y = __fdiv_rn(acc.y, denom);
+        acc.z = __fdiv_rn(acc.z, denom); acc.w = __fdiv_rn(acc.w, denom);
+        ss_local += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+        if (!p.normalise) {
+            if (p.out) reinterpret_cast<float4*>(p.out)[(size_t)row * d4 + c] = acc;
+            if (p.out_bf16) {
+                __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(p.out_bf16) + ((size_t)row * d4 + c) * 2;
+                o[0] = __floats2bfloat162_rn(acc.x, acc.y);
+                o[1] = __floats2bfloat162_rn(acc.z, acc.w);
+            }
+        } else {
+            s_rows[c] = acc;
+        }
+    }
+    if (!p.normalise && !p.out_norm) return;
+    ss_local = warp_sum(ss_local);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = ss_local;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kPoolThreads / 32; ++w) s += s_red[w];
+        const float nrm = __fsqrt_rn(s);
+        s_scalar[1] = nrm;
+        if (p.out_norm) p.out_norm[row] = nrm;
+    }
+    __syncthreads();
+    if (!p.normalise) return;
+    const float inv_den = fmaxf(s_scalar[1], 1e-12f);
+    for (int c = tid; c < d4; c += kPoolThreads) {
+        float4 v = s_rows[c];
+        v.x = __fdiv_rn(v.x, inv_den); v.y = __fdiv_rn(v.y, inv_den);
+        v.z = __fdiv_rn(v.z, inv_den); v.w = __fdiv_rn(v.w, inv_den);
+        if (p.out) reinterpret_cast<float4*>(p.out)[(size_t)row * d4 + c] = v;
+        if (p.out_bf16) {
+            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(p.out_bf16) + ((size_t)row * d4 + c) * 2;
+            o[0] = __floats2bfloat162_rn(v.x, v.y);
+            o[1] = __floats2bfloat162_rn(v.z, v.w);
+        }
+    }
+}
+
+constexpr size_t kPoolSplitSmem = 160 * 1024;
+
+// CTAs per row: a power of two <= 16 that brings the grid to about two CTAs per SM, leaves every CTA >= 64 tokens and keeps
+// the S partial rows in the leader's shared memory.  RDV_POOL_SPLIT=0 turns the split off, =S forces it (tests).
+static int pool_split(int n, int L, int d, size_t base_smem) {
+    int want = 0;
+    if (const char* e = getenv("RDV_POOL_SPLIT")) want = atoi(e), want = want <= 0 ? 1 : want;
+    int S = 1;
+    while (S < 16 && (want ? S * 2 <= want : ((int64_t)n * S * 2 <= 2 * 148 && L / (S * 2) >= 64))) S *= 2;
+    while (S > 1 && base_smem + (size_t)S * d * 4 > kPoolSplitSmem) S /= 2;
+    return S;
+}
+
 }  // namespace rdv
 
 extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int32_t n, int32_t L, int32_t d,
@@ -177,6 +342,25 @@ extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int
     const size_t smem = ((size_t)G * cols + (size_t)d4) * sizeof(float4);
     RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024),
                         "cudaFuncSetAttribute(mean_pool)");
+    const int S = pool_split(n, L, d, (size_t)G * cols * sizeof(float4));
+    if (S > 1) {
+        RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSplitSmem),
+                            "cudaFuncSetAttribute(mean_pool_split)");
+        RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_split_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
+                            "cudaFuncSetAttribute(mean_pool_split, cluster)");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n * S);
+        cfg.blockDim = dim3(kPoolThreads);
+        cfg.dynamicSmemBytes = ((size_t)G * cols + (size_t)S * d4) * sizeof(float4);
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mean_pool_split_kernel, p, S);
+        if (e != cudaSuccess) return cuda_fail(e, "mean_pool_split_kernel");
+        return RDV_OK;
+    }
     mean_pool_kernel<<<n, kPoolThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     RDV_LAUNCH_CHECK("mean_pool_kernel");
     return RDV_OK;

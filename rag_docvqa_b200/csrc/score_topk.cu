@@ -372,6 +372,30 @@ __global__ void __launch_bounds__(kScoreThreads) topk_segments_kernel(const int6
     select_topk<40>(sel, b, scores + r0, n, reinterpret_cast<float*>(smem_dyn), s_red, BlockSync());
 }
 
+// Second level of pooled-patch retrieval, one block per document: the k best of the document's (strips x kk) per-strip
+// candidates, mapped back to patch indices; the strips' own scores (a strip's rank-0 candidate = its best patch); the
+// k_strips best strips.
+__global__ void __launch_bounds__(kScoreThreads) pooled_doc_kernel(const int64_t* __restrict__ doc_strip_off, int L, int kk,
+                                                                   const int32_t* __restrict__ l_idx,
+                                                                   const float* __restrict__ l_val, SelectArgs patch,
+                                                                   float* __restrict__ strip_scores, SelectArgs strips) {
+    __shared__ unsigned long long s_red[kScoreWarps];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t s0 = doc_strip_off[b];
+    const int ns = (int)(doc_strip_off[b + 1] - s0);
+    for (int s = tid; s < ns; s += kScoreThreads) strip_scores[s0 + s] = __ldcg(l_val + (s0 + s) * kk);
+    select_topk<16>(patch, b, l_val + s0 * kk, ns * kk, nullptr, s_red, BlockSync());
+    __syncthreads();                               // the positions are written; the strip scores are visible to the block
+    if (tid < patch.k) {
+        const size_t o = (size_t)b * patch.k + tid;
+        const int pos = patch.topk_idx[o];
+        if (pos >= 0) patch.topk_idx[o] = (pos / kk) * L + __ldcg(l_idx + s0 * kk + pos);     // strip in the document, patch in the strip
+    }
+    select_topk<16>(strips, b, strip_scores + s0, ns, nullptr, s_red, BlockSync());
+}
+
 static int launch_segments(const float* scores, const int64_t* row_off, int B, const SelectArgs& sel, cudaStream_t s) {
     RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(topk_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024),
                         "cudaFuncSetAttribute(topk_segments)");
@@ -452,6 +476,40 @@ extern "C" int rdv_score_topk_f32(const rdv_tile_desc* d_tiles, int32_t total_ti
     rc = launch_stream(p, algo, s);
     if (rc) return rc;
     return launch_segments(d_sims, d_row_off, B, p.sel, s);
+}
+
+extern "C" int rdv_pooled_select_f32(const float* d_sims, const int64_t* d_strip_row_off, int64_t n_strips, int32_t L,
+                                     const int64_t* d_doc_strip_off, int32_t B, int32_t max_strips, int32_t k, int32_t k_strips,
+                                     int32_t* d_ws_idx, float* d_ws_val, int32_t* d_ws_cnt, int32_t* d_patch_idx,
+                                     float* d_patch_val, int32_t* d_patch_cnt, float* d_strip_scores, int32_t* d_strip_idx,
+                                     float* d_strip_val, int32_t* d_strip_cnt, void* stream) {
+    RDV_REQUIRE(B >= 0 && n_strips >= 0 && n_strips < (1ll << 31) && L >= 1 && max_strips >= 0, RDV_E_INVALID, "pooled_select_f32: bad sizes");
+    RDV_REQUIRE(k >= 1 && k <= kSelWarpK && k_strips >= 1 && k_strips <= kSelWarpK, RDV_E_LIMIT,
+                "pooled_select_f32: k=%d / k_strips=%d outside [1, %d]", k, k_strips, kSelWarpK);
+    const int kk = k < L ? k : L;
+    RDV_REQUIRE((int64_t)max_strips * kk <= 16 * kScoreThreads, RDV_E_LIMIT,
+                "pooled_select_f32: %d strips x %d candidates exceed the %d a block selects from registers", max_strips, kk,
+                16 * kScoreThreads);
+    if (B == 0) return RDV_OK;
+    RDV_REQUIRE(d_doc_strip_off && d_patch_idx && d_patch_val && d_patch_cnt && d_strip_idx && d_strip_val && d_strip_cnt,
+                RDV_E_INVALID, "pooled_select_f32: null pointer");
+    RDV_REQUIRE(n_strips == 0 || (d_sims && d_strip_row_off && d_ws_idx && d_ws_val && d_ws_cnt && d_strip_scores), RDV_E_INVALID,
+                "pooled_select_f32: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n_strips > 0) {
+        SelectArgs l = {};
+        l.k = kk; l.cache_floats = cache_floats_for(L, kk, 40 * kScoreThreads);
+        l.topk_idx = d_ws_idx; l.topk_val = d_ws_val; l.topk_cnt = d_ws_cnt;
+        int rc = launch_segments(d_sims, d_strip_row_off, (int)n_strips, l, s);          // k best patches of every strip
+        if (rc) return rc;
+    }
+    SelectArgs p = {}, q = {};
+    p.k = k; p.topk_idx = d_patch_idx; p.topk_val = d_patch_val; p.topk_cnt = d_patch_cnt;
+    q.k = k_strips; q.topk_idx = d_strip_idx; q.topk_val = d_strip_val; q.topk_cnt = d_strip_cnt;
+    cudaError_t e = launch_pdl(kPdlSelect, pooled_doc_kernel, dim3(B), dim3(kScoreThreads), 0, s, d_doc_strip_off, (int)L, kk,
+                               (const int32_t*)d_ws_idx, (const float*)d_ws_val, p, d_strip_scores, q);
+    if (e != cudaSuccess) return cuda_fail(e, "pooled_doc_kernel");
+    return RDV_OK;
 }
 
 extern "C" int rdv_topk_segments_f32(const float* d_scores, const int64_t* d_row_off, int32_t B, int32_t k,

@@ -390,9 +390,9 @@ def pooled_patch_topk(patch_embeddings: Sequence[torch.Tensor], question_embeddi
     encoder outputs ImageEncoder returns (src/_modules.py:1627-1666), 102 400 vectors for 50 strips -- is scored against it with
     Retriever._get_similarities' cosine (src/_modules.py:1990-1993: eps on the product of the norms), the k best patches per
     document are selected, a strip is scored by its best patch and the k_strips best strips are selected (torch.topk,
-    src/_modules.py:2408; lowest index first on ties).  One pooling launch, the streaming score kernel over all documents and
-    three segmented top-k launches (per strip, per document over the strips' candidates, over the strip scores); every
-    patch vector is read from HBM exactly once."""
+    src/_modules.py:2408; lowest index first on ties).  Four launches: pooling, the streaming score kernel over all documents,
+    the top-k of every strip, and per document the top-k of its strips' candidates + the strip scores + their top-k
+    (rdv_pooled_select_f32); every patch vector is read from HBM exactly once."""
     _require_cuda(question_embeddings, "question_embeddings")
     device = question_embeddings.device
     B = len(patch_embeddings)
@@ -424,39 +424,30 @@ def pooled_patch_topk(patch_embeddings: Sequence[torch.Tensor], question_embeddi
         total_strips = sum(n_strips)
         sizes = [n * L for n in n_strips]
         similarities = list(torch.split(sims, sizes)) if B else []
-        patch_idx = torch.full((B, k), -1, dtype=torch.int32, device=device)
-        patch_val = torch.full((B, k), float("-inf"), dtype=torch.float32, device=device)
-        patch_cnt = torch.zeros((B,), dtype=torch.int32, device=device)
+        fill = total_strips == 0                                                    # no strip at all: nothing launches
+        patch_idx = (torch.full if fill else torch.empty)((B, k), *((-1,) if fill else ()), dtype=torch.int32, device=device)
+        patch_val = (torch.full if fill else torch.empty)((B, k), *((float("-inf"),) if fill else ()), dtype=torch.float32, device=device)
+        patch_cnt = torch.zeros((B,), dtype=torch.int32, device=device) if fill else torch.empty((B,), dtype=torch.int32, device=device)
         strip_scores = [sims.new_empty(0) for _ in range(B)]
-        s_idx = torch.full((B, k_strips), -1, dtype=torch.int32, device=device)
-        s_val = torch.full((B, k_strips), float("-inf"), dtype=torch.float32, device=device)
-        s_cnt = torch.zeros((B,), dtype=torch.int32, device=device)
+        s_idx = (torch.full if fill else torch.empty)((B, k_strips), *((-1,) if fill else ()), dtype=torch.int32, device=device)
+        s_val = (torch.full if fill else torch.empty)((B, k_strips), *((float("-inf"),) if fill else ()), dtype=torch.float32, device=device)
+        s_cnt = torch.zeros((B,), dtype=torch.int32, device=device) if fill else torch.empty((B,), dtype=torch.int32, device=device)
         if total_strips:
             # two-level selection: a document's 102 400 scores are 50 segments of 2048, so the k best of every STRIP come
-            # first (one block per strip, register-resident: 400 blocks instead of 8), then the k best of a document's
-            # 50 x k candidates; a strip's own score is its rank-0 candidate (torch.max: NaN greatest, as torch.topk ranks it)
+            # first (one block per strip, register-resident: 400 blocks instead of 8), then per document the k best of its
+            # strips' candidates; a strip's own score is its rank-0 candidate (torch.max: NaN greatest, as torch.topk ranks
+            # it).  Both levels, the index arithmetic and the strips' top-k are two launches of ONE C call.
             kk = min(k, L)
-            strip_off, cand_off, strip_off_doc = _pooled_offsets(tuple(n_strips), L, kk, device)
-            l_idx = torch.empty((total_strips, kk), dtype=torch.int32, device=device)
-            l_val = torch.empty((total_strips, kk), dtype=torch.float32, device=device)
-            l_cnt = torch.empty((total_strips,), dtype=torch.int32, device=device)
-            s = _stream_ptr(device)
-            _lib.check(_lib_fn.rdv_topk_segments_f32(sims.data_ptr(), strip_off.data_ptr(), total_strips, kk, L, l_idx.data_ptr(),
-                                                     l_val.data_ptr(), l_cnt.data_ptr(), s))
-            pos = torch.empty((B, k), dtype=torch.int32, device=device)
-            _lib.check(_lib_fn.rdv_topk_segments_f32(l_val.data_ptr(), cand_off.data_ptr(), B, k, max(n_strips) * kk, pos.data_ptr(),
-                                                     patch_val.data_ptr(), patch_cnt.data_ptr(), s))
-            # candidate position -> patch index: (strip within the document) * L + (patch within the strip)
-            valid = pos >= 0
-            p64 = pos.clamp(min=0).to(torch.int64)
-            strip_in_doc = p64 // kk
-            where = (cand_off[:B, None] + p64).clamp(max=l_idx.numel() - 1)         # (an empty last document points past the end)
-            local = torch.gather(l_idx.reshape(-1), 0, where.reshape(-1)).reshape(B, k)
-            patch_idx = torch.where(valid, (strip_in_doc * L).to(torch.int32) + local, torch.full_like(pos, -1))
-            best = l_val[:, 0].contiguous()                                        # (total_strips,): best patch of every strip
+            strip_off, _, strip_off_doc = _pooled_offsets(tuple(n_strips), L, kk, device)
+            ws_idx = torch.empty((total_strips, kk), dtype=torch.int32, device=device)
+            ws_val = torch.empty((total_strips, kk), dtype=torch.float32, device=device)
+            ws_cnt = torch.empty((total_strips,), dtype=torch.int32, device=device)
+            best = torch.empty((total_strips,), dtype=torch.float32, device=device)
+            _lib.check(_lib_fn.rdv_pooled_select_f32(
+                sims.data_ptr(), strip_off.data_ptr(), total_strips, L, strip_off_doc.data_ptr(), B, max(n_strips), k, k_strips,
+                ws_idx.data_ptr(), ws_val.data_ptr(), ws_cnt.data_ptr(), patch_idx.data_ptr(), patch_val.data_ptr(),
+                patch_cnt.data_ptr(), best.data_ptr(), s_idx.data_ptr(), s_val.data_ptr(), s_cnt.data_ptr(), _stream_ptr(device)))
             strip_scores = list(torch.split(best, n_strips))
-            _lib.check(_lib_fn.rdv_topk_segments_f32(best.data_ptr(), strip_off_doc.data_ptr(), B, k_strips, max(n_strips),
-                                                     s_idx.data_ptr(), s_val.data_ptr(), s_cnt.data_ptr(), s))
     return PooledPatchTopK(similarities, patch_idx, patch_val, patch_cnt, strip_scores, s_idx, s_val, s_cnt, q)
 
 

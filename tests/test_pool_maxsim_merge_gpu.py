@@ -241,3 +241,32 @@ def test_mean_pooling_masked_nan_is_not_read():
     unmasked = dirty.clone()
     unmasked[row, 0, 5] = float("nan")                                   # an UNMASKED NaN is data: it propagates here too
     assert torch.isnan(F.mean_pooling(unmasked.to(DEV), mask.to(DEV)).cpu()[row, 5])
+
+
+@pytest.mark.parametrize("split", ["auto", "0", "2", "16"])
+@pytest.mark.parametrize("n,L,d", [(8, 2048, 768), (3, 1000, 1024), (1, 4096, 64), (5, 70, 768)])
+def test_mean_pooling_row_split_over_a_cluster(monkeypatch, split, n, L, d):
+    """Few rows of many tokens (the rendered questions of pooled-patch retrieval): a row is summed by a thread-block cluster.
+    Every split factor gives the oracle's result within fp32 summation error, bit-identically from run to run, and the
+    normalised / bf16 / norm outputs agree with it."""
+    from rag_docvqa_b200 import functional as F
+    if split == "auto":
+        monkeypatch.delenv("RDV_POOL_SPLIT", raising=False)
+    else:
+        monkeypatch.setenv("RDV_POOL_SPLIT", split)
+    g = torch.Generator().manual_seed(n * 1000 + L)
+    embs = torch.randn(n, L, d, generator=g)
+    mask = (torch.rand(n, L, generator=g) < 0.8).to(torch.int64)
+    mask[0, L // 2:] = 0                                        # a row whose second half is padding: whole CTAs see no token
+    if n > 1:
+        mask[1] = 0                                             # nothing at all: clamp(min=1e-9) keeps 0 / 1e-9 = 0
+    ref = R.mean_pooling(embs, mask)
+    e, m = embs.to(DEV), mask.to(DEV)
+    got, bf, nrm = F.mean_pooling(e, m, out_bf16=True, return_norm=True)
+    again = F.mean_pooling(e, m)
+    assert torch.equal(got, again)
+    torch.testing.assert_close(got.cpu(), ref, rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(nrm.cpu(), ref.norm(dim=1), rtol=2e-5, atol=2e-6)
+    assert torch.equal(bf.cpu(), got.cpu().to(torch.bfloat16))
+    gotn = F.mean_pooling(e, m, normalise=True)
+    torch.testing.assert_close(gotn.cpu(), torch.nn.functional.normalize(ref, dim=1), rtol=2e-5, atol=2e-6)

@@ -144,3 +144,33 @@ def test_corpus_searcher_empty_shard():
     assert (i == -1).all() and torch.isneginf(v).all()
     v2, i2 = empty.search_local(torch.randn(7, 64, device=DEV), 3)
     assert (i2 == -1).all() and torch.isneginf(v2).all()
+
+
+def test_two_devices_in_one_process():
+    """Kernel attributes (dynamic shared memory above 48 KB, cluster size) belong to a device's context: a process that
+    uses cuda:0 and then cuda:1 must be able to launch the tcgen05, TMA-ring, pooling, gather and cluster kernels on both
+    (the opt-in used to be remembered once per process).  Needs >= 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    from rag_docvqa_b200 import functional as F
+    from rag_docvqa_b200 import sharded, synth
+    results = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        g = torch.Generator().manual_seed(3)
+        E = torch.randn(3000, 256, generator=g)
+        Q = torch.randn(130, 256, generator=g)
+        with torch.cuda.device(dev):
+            v, i = sharded.CorpusShard.from_f32(E.to(dev)).search_local(Q.to(dev), 10)            # tc_score_kernel (~209 KB)
+            emb, q = synth.make_embeddings([300, 17, 0, 600], 384, 5)
+            a = F.score_topk([e.to(dev) for e in emb], q.to(dev), 5, algo=2)                      # score_tma_kernel (192 KB)
+            b = F.score_topk([e.to(dev) for e in emb], q.to(dev), 5, cluster=True)                # clusters of 16
+            qq, pp = torch.randn(1, 256, 128, generator=g), torch.randn(3, 256, 128, generator=g)
+            m = F.late_interaction(qq.to(dev), pp.to(dev), mode="tf32x3")                         # maxsim_tf32x3_kernel (192 KB)
+            embs, am = synth.make_token_batch(64, 1024, 7, max_len=40)
+            p = F.mean_pooling(embs.to(dev), am.to(dev), normalise=True)                          # mean_pool_kernel
+            torch.cuda.synchronize(dev)
+        assert torch.equal(a.topk_idx.cpu(), b.topk_idx.cpu())
+        results.append((i.cpu(), a.topk_idx.cpu(), m.cpu(), p.cpu()))
+    for r in results[1:]:
+        for x, y in zip(results[0], r):
+            assert torch.equal(x, y)
