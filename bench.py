@@ -656,6 +656,58 @@ def pool_leg(ctx, n_chunks, dim, hbm_peak):
             "GBps": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / hbm_peak}
 
 
+def embed_leg(ctx, B, L, hbm_peak, with_cpu):
+    """What follows the gather (section 8f rank 2, last clause): the generator's input embeddings of one batch's packed tensors,
+    shared(ids) + SpatialEmbeddings(boxes) (src/VT5.py:194-204, src/_modules.py:70-86), t5-base sizes, one launch."""
+    from rag_docvqa_b200.vt5_embed import SpatialEmbeddings, VT5InputEmbeddings
+    D, V, n_pos = 768, 32128, 1024
+    g = torch.Generator().manual_seed(synth_seed(9))
+    w = {"x": torch.randn(n_pos, D, generator=g), "y": torch.randn(n_pos, D, generator=g), "g": 1 + 0.1 * torch.randn(D, generator=g),
+         "b": 0.1 * torch.randn(D, generator=g), "W": torch.randn(D, D, generator=g) / D ** 0.5, "lb": 0.1 * torch.randn(D, generator=g),
+         "shared": torch.randn(V, D, generator=g)}
+    # packed tensors shaped like the gather's: a 20-token prompt on the full-page box, words of 1-3 tokens sharing a box, ~12 % padding
+    ids = torch.randint(2, V, (B, L), generator=g)
+    boxes = torch.zeros((B, L, 4), dtype=torch.int64)
+    word = torch.randint(0, 1001, (B, L, 4), generator=g)
+    new_word = torch.rand(B, L, generator=g) < 0.75
+    for b in range(B):
+        fill = int(L * (0.8 + 0.2 * torch.rand(1, generator=g).item()))
+        idx = torch.cummax(torch.where(new_word[b], torch.arange(L), torch.zeros(L, dtype=torch.int64)), 0).values
+        boxes[b] = word[b][idx]
+        boxes[b, :20] = torch.tensor([0, 0, 1000, 1000])
+        boxes[b, fill:] = 0
+        ids[b, fill:] = 0
+    sp = SpatialEmbeddings(w["x"], w["y"], w["g"], w["b"], 1e-12, w["W"], w["lb"], device=ctx.dev)
+    emb = VT5InputEmbeddings(sp, w["shared"])
+    ids_d, boxes_d = ids.to(ctx.dev), boxes.to(ctx.dev)
+    for _ in range(3):
+        emb(ids_d, boxes_d)
+    emb.check()
+    reps = 20
+    ms = timed_loop(lambda i: emb(ids_d, boxes_d), reps, torch.cuda.synchronize) / reps
+    n = B * L
+    by = n * (D * 4 * 2 + 5 * 8)
+    out = {"kernel": "vt5_embed_kernel", "shape": [B, L, D], "tokens_per_s": n / ms * 1e3, "ms": ms, "algorithmic_bytes": by,
+           "GBps": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / hbm_peak,
+           "what": "input_embeds = shared(ids) + spatial_embedding(boxes) for one batch's packed tensors; algorithmic bytes = the row "
+                   "written + the token's embedding row read + ids / boxes (the 32128 x 768 token table is 99 MB: part of it stays "
+                   "in the 126 MB L2 between launches, as it does between batches in use; the coordinate tables are L2-resident by design)"}
+    if with_cpu:
+        from oracle import ref_restated as R
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sb = max(1, min(B, 8))
+
+        def cpu():
+            spat = R.spatial_embeddings(boxes[:sb], w["x"], w["y"], w["g"], w["b"], 1e-12, w["W"], w["lb"])
+            return R.vt5_input_embeds(ids[:sb], boxes[:sb], w["shared"], spat)
+        best, _ = time_cpu(cpu, 2.0)
+        out["cpu_tokens_per_s"] = sb * L / best
+        out["cpu_sample"] = "oracle (the reference's torch CPU operators: 5 embedding lookups, LayerNorm, Linear) on %d of the %d rows, %d threads" % (sb, B, threads)
+    del emb, sp
+    return out
+
+
 def e2e_text(ctx, args, live, lazy, cached=False):
     """The drop-in Retriever.retrieve with HOST inputs: pinned host embeddings + the reference's nested lists + PIL pages in,
     the 9-tuple out; H2D and D2H inside the timed region."""
@@ -812,6 +864,8 @@ def run_ours(args):
             pool["pool_score_topk_gather"] = {"ms": tot_ms, "GBps": tot_by / tot_ms / 1e6, "frac_hbm": tot_by / tot_ms / 1e6 / hbm_peak,
                                               "what": "pooling of the batch's %d chunks followed by one step, one dependent chain" % n_chunks}
         line["pool"] = pool
+        if args.workload == "C2":
+            line["embed"] = embed_leg(ctx, w.docs, 512, hbm_peak, with_cpu=(rank == 0 and world == 1))
     if args.extras and rank == 0 and world == 1:
         extras.update(stage_extras(ctx.dev, hbm_peak, 20))
     if extras:

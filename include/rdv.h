@@ -44,6 +44,10 @@ RDV_API int rdv_abi_version(void);
 /* Thread-local text of the last error returned on this thread ("" if none). */
 RDV_API const char* rdv_last_error(void);
 
+/* sizeof() of a struct of this header by name ("rdv_gather_args", ...), -1 for an unknown name: a binding checks its own
+ * mirror of the layout against it (tests/test_abi.py does for the ctypes one). */
+RDV_API int64_t rdv_struct_size(const char* name);
+
 /* SM count / compute capability of the current device (as the launch heuristics see it). */
 RDV_API int rdv_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 
@@ -415,6 +419,43 @@ RDV_API int rdv_gather_vt5_inputs(const rdv_docstore* ds, const rdv_gather_args*
 RDV_API int rdv_retrieve_vt5_f32(const rdv_cta_desc* d_ctas, int64_t n_ctas, int32_t cluster, const float* d_q, int32_t d,
                                  int32_t max_rows, float* d_sims, const rdv_docstore* ds, const rdv_gather_args* args,
                                  void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * The generator's input embeddings from the gather's tensors (last clause): the tail of
+ * VT5.prepare_inputs_for_vqa (src/VT5.py:194-204)
+ *     input_embeds = language_backbone.shared(ids) + spatial_embedding(boxes) [+ layout_embedding(labels) * scale]
+ * with SpatialEmbeddings.forward (src/_modules.py:70-86; inference, dropout = identity):
+ *     Linear(LayerNorm(x_emb[l] + y_emb[u] + x_emb[r] + y_emb[b])).
+ * LayerNorm's centring and the Linear are linear in the summed rows, so the (tokens, D) x (D, D) GEMM of the reference is
+ * folded into per-coordinate tables once per model (rdv_vt5_embed_tables_build, fp64 accumulation):
+ *     xw / yw (n_pos, D)   ((row - mean(row)) * ln_weight) W^T          c (D) = ln_bias W^T + lin_bias
+ *     gxx / gxy / gyy (n_pos, n_pos)   dot products of the centred rows: var(sum) * D is ten of their entries
+ * and rdv_vt5_input_embeds_f32 is ONE pass: per token four table rows, ten scalars, the token's embedding row, one row out
+ * (fp32; agrees with the reference's fp32 modules to ~1e-6 relative, the tolerance tests/test_vt5_embed_gpu.py states).
+ *   d_ids (B, L) int64 or NULL (spatial embedding only), d_boxes (B, L, 4) int64, d_labels (B, L) int64 or NULL; row b of
+ *   each starts b * ld tokens into its buffer (ld >= L: the gather's (B, max_len) buffers trimmed to the longest row);
+ *   d_out (B, L, D) contiguous.  *d_bad (may be NULL) gets bit 0 / 1 / 2 set when a box coordinate / token id / layout
+ *   label is outside its table (torch.nn.Embedding raises; here the entry is clamped and the flag tells the host). */
+typedef struct rdv_vt5_embed_tables {
+    int32_t D, n_pos;
+    const float *xw, *yw, *gxx, *gxy, *gyy, *c;
+    float eps;                /* LayerNorm eps (CustomT5Config.layer_norm_eps, src/_modules.py:45) */
+    int32_t V;                /* rows of `shared` */
+    const float* shared;      /* (V, D) language_backbone.shared.weight or NULL */
+    const float* layout;      /* (n_labels, D) layout_embedding.weight or NULL */
+    int32_t n_labels;
+    float layout_scale;       /* layout_embedding_scale (src/VT5.py:35) */
+} rdv_vt5_embed_tables;
+
+/* d_ws_means: 2 * n_pos doubles of scratch.  D: a multiple of 4, <= 1024.  d_lin_bias may be NULL. */
+RDV_API int rdv_vt5_embed_tables_build(const float* d_x_emb, const float* d_y_emb, int32_t n_pos, int32_t D,
+                                       const float* d_ln_weight, const float* d_ln_bias, const float* d_lin_weight,
+                                       const float* d_lin_bias, double* d_ws_means, float* d_xw, float* d_yw,
+                                       float* d_gxx, float* d_gxy, float* d_gyy, float* d_c, void* stream);
+RDV_API int rdv_vt5_input_embeds_f32(const rdv_vt5_embed_tables* t, const int64_t* d_ids, const int64_t* d_boxes,
+                                     const int64_t* d_labels, int32_t B, int32_t L, int64_t ld, float* d_out,
+                                     int32_t* d_bad, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -214,6 +214,31 @@ def pooled_patch_scores(patch_embeddings: Sequence[torch.Tensor], question_embed
     return sims, strips, q
 
 
+# --------------------------------------------------------------------------------------
+# f2: the generator's input embeddings   reference: src/_modules.py:70-86, src/VT5.py:194-204
+# --------------------------------------------------------------------------------------
+def spatial_embeddings(bbox: torch.Tensor, x_emb: torch.Tensor, y_emb: torch.Tensor, ln_weight: torch.Tensor,
+                       ln_bias: torch.Tensor, eps: float, lin_weight: torch.Tensor, lin_bias: torch.Tensor) -> torch.Tensor:
+    """SpatialEmbeddings.forward in eval mode (dropout = identity): the same torch operators in the same order, in the
+    dtype of the weights (float32 = the reference; pass float64 copies for the yardstick)."""
+    left = F.embedding(bbox[:, :, 0], x_emb)                             # :71
+    upper = F.embedding(bbox[:, :, 1], y_emb)                            # :72
+    right = F.embedding(bbox[:, :, 2], x_emb)                            # :73
+    lower = F.embedding(bbox[:, :, 3], y_emb)                            # :74
+    emb = left + upper + right + lower                                   # :76-81
+    emb = F.layer_norm(emb, (emb.shape[-1],), ln_weight, ln_bias, eps)   # :83 (BertLayerNorm = nn.LayerNorm)
+    return F.linear(emb, lin_weight, lin_bias)                           # :85 (MLP with one layer = nn.Linear)
+
+
+def vt5_input_embeds(input_ids: torch.Tensor, bbox: torch.Tensor, shared: torch.Tensor, spatial: torch.Tensor,
+                     layout_labels: torch.Tensor = None, layout_emb: torch.Tensor = None, layout_scale: float = 1.0):
+    """The sum of VT5.prepare_inputs_for_vqa (src/VT5.py:194-204); `spatial` = spatial_embeddings(bbox, ...)."""
+    out = F.embedding(input_ids, shared) + spatial                       # :195, :202
+    if layout_labels is not None:
+        out = out + F.embedding(layout_labels, layout_emb) * layout_scale    # :198, :204
+    return out
+
+
 def late_interaction(query: torch.Tensor, patches: torch.Tensor) -> torch.Tensor:
     qn = F.normalize(query, p=2, dim=-1)                                # :445
     pn = F.normalize(patches, p=2, dim=-1)                              # :446

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Struc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA = 0, 1, 2
@@ -61,6 +61,13 @@ class P2SArgsStruct(Structure):
                 ("doc_total", c_void_p), ("out", c_void_p), ("mask", c_void_p), ("max_h", c_int32), ("reserved", c_int32)]
 
 
+class EmbedTablesStruct(Structure):
+    """Mirror of `rdv_vt5_embed_tables` (include/rdv.h)."""
+    _fields_ = [("D", c_int32), ("n_pos", c_int32)] + [(n, c_void_p) for n in ("xw", "yw", "gxx", "gxy", "gyy", "c")] + [
+        ("eps", c_float), ("V", c_int32), ("shared", c_void_p), ("layout", c_void_p), ("n_labels", c_int32),
+        ("layout_scale", c_float)]
+
+
 class SmallLayoutStruct(Structure):
     """Mirror of `rdv_small_layout` (include/rdv.h)."""
     _fields_ = [(n, c_int32) for n in ("algo", "tile_rows", "n_tiles", "max_rows")] + [(n, c_int64) for n in (
@@ -105,6 +112,11 @@ SIGNATURES = {
     "rdv_pooled_select_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
+    "rdv_struct_size": (c_int64, [c_char_p]),
+    "rdv_vt5_embed_tables_build": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdv_vt5_input_embeds_f32": (c_int32, [POINTER(EmbedTablesStruct), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64,
+                                           c_void_p, c_void_p, c_void_p]),
     "rdv_mean_pool_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "rdv_row_inv_norm_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),

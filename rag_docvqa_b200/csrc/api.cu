@@ -52,9 +52,19 @@ int sm_count() {
 
 }  // namespace rdv
 
-extern "C" int rdv_abi_version(void) { return 16; }
+extern "C" int rdv_abi_version(void) { return 17; }
 
 extern "C" const char* rdv_last_error(void) { return rdv::g_error; }
+
+extern "C" int64_t rdv_struct_size(const char* name) {
+    if (!name) return -1;
+#define RDV_SIZE_OF(T) if (strcmp(name, #T) == 0) return (int64_t)sizeof(T)
+    RDV_SIZE_OF(rdv_tile_desc); RDV_SIZE_OF(rdv_cta_desc); RDV_SIZE_OF(rdv_small_layout); RDV_SIZE_OF(rdv_chunk_rec);
+    RDV_SIZE_OF(rdv_tok_rec); RDV_SIZE_OF(rdv_docstore); RDV_SIZE_OF(rdv_gather_args); RDV_SIZE_OF(rdv_pagestore);
+    RDV_SIZE_OF(rdv_visual_args); RDV_SIZE_OF(rdv_p2s_img); RDV_SIZE_OF(rdv_p2s_args); RDV_SIZE_OF(rdv_vt5_embed_tables);
+#undef RDV_SIZE_OF
+    return -1;
+}
 
 extern "C" int rdv_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
     int dev = 0;

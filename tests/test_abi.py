@@ -80,3 +80,15 @@ def test_argument_errors_are_reported_before_any_launch():
     assert lib.rdv_page_vote(None, None, None, None, 0, 5, 1, 1, None, None, None) == _lib.OK
     assert lib.rdv_layout_assign(None, None, None, None, None, None, None, 0, 1, None, None, None, None) == _lib.OK
     assert lib.rdv_s2_weights(None, None, 0, None, 0, 0, None, 0, None, None) == _lib.OK
+
+
+def test_ctypes_struct_layouts_match_the_header():
+    """Every struct the binding mirrors by hand has the size the compiler gave it (rdv_struct_size)."""
+    from rag_docvqa_b200 import _lib
+    mirrors = {"rdv_docstore": _lib.DocStoreStruct, "rdv_gather_args": _lib.GatherArgsStruct, "rdv_pagestore": _lib.PageStoreStruct,
+               "rdv_visual_args": _lib.VisualArgsStruct, "rdv_p2s_args": _lib.P2SArgsStruct,
+               "rdv_small_layout": _lib.SmallLayoutStruct, "rdv_vt5_embed_tables": _lib.EmbedTablesStruct}
+    for name, mirror in mirrors.items():
+        assert _lib.lib.rdv_struct_size(name.encode()) == ctypes.sizeof(mirror), name
+    assert _lib.lib.rdv_struct_size(b"rdv_chunk_rec") == 32 and _lib.lib.rdv_struct_size(b"rdv_tok_rec") == 32
+    assert _lib.lib.rdv_struct_size(b"no_such_struct") == -1

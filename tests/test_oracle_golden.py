@@ -282,3 +282,38 @@ def test_pooled_patch_golden(golden_dir):
         live = retr._get_similarities([p.reshape(-1, p.shape[2]) for p in patches], model_utils.mean_pooling(q, mask))
         for b in range(n_docs):
             assert torch.equal(sims[b], live[b])
+
+
+def test_vt5_embed_golden(golden_dir):
+    """The generator-input embeddings: the oracle's restatement of SpatialEmbeddings.forward and of the embedding sum of
+    VT5.prepare_inputs_for_vqa equals what the reference's own module / method produced (tests/golden/vt5_embed.npz; same
+    torch CPU operators in the same order), and the live module when the reference is mounted."""
+    z = np.load(os.path.join(golden_dir, "vt5_embed.npz"))
+    w = {k: torch.from_numpy(z[k]) for k in ("x_emb", "y_emb", "ln_weight", "ln_bias", "lin_weight", "lin_bias", "shared", "layout")}
+    eps = float(z["eps"])
+
+    def spatial(bbox):
+        return R.spatial_embeddings(bbox, w["x_emb"], w["y_emb"], w["ln_weight"], w["ln_bias"], eps, w["lin_weight"], w["lin_bias"])
+    bbox = torch.from_numpy(z["bbox"])
+    torch.testing.assert_close(spatial(bbox), torch.from_numpy(z["spatial"]), rtol=1e-6, atol=1e-6)
+    for name, labelled in (("plain", False), ("layout", True)):
+        ids, boxes = torch.from_numpy(z[name + "_ids"]), torch.from_numpy(z[name + "_boxes"])
+        labels = torch.from_numpy(z[name + "_labels"]) if labelled else None
+        got = R.vt5_input_embeds(ids, boxes, w["shared"], spatial(boxes), labels, w["layout"], float(z["layout_scale"]))
+        torch.testing.assert_close(got, torch.from_numpy(z[name + "_embeds"]), rtol=1e-6, atol=1e-6)
+    # float64 weights: the yardstick the GPU test measures both against
+    w64 = {k: v.double() for k, v in w.items()}
+    ref64 = R.spatial_embeddings(bbox, w64["x_emb"], w64["y_emb"], w64["ln_weight"], w64["ln_bias"], eps, w64["lin_weight"], w64["lin_bias"])
+    assert (ref64.float() - torch.from_numpy(z["spatial"])).abs().max() < 2e-5
+    if reference_available():
+        import types
+        from oracle.ref_import import import_reference
+        modules, _, _ = import_reference()
+        cfg = types.SimpleNamespace(max_2d_position_embeddings=w["x_emb"].shape[0], hidden_size=w["x_emb"].shape[1],
+                                    layer_norm_eps=eps, hidden_dropout_prob=0.1)
+        live = modules.SpatialEmbeddings(cfg).eval()
+        live.load_state_dict({"x_position_embeddings.weight": w["x_emb"], "y_position_embeddings.weight": w["y_emb"],
+                              "LayerNorm.weight": w["ln_weight"], "LayerNorm.bias": w["ln_bias"],
+                              "spatial_emb_matcher.layers.0.weight": w["lin_weight"], "spatial_emb_matcher.layers.0.bias": w["lin_bias"]})
+        with torch.no_grad():
+            assert torch.equal(live(bbox), spatial(bbox))
