@@ -34,6 +34,7 @@ struct EmbedParams {
     float* out;              // (B, L, D) contiguous
     int32_t* bad;            // |= 1 box coordinate, |= 2 token id, |= 4 layout label outside its table
     int32_t layout_in_smem;  // the layout table fits kEmbLayoutSmem: staged once per block
+    int32_t* work;           // {next chunk, blocks done}: zero before the launch, zero again after it
 };
 
 struct __align__(16) TokMeta {   // what the consumers need about one token: two 16-byte shared-memory loads
@@ -48,48 +49,87 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     return v;
 }
 
-// Persistent.  A block = D / 4 consumer threads, one float4 COLUMN each, + one producer warp.
-//   producer warp: runs two chunks of 32 tokens ahead.  Lane = token: ids, box and label, validation, the ten Gram entries
-//     of the variance (ten independent loads per lane: one round for 32 tokens), 1 / sqrt(var + eps), "same box as the
-//     previous token" -> shared memory.  One __syncthreads per chunk hands a chunk over.
-//   consumer thread: walks the block's contiguous run of tokens with a register ring of kEmbDepth tokens in flight (the four
-//     coordinate rows' and the token row's float4 of ITS column: 5 independent 128-bit loads per token, coalesced across the
-//     block), adds, scales, writes its column of the output row.  A repeated box (all tokens of a word, the prompt, the
-//     padding) costs one load: the spatial value of the column stays in a register.
+__device__ __forceinline__ uint32_t emb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void emb_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(emb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void emb_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void emb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(emb_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// Persistent.  A block = D / 4 consumer threads, one float4 COLUMN each, + one producer warp; chunks of 32 tokens are
+// handed out by an atomic counter (a chunk of padding costs a fifth of a chunk of words: a static split left SMs idle).
+//   producer warp: claims the next chunk and describes it, up to kEmbSlots chunks ahead.  Lane = token: ids, box and label,
+//     validation, the ten Gram entries of the variance (ten independent loads per lane: one round for 32 tokens),
+//     1 / sqrt(var + eps), "same box as the previous token" -> a shared-memory slot, published through an mbarrier.
+//   consumer thread: a register ring of kEmbDepth tokens in flight (the four coordinate rows' and the token row's float4 of
+//     ITS column: 5 independent 128-bit loads per token, coalesced across the block), adds, scales, writes its column of
+//     the output row; the ring runs on into the next chunk.  A repeated box (all tokens of a word, the prompt, the padding)
+//     costs one load: the spatial value of the column stays in a register.  A warp releases a slot when it is through
+//     with it: consumer warps never wait for each other.
 // History, 64 x 512 tokens at D = 768: a warp per token with the rows in registers (four rounds of dependent loads per
 // token) 122 us; per-warp shared-memory rings filled by 1-D bulk copies (TMA) or by cp.async 67-77 us -- six warps per SM
-// spent ~460 instructions per token on addressing and issue, and the rings sat half empty.  A thread per column needs ~40.
+// spent ~460 instructions per token on addressing and issue, and the rings sat half empty; a thread per column with a
+// static split of the tokens and a __syncthreads per chunk 59 us (26 % of the stall samples at the barrier).
+constexpr int kEmbSlots = 4;
+
 template <bool LAYOUT, bool WIDE>      // WIDE: D > 896 (more than 224 consumer threads): one block per SM
 __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) vt5_embed_kernel(const EmbedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];              // the layout table, when it is staged
-    __shared__ TokMeta s_meta[3][kEmbChunk];
+    __shared__ TokMeta s_meta[kEmbSlots][kEmbChunk];
+    __shared__ int s_chunk[kEmbSlots];                                      // the chunk a slot describes, -1: no more chunks
+    __shared__ __align__(8) uint64_t s_full[kEmbSlots], s_empty[kEmbSlots];
     const rdv_vt5_embed_tables& T = p.t;
     const int d4 = T.D >> 2, np = T.n_pos;
     const int n_cons = (int)blockDim.x - 32;                                // consumer threads (>= d4, multiple of 32)
     const int tid = threadIdx.x;
     const int64_t n = (int64_t)p.B * p.L;
-    // the block's tokens: a contiguous run, split evenly in units of the ring depth; chunks are counted from its start
-    const int64_t units = (n + kEmbDepth - 1) / kEmbDepth;
-    const int64_t t_begin = (int64_t)blockIdx.x * units / gridDim.x * kEmbDepth;
-    const int64_t t_end = min(n, (int64_t)(blockIdx.x + 1) * units / gridDim.x * kEmbDepth);
-    if (t_begin >= t_end) return;
-    const int64_t c_end = (t_end - t_begin + kEmbChunk - 1) / kEmbChunk;      // chunks 0 .. c_end - 1
+    const int n_chunks = (int)((n + kEmbChunk - 1) / kEmbChunk);
 
+    if (tid == 0) {
+        for (int i = 0; i < kEmbSlots; ++i) {
+            emb_mbar_init(&s_full[i], 1);
+            emb_mbar_init(&s_empty[i], (uint32_t)(n_cons >> 5));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (LAYOUT && p.layout_in_smem) {
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         const float4* src = reinterpret_cast<const float4*>(T.layout);
         for (int i = tid; i < T.n_labels * d4; i += blockDim.x) dst[i] = __ldg(src + i);
     }
+    __syncthreads();
 
     if (tid >= n_cons) {
         // ------------------------------------------------ producer warp ------------------------------------------------
         const int lane = tid - n_cons;
         int bad = 0;
-        int last_l = -1, last_u = -1, last_r = -1, last_b = -1;             // box of the previous chunk's last token
-        auto produce = [&](int64_t chunk) {
+        for (int k = 0;; ++k) {
+            const int slot = k % kEmbSlots;
+            if (k >= kEmbSlots) emb_mbar_wait(&s_empty[slot], (uint32_t)(k / kEmbSlots - 1) & 1u);
+            int chunk = 0;
+            if (lane == 0) chunk = atomicAdd(p.work, 1);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk >= n_chunks) {
+                if (lane == 0) {
+                    s_chunk[slot] = -1;
+                    emb_mbar_arrive(&s_full[slot]);
+                }
+                break;
+            }
             TokMeta m = {};
-            const int64_t tok = t_begin + chunk * kEmbChunk + lane;
-            if (tok < t_end) {
+            const int64_t tok = (int64_t)chunk * kEmbChunk + lane;
+            if (tok < n) {
                 const int64_t src = (tok / p.L) * p.ld + (tok % p.L);
                 const longlong2* bx = reinterpret_cast<const longlong2*>(p.boxes + src * 4);
                 const longlong2 b0 = bx[0], b1 = bx[1];
@@ -115,28 +155,30 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
                 const double cross = (((double)g4 + (double)g5) + ((double)g6 + (double)g7)) + ((double)g8 + (double)g9);
                 m.rstd = (float)(1.0 / sqrt(fmax(sq + 2.0 * cross, 0.0) / (double)T.D + (double)T.eps));
             }
-            int pl = __shfl_up_sync(0xffffffffu, m.l, 1), pu = __shfl_up_sync(0xffffffffu, m.u, 1);
-            int pr = __shfl_up_sync(0xffffffffu, m.r, 1), pb = __shfl_up_sync(0xffffffffu, m.b, 1);
-            if (lane == 0) { pl = last_l; pu = last_u; pr = last_r; pb = last_b; }
-            m.same = m.l == pl && m.u == pu && m.r == pr && m.b == pb;
-            last_l = __shfl_sync(0xffffffffu, m.l, 31); last_u = __shfl_sync(0xffffffffu, m.u, 31);
-            last_r = __shfl_sync(0xffffffffu, m.r, 31); last_b = __shfl_sync(0xffffffffu, m.b, 31);
-            s_meta[chunk % 3][lane] = m;
-        };
-        produce(0);
-        produce(1);
-        __syncthreads();
-        for (int64_t chunk = 0; chunk < c_end; ++chunk) {
-            produce(chunk + 2);                             // while the consumers stream `chunk` (and prefetch into chunk + 1)
-            __syncthreads();
+            const int pl = __shfl_up_sync(0xffffffffu, m.l, 1), pu = __shfl_up_sync(0xffffffffu, m.u, 1);
+            const int pr = __shfl_up_sync(0xffffffffu, m.r, 1), pb = __shfl_up_sync(0xffffffffu, m.b, 1);
+            m.same = lane > 0 && m.l == pl && m.u == pu && m.r == pr && m.b == pb;   // a chunk's first token always loads
+            s_meta[slot][lane] = m;
+            if (lane == 0) s_chunk[slot] = chunk;
+            __syncwarp();
+            if (lane == 0) emb_mbar_arrive(&s_full[slot]);  // release: the slot's contents are visible to whoever sees the flip
         }
         if (bad && p.bad) atomicOr(p.bad, bad);
+        if (lane == 0) {
+            // every block passes here only after the counter has run out: the last one puts the workspace back to zero
+            __threadfence();
+            if (atomicAdd(p.work + 1, 1) == (int)gridDim.x - 1) {
+                atomicExch(p.work, 0);
+                atomicExch(p.work + 1, 0);
+            }
+        }
         return;
     }
 
     // ---------------------------------------------------- consumers ----------------------------------------------------
     const int c = tid;                                       // this thread's float4 column
     const bool active = c < d4;
+    const int lane = tid & 31;
     const float4* xw = reinterpret_cast<const float4*>(T.xw) + c;
     const float4* yw = reinterpret_cast<const float4*>(T.yw) + c;
     const float4* sem = reinterpret_cast<const float4*>(T.shared) + c;
@@ -153,10 +195,10 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
         const int4 lurb = *reinterpret_cast<const int4*>(&m.l);
         const int4 rest = *reinterpret_cast<const int4*>(&m.id);            // id, lab, same, rstd
         if (!rest.z) {
-            buf[slot][0] = __ldg(xw + (size_t)lurb.x * d4); buf[slot][1] = __ldg(yw + (size_t)lurb.y * d4);
-            buf[slot][2] = __ldg(xw + (size_t)lurb.z * d4); buf[slot][3] = __ldg(yw + (size_t)lurb.w * d4);
+            buf[slot][0] = ldg_stream(xw + (size_t)lurb.x * d4); buf[slot][1] = ldg_stream(yw + (size_t)lurb.y * d4);
+            buf[slot][2] = ldg_stream(xw + (size_t)lurb.z * d4); buf[slot][3] = ldg_stream(yw + (size_t)lurb.w * d4);
         }
-        if (has_ids) buf[slot][4] = __ldg(sem + (size_t)rest.x * d4);
+        if (has_ids) buf[slot][4] = ldg_stream(sem + (size_t)rest.x * d4);
     };
     auto consume = [&](int slot, const TokMeta& m, float4* dst) {
         const int4 rest = *reinterpret_cast<const int4*>(&m.id);
@@ -180,33 +222,47 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
         }
         __stcs(dst, o);                                      // written once, read by the next model stage
     };
+    auto tokens_of = [&](int chunk) { return chunk < 0 ? 0 : (int)min((int64_t)kEmbChunk, n - (int64_t)chunk * kEmbChunk); };
 
-    __syncthreads();                                         // chunks 0 and 1 are described (and the layout table staged)
-    const int n_local = (int)(t_end - t_begin);
+    emb_mbar_wait(&s_full[0], 0);
+    int chunk = s_chunk[0];
+    int ntok = tokens_of(chunk);
     if (active) {
 #pragma unroll
         for (int i = 0; i < kEmbDepth; ++i)
-            if (i < n_local) load(i, s_meta[0][i]);
+            if (i < ntok) load(i, s_meta[0][i]);
     }
-    float4* dst = out + (size_t)t_begin * d4;
-    for (int chunk = 0; chunk < (int)c_end; ++chunk) {
-        const TokMeta* cur = s_meta[chunk % 3];
-        const TokMeta* nxt = s_meta[(chunk + 1) % 3];
-        const int left = n_local - chunk * kEmbChunk;        // tokens from the start of this chunk to the end of the run
-        if (active) {
+    for (int k = 0; chunk >= 0; ++k) {
+        const int slot = k % kEmbSlots, nslot = (k + 1) % kEmbSlots;
+        const TokMeta* cur = s_meta[slot];
+        const TokMeta* nxt = s_meta[nslot];
+        float4* dst = out + (size_t)chunk * kEmbChunk * d4;
+        int nchunk = -1, nntok = 0;
 #pragma unroll 1
-            for (int q0 = 0; q0 < kEmbChunk; q0 += kEmbDepth) {
+        for (int q0 = 0; q0 < kEmbChunk; q0 += kEmbDepth) {
+            if (q0 == kEmbChunk - kEmbDepth) {               // the ring is about to run on into the next chunk
+                emb_mbar_wait(&s_full[nslot], (uint32_t)((k + 1) / kEmbSlots) & 1u);
+                nchunk = s_chunk[nslot];
+                nntok = tokens_of(nchunk);
+            }
+            if (active) {
 #pragma unroll
                 for (int i = 0; i < kEmbDepth; ++i) {        // one revolution of the ring: slots are literals
                     const int q = q0 + i;
-                    if (q < left) consume(i, cur[q], dst + (size_t)q * d4);
-                    const int k = q + kEmbDepth;             // may reach into chunk + 1: described one barrier ago
-                    if (k < left) load(i, k < kEmbChunk ? cur[k] : nxt[k - kEmbChunk]);
+                    if (q < ntok) consume(i, cur[q], dst + (size_t)q * d4);
+                    const int kk = q + kEmbDepth;
+                    if (kk < kEmbChunk) {
+                        if (kk < ntok) load(i, cur[kk]);
+                    } else if (kk - kEmbChunk < nntok) {
+                        load(i, nxt[kk - kEmbChunk]);
+                    }
                 }
             }
         }
-        dst += (size_t)kEmbChunk * d4;
-        __syncthreads();                                     // chunk + 2 is described; chunk's slot may be overwritten next round
+        __syncwarp();
+        if (lane == 0) emb_mbar_arrive(&s_empty[slot]);      // this warp is through with the slot
+        chunk = nchunk;
+        ntok = nntok;
     }
 }
 
@@ -285,13 +341,14 @@ extern "C" int rdv_vt5_embed_tables_build(const float* d_x_emb, const float* d_y
 
 extern "C" int rdv_vt5_input_embeds_f32(const rdv_vt5_embed_tables* t, const int64_t* d_ids, const int64_t* d_boxes,
                                         const int64_t* d_labels, int32_t B, int32_t L, int64_t ld, float* d_out,
-                                        int32_t* d_bad, void* stream) {
+                                        int32_t* d_bad, int32_t* d_work, void* stream) {
     using namespace rdv;
     RDV_REQUIRE(t, RDV_E_INVALID, "vt5_input_embeds_f32: null tables");
     RDV_REQUIRE(B >= 0 && L >= 0 && ld >= L, RDV_E_INVALID, "vt5_input_embeds_f32: B=%d, L=%d, ld=%lld", B, L, (long long)ld);
     RDV_REQUIRE(t->D >= 4 && t->D <= 1024 && (t->D & 3) == 0 && t->n_pos >= 1, RDV_E_INVALID,
                 "vt5_input_embeds_f32: D=%d must be a multiple of 4 in [4, 1024]", t->D);
     if ((int64_t)B * L == 0) return RDV_OK;
+    RDV_REQUIRE(d_work, RDV_E_INVALID, "vt5_input_embeds_f32: null workspace");
     RDV_REQUIRE(d_boxes && d_out && t->xw && t->yw && t->gxx && t->gxy && t->gyy && t->c, RDV_E_INVALID,
                 "vt5_input_embeds_f32: null pointer");
     RDV_REQUIRE(!d_ids || (t->shared && t->V >= 1), RDV_E_INVALID, "vt5_input_embeds_f32: input ids without a token table");
@@ -300,16 +357,17 @@ extern "C" int rdv_vt5_input_embeds_f32(const rdv_vt5_embed_tables* t, const int
                 (!d_ids || aligned16(t->shared)) && (!d_labels || aligned16(t->layout)), RDV_E_ALIGN,
                 "vt5_input_embeds_f32: boxes, out and the tables must be 16-byte aligned");
     EmbedParams p;
-    p.t = *t; p.ids = d_ids; p.boxes = d_boxes; p.labels = d_labels; p.B = B; p.L = L; p.ld = ld; p.out = d_out; p.bad = d_bad;
+    p.t = *t; p.ids = d_ids; p.boxes = d_boxes; p.labels = d_labels; p.B = B; p.L = L; p.ld = ld; p.out = d_out; p.bad = d_bad; p.work = d_work;
     const int d4 = t->D / 4;
     const int threads = (d4 + 31) / 32 * 32 + 32;           // one float4 column per consumer thread + the producer warp
     const size_t layout_bytes = d_labels ? (size_t)t->n_labels * t->D * 4 : 0;
     p.layout_in_smem = d_labels && layout_bytes <= (size_t)kEmbLayoutSmem;
     const size_t smem = p.layout_in_smem ? layout_bytes : 0;
     const int64_t n = (int64_t)B * L;
-    const int64_t units = (n + kEmbDepth - 1) / kEmbDepth;
-    int64_t blocks = 2 * (int64_t)sm_count();               // two resident blocks per SM, each a contiguous run of tokens
-    if (blocks > units) blocks = units;
+    const int64_t chunks = (n + kEmbChunk - 1) / kEmbChunk;
+    RDV_REQUIRE(chunks < (1ll << 31), RDV_E_LIMIT, "vt5_input_embeds_f32: %lld tokens", (long long)n);
+    int64_t blocks = (threads > 256 ? 1 : 2) * (int64_t)sm_count();      // every resident slot of the device, once
+    if (blocks > chunks) blocks = chunks;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool wide = threads > 256;
     if (d_labels && wide) {

@@ -50,6 +50,7 @@ class SpatialEmbeddings:
         self.gyy = torch.empty((n_pos, n_pos), dtype=torch.float32, device=device)
         self.c = torch.empty((D,), dtype=torch.float32, device=device)
         self.bad = torch.zeros((1,), dtype=torch.int32, device=device)
+        self._work = {}                                                 # stream -> the kernel's chunk counter (kept zero)
         with torch.cuda.device(device):
             means = torch.empty((2 * n_pos,), dtype=torch.float64, device=device)
             _lib.check(_lib_fn.rdv_vt5_embed_tables_build(
@@ -109,9 +110,13 @@ class SpatialEmbeddings:
             ids_r = None if ids is None else ids.contiguous()
             lab_r = None if labels is None else labels.contiguous()
         with torch.cuda.device(boxes.device):
+            stream = _stream_ptr(boxes.device)
+            work = self._work.get(stream)
+            if work is None:
+                work = self._work[stream] = torch.zeros((2,), dtype=torch.int32, device=self.device)
             _lib.check(_lib_fn.rdv_vt5_input_embeds_f32(
                 ctypes.byref(struct), 0 if ids_r is None else ids_r.data_ptr(), boxes.data_ptr(),
-                0 if lab_r is None else lab_r.data_ptr(), B, L, ld, out.data_ptr(), self.bad.data_ptr(), _stream_ptr(boxes.device)))
+                0 if lab_r is None else lab_r.data_ptr(), B, L, ld, out.data_ptr(), self.bad.data_ptr(), work.data_ptr(), stream))
         return out
 
     def forward(self, bbox: torch.Tensor) -> torch.Tensor:
