@@ -160,6 +160,10 @@ __global__ void __launch_bounds__(kPoolThreads, 4) mean_pool_kernel(const PoolPa
 // of the row exactly as the kernel above does, stores its partial row into the LEADER's shared memory (st.shared::cluster),
 // and after one cluster barrier the leader adds the S partial rows in rank order (deterministic), divides and normalises.
 // ---------------------------------------------------------------------------------------------------------------------
+// 1024 threads: with D = 768 that is five token groups per CTA, 960 threads x 8 independent 128-bit loads = 120 KB in
+// flight per SM (256 threads: one group, 24 KB in flight, 60 us for the 50 MB of 8 x 2048 x 768 questions).
+constexpr int kSplitThreads = 1024;
+
 __device__ __forceinline__ uint32_t pool_cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -172,10 +176,10 @@ __device__ __forceinline__ void pool_remote_store(const void* local, uint32_t ra
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(r), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(kPoolThreads) mean_pool_split_kernel(const PoolParams p, const int S) {
+__global__ void __launch_bounds__(kSplitThreads) mean_pool_split_kernel(const PoolParams p, const int S) {
     extern __shared__ float4 s_dyn[];             // [G][cols] group partials | [S][d4] the ranks' partial rows (leader's copy is read)
     __shared__ float s_mask[kPoolMaxL];
-    __shared__ float s_red[kPoolThreads / 32];
+    __shared__ float s_red[kSplitThreads / 32];
     __shared__ float s_scalar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(kPoolThreads) mean_pool_split_kernel(const Poo
     const int64_t* mrow = p.mask + (size_t)row * p.L;
 
     float cnt = 0.f;                              // the whole mask row in every CTA: the same count, summed in the same order
-    for (int t = tid; t < p.L; t += kPoolThreads) {
+    for (int t = tid; t < p.L; t += kSplitThreads) {
         const float m = (float)mrow[t];
         s_mask[t] = m;
         cnt += m;
@@ -195,14 +199,14 @@ __global__ void __launch_bounds__(kPoolThreads) mean_pool_split_kernel(const Poo
     __syncthreads();
     if (tid == 0) {
         float c = 0.f;
-        for (int w = 0; w < kPoolThreads / 32; ++w) c += s_red[w];
+        for (int w = 0; w < kSplitThreads / 32; ++w) c += s_red[w];
         s_scalar[0] = fmaxf(c, 1e-9f);
     }
     __syncthreads();
     const float denom = s_scalar[0];
 
-    const int cols = d4 < kPoolThreads ? d4 : kPoolThreads;
-    const int G = kPoolThreads / cols;
+    const int cols = d4 < kSplitThreads ? d4 : kSplitThreads;
+    const int G = kSplitThreads / cols;
     const int g = tid / cols, c0 = tid - g * cols;
     const bool active = g < G;
     const int per = (p.L + S - 1) / S;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(kPoolThreads) mean_pool_split_kernel(const Poo
     if (rank != 0) return;
 
     float ss_local = 0.f;
-    for (int c = tid; c < d4; c += kPoolThreads) {
+    for (int c = tid; c < d4; c += kSplitThreads) {
         float4 acc = s_rows[c];
         for (int r = 1; r < S; ++r) {
             const float4 o = s_rows[(size_t)r * d4 + c];
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(kPoolThreads) mean_pool_split_kernel(const Poo
     __syncthreads();
     if (tid == 0) {
         float s = 0.f;
-        for (int w = 0; w < kPoolThreads / 32; ++w) s += s_red[w];
+        for (int w = 0; w < kSplitThreads / 32; ++w) s += s_red[w];
         const float nrm = __fsqrt_rn(s);
         s_scalar[1] = nrm;
         if (p.out_norm) p.out_norm[row] = nrm;
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kPoolThreads) mean_pool_split_kernel(const Poo
     __syncthreads();
     if (!p.normalise) return;
     const float inv_den = fmaxf(s_scalar[1], 1e-12f);
-    for (int c = tid; c < d4; c += kPoolThreads) {
+    for (int c = tid; c < d4; c += kSplitThreads) {
         float4 v = s_rows[c];
         v.x = __fdiv_rn(v.x, inv_den); v.y = __fdiv_rn(v.y, inv_den);
         v.z = __fdiv_rn(v.z, inv_den); v.w = __fdiv_rn(v.w, inv_den);
@@ -342,7 +346,9 @@ extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int
     const size_t smem = ((size_t)G * cols + (size_t)d4) * sizeof(float4);
     RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024),
                         "cudaFuncSetAttribute(mean_pool)");
-    const int S = pool_split(n, L, d, (size_t)G * cols * sizeof(float4));
+    const int cols_s = d4 < kSplitThreads ? d4 : kSplitThreads;
+    const int G_s = kSplitThreads / cols_s;
+    const int S = pool_split(n, L, d, (size_t)G_s * cols_s * sizeof(float4));
     if (S > 1) {
         RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSplitSmem),
                             "cudaFuncSetAttribute(mean_pool_split)");
@@ -350,8 +356,8 @@ extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int
                             "cudaFuncSetAttribute(mean_pool_split, cluster)");
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)n * S);
-        cfg.blockDim = dim3(kPoolThreads);
-        cfg.dynamicSmemBytes = ((size_t)G * cols + (size_t)S * d4) * sizeof(float4);
+        cfg.blockDim = dim3(kSplitThreads);
+        cfg.dynamicSmemBytes = ((size_t)G_s * cols_s + (size_t)S * d4) * sizeof(float4);
         cfg.stream = static_cast<cudaStream_t>(stream);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
