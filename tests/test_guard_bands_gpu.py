@@ -146,6 +146,20 @@ def test_pool_maxsim_merge_pooled():
     run_guarded(T.test_topk_segments_matches_oracle)
     run_guarded(T.test_topk_merge_equals_unsharded, 4, 10)
     run_guarded(T.test_pooled_patch_golden, GOLDEN)
+    run_guarded(T.test_pooled_patch_c4_shape_and_nan)
+    for split, n, L, d in (("auto", 8, 2048, 768), ("16", 3, 1000, 1024), ("2", 5, 70, 768), ("16", 1, 4096, 64)):
+        with pytest.MonkeyPatch.context() as mp:                 # the cluster-split pooling kernel: leader's DSMEM rows
+            run_guarded(T.test_mean_pooling_row_split_over_a_cluster, mp, split, n, L, d)
+
+
+def test_input_embeddings():
+    import test_vt5_embed_gpu as T
+    run_guarded(T.test_golden_spatial_module_and_prepare_inputs, GOLDEN)
+    for D, B, L in ((768, 5, 131), (1024, 2, 77), (100, 2, 33), (4, 1, 5), (768, 1, 1)):
+        assert run_guarded(T.test_shapes_against_the_float64_oracle, D, B, L) > 0
+    run_guarded(T.test_trimmed_views_of_the_gather_buffers_and_empty_batches)
+    run_guarded(T.test_out_of_range_indices_are_flagged_not_read)
+    run_guarded(T.test_after_the_gather_kernel)
 
 
 def test_tensor_core_paths(monkeypatch):
