@@ -60,7 +60,7 @@ def ncu_traffic(kernel, grid):
         e = doc["kernels"].get("%s|grid %s|cold" % (kernel, grid))
         if e is None:
             return None
-        return {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "capture": e["capture"], "commit": doc.get("commit"),
+        return {"dram_bytes_per_launch": e["dram_bytes_per_launch"], "capture": e["capture"], "commit": e.get("commit", doc.get("commit")),
                 "ncu_duration_us_cold_serialised": e.get("duration_us")}
     except Exception:
         return None

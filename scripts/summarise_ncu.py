@@ -122,9 +122,18 @@ def main(tag):
     with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
         f.write("\n".join(lines) + "\n")
     tpath = os.path.join(OUT, "traffic.json")
+    # a kernel's entry carries the commit its capture was taken at: entries whose capture did not change keep theirs
+    head, old = commit(), {}
+    if os.path.exists(tpath):
+        prev = json.load(open(tpath))
+        old = {k: dict(v, commit=v.get("commit", prev.get("commit"))) for k, v in prev.get("kernels", {}).items()}
+    for k, v in traffic.items():
+        o = old.get(k)
+        same = o and o.get("capture") == v["capture"] and abs(o.get("duration_us", -1) - v["duration_us"]) < 1e-9
+        v["commit"] = o["commit"] if same else head
     doc = {"_comment": "per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) from `ncu --set full` captures; "
-                       "bench.py copies the entry of its dominant kernel into roofline.traffic together with `capture` and `commit`",
-           "commit": commit(), "round": tag, "kernels": traffic}
+                       "bench.py copies the entry of its dominant kernel into roofline.traffic together with `capture` and the entry's `commit` (the commit the capture was taken at; the top-level `commit` is the one the file was last regenerated at)",
+           "commit": head, "round": tag, "kernels": traffic}
     with open(tpath, "w") as f:
         json.dump(doc, f, indent=1)
     print("\n".join(lines[:40]))
