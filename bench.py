@@ -1309,7 +1309,7 @@ def pooled_config(B, strips, L, d, k):
 def run_pooled(args):
     """C4p (north_star's wording of configs[3]): every patch vector of 50 strips (102 400 x 768 fp32 = 315 MB per
     document) scored against the mean-pooled question, top-k patches, strips ranked by their best patch.  A step = one batch
-    of B questions through functional.pooled_patch_topk (pool, streaming score, three segmented top-k)."""
+    of B questions through functional.pooled_patch_topk (pool, streaming score, top-k per strip, per-document selection)."""
     from rag_docvqa_b200 import functional as F
     from rag_docvqa_b200 import synth
     ctx = Ctx()
