@@ -435,7 +435,9 @@ RDV_API int rdv_retrieve_vt5_f32(const rdv_cta_desc* d_ctas, int64_t n_ctas, int
  * (fp32; agrees with the reference's fp32 modules to ~1e-6 relative, the tolerance tests/test_vt5_embed_gpu.py states).
  *   d_ids (B, L) int64 or NULL (spatial embedding only), d_boxes (B, L, 4) int64, d_labels (B, L) int64 or NULL; row b of
  *   each starts b * ld tokens into its buffer (ld >= L: the gather's (B, max_len) buffers trimmed to the longest row);
- *   d_out (B, L, D) contiguous.  *d_bad (may be NULL) gets bit 0 / 1 / 2 set when a box coordinate / token id / layout
+ *   d_out (B, out_ld, D) with out_ld >= L: the tokens of row b go to rows [b * out_ld, b * out_ld + L) -- out_ld = L is the
+ *   contiguous (B, L, D); out_ld = L + n_visual_tokens writes straight into the buffer the reference builds with torch.cat
+ *   (src/VT5.py:205), whose tail the caller fills with the generator's visual tokens.  *d_bad (may be NULL) gets bit 0 / 1 / 2 set when a box coordinate / token id / layout
  *   label is outside its table (torch.nn.Embedding raises; here the entry is clamped and the flag tells the host).
  *   d_work: two int32 of scratch (the chunk counter of the persistent kernel), ZERO before the first launch; the kernel
  *   leaves them zero.  Launches that may run concurrently (different streams) need their own. */
@@ -457,7 +459,7 @@ RDV_API int rdv_vt5_embed_tables_build(const float* d_x_emb, const float* d_y_em
                                        float* d_gxx, float* d_gxy, float* d_gyy, float* d_c, void* stream);
 RDV_API int rdv_vt5_input_embeds_f32(const rdv_vt5_embed_tables* t, const int64_t* d_ids, const int64_t* d_boxes,
                                      const int64_t* d_labels, int32_t B, int32_t L, int64_t ld, float* d_out,
-                                     int32_t* d_bad, int32_t* d_work, void* stream);
+                                     int64_t out_ld, int32_t* d_bad, int32_t* d_work, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------

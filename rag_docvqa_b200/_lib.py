@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p, POINTER, Struc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librdv.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 OK, E_INVALID, E_ALIGN, E_CUDA, E_LIMIT = 0, -1, -2, -3, -4
 SCORE_AUTO, SCORE_LDG, SCORE_TMA = 0, 1, 2
@@ -116,7 +116,7 @@ SIGNATURES = {
     "rdv_vt5_embed_tables_build": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdv_vt5_input_embeds_f32": (c_int32, [POINTER(EmbedTablesStruct), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64,
-                                           c_void_p, c_void_p, c_void_p, c_void_p]),
+                                           c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "rdv_mean_pool_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "rdv_row_inv_norm_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),

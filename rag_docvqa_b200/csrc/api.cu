@@ -52,7 +52,7 @@ int sm_count() {
 
 }  // namespace rdv
 
-extern "C" int rdv_abi_version(void) { return 18; }
+extern "C" int rdv_abi_version(void) { return 19; }
 
 extern "C" const char* rdv_last_error(void) { return rdv::g_error; }
 

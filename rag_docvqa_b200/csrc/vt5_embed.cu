@@ -31,7 +31,8 @@ struct EmbedParams {
     const int64_t* labels;   // (B, L) rows `ld` apart or null
     int32_t B, L;
     int64_t ld;
-    float* out;              // (B, L, D) contiguous
+    float* out;              // (B, out_ld, D): row b of the tokens starts b * out_ld rows in (out_ld = L: contiguous)
+    int64_t out_ld;
     int32_t* bad;            // |= 1 box coordinate, |= 2 token id, |= 4 layout label outside its table
     int32_t layout_in_smem;  // the layout table fits kEmbLayoutSmem: staged once per block
     int32_t* work;           // {next chunk, blocks done}: zero before the launch, zero again after it
@@ -39,7 +40,9 @@ struct EmbedParams {
 
 struct __align__(16) TokMeta {   // what the consumers need about one token: two 16-byte shared-memory loads
     int l, u, r, b;
-    int id, lab, same;
+    int id;
+    int lab_same;                // label << 1 | "same box as the previous token of the chunk"
+    int out_tok;                 // row of the output this token is written to: b * out_ld + t
     float rstd;
 };
 
@@ -144,7 +147,9 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
                 }
                 if (p.ids && (unsigned long long)id >= (unsigned long long)T.V) { bad |= 2; id = 0; }
                 if (p.labels && (unsigned long long)lab >= (unsigned long long)T.n_labels) { bad |= 4; lab = 0; }
-                m.l = (int)c4[0]; m.u = (int)c4[1]; m.r = (int)c4[2]; m.b = (int)c4[3]; m.id = (int)id; m.lab = (int)lab;
+                m.l = (int)c4[0]; m.u = (int)c4[1]; m.r = (int)c4[2]; m.b = (int)c4[3]; m.id = (int)id;
+                m.lab_same = (int)lab << 1;
+                m.out_tok = (int)((tok / p.L) * p.out_ld + (tok % p.L));
                 // |x~_l + y~_u + x~_r + y~_b|^2: four squares and six cross terms, summed in fp64
                 const size_t lo = (size_t)m.l * np, uo = (size_t)m.u * np, ro = (size_t)m.r * np, bo = (size_t)m.b * np;
                 const float g0 = __ldg(T.gxx + lo + m.l), g1 = __ldg(T.gyy + uo + m.u), g2 = __ldg(T.gxx + ro + m.r);
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
             }
             const int pl = __shfl_up_sync(0xffffffffu, m.l, 1), pu = __shfl_up_sync(0xffffffffu, m.u, 1);
             const int pr = __shfl_up_sync(0xffffffffu, m.r, 1), pb = __shfl_up_sync(0xffffffffu, m.b, 1);
-            m.same = lane > 0 && m.l == pl && m.u == pu && m.r == pr && m.b == pb;   // a chunk's first token always loads
+            m.lab_same |= (lane > 0 && m.l == pl && m.u == pu && m.r == pr && m.b == pb) ? 1 : 0;   // a chunk's first token always loads
             s_meta[slot][lane] = m;
             if (lane == 0) s_chunk[slot] = chunk;
             __syncwarp();
@@ -193,16 +198,17 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
     float4 sp = cc;
     auto load = [&](int slot, const TokMeta& m) {            // the five loads of a token
         const int4 lurb = *reinterpret_cast<const int4*>(&m.l);
-        const int4 rest = *reinterpret_cast<const int4*>(&m.id);            // id, lab, same, rstd
-        if (!rest.z) {
+        const int4 rest = *reinterpret_cast<const int4*>(&m.id);            // id, label / same, output row, rstd
+        if (!(rest.y & 1)) {
             buf[slot][0] = ldg_stream(xw + (size_t)lurb.x * d4); buf[slot][1] = ldg_stream(yw + (size_t)lurb.y * d4);
             buf[slot][2] = ldg_stream(xw + (size_t)lurb.z * d4); buf[slot][3] = ldg_stream(yw + (size_t)lurb.w * d4);
         }
         if (has_ids) buf[slot][4] = ldg_stream(sem + (size_t)rest.x * d4);
     };
-    auto consume = [&](int slot, const TokMeta& m, float4* dst) {
+    auto consume = [&](int slot, const TokMeta& m) {
         const int4 rest = *reinterpret_cast<const int4*>(&m.id);
-        if (!rest.z) {
+        float4* dst = out + (size_t)rest.z * d4;
+        if (!(rest.y & 1)) {
             const float rstd = __int_as_float(rest.w);
             const float4 a0 = buf[slot][0], a1 = buf[slot][1], a2 = buf[slot][2], a3 = buf[slot][3];
             sp.x = fmaf(((a0.x + a1.x) + a2.x) + a3.x, rstd, cc.x);
@@ -216,7 +222,8 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
             o.x = __fadd_rn(e.x, o.x); o.y = __fadd_rn(e.y, o.y); o.z = __fadd_rn(e.z, o.z); o.w = __fadd_rn(e.w, o.w);
         }
         if (LAYOUT) {                                        // + layout * scale, the product rounded first (src/VT5.py:204)
-            const float4 e = p.layout_in_smem ? lay_s[(size_t)rest.y * d4] : __ldg(lay_g + (size_t)rest.y * d4);
+            const int lab = rest.y >> 1;
+            const float4 e = p.layout_in_smem ? lay_s[(size_t)lab * d4] : __ldg(lay_g + (size_t)lab * d4);
             o.x = __fadd_rn(o.x, __fmul_rn(e.x, scale)); o.y = __fadd_rn(o.y, __fmul_rn(e.y, scale));
             o.z = __fadd_rn(o.z, __fmul_rn(e.z, scale)); o.w = __fadd_rn(o.w, __fmul_rn(e.w, scale));
         }
@@ -236,7 +243,6 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
         const int slot = k % kEmbSlots, nslot = (k + 1) % kEmbSlots;
         const TokMeta* cur = s_meta[slot];
         const TokMeta* nxt = s_meta[nslot];
-        float4* dst = out + (size_t)chunk * kEmbChunk * d4;
         int nchunk = -1, nntok = 0;
 #pragma unroll 1
         for (int q0 = 0; q0 < kEmbChunk; q0 += kEmbDepth) {
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(WIDE ? kEmbMaxCols + 32 : 256, WIDE ? 1 : 2) v
 #pragma unroll
                 for (int i = 0; i < kEmbDepth; ++i) {        // one revolution of the ring: slots are literals
                     const int q = q0 + i;
-                    if (q < ntok) consume(i, cur[q], dst + (size_t)q * d4);
+                    if (q < ntok) consume(i, cur[q]);
                     const int kk = q + kEmbDepth;
                     if (kk < kEmbChunk) {
                         if (kk < ntok) load(i, cur[kk]);
@@ -341,10 +347,12 @@ extern "C" int rdv_vt5_embed_tables_build(const float* d_x_emb, const float* d_y
 
 extern "C" int rdv_vt5_input_embeds_f32(const rdv_vt5_embed_tables* t, const int64_t* d_ids, const int64_t* d_boxes,
                                         const int64_t* d_labels, int32_t B, int32_t L, int64_t ld, float* d_out,
-                                        int32_t* d_bad, int32_t* d_work, void* stream) {
+                                        int64_t out_ld, int32_t* d_bad, int32_t* d_work, void* stream) {
     using namespace rdv;
     RDV_REQUIRE(t, RDV_E_INVALID, "vt5_input_embeds_f32: null tables");
-    RDV_REQUIRE(B >= 0 && L >= 0 && ld >= L, RDV_E_INVALID, "vt5_input_embeds_f32: B=%d, L=%d, ld=%lld", B, L, (long long)ld);
+    RDV_REQUIRE(B >= 0 && L >= 0 && ld >= L && out_ld >= L, RDV_E_INVALID, "vt5_input_embeds_f32: B=%d, L=%d, ld=%lld, out_ld=%lld", B, L,
+                (long long)ld, (long long)out_ld);
+    RDV_REQUIRE((int64_t)B * out_ld < (1ll << 31), RDV_E_LIMIT, "vt5_input_embeds_f32: %lld output rows", (long long)B * out_ld);
     RDV_REQUIRE(t->D >= 4 && t->D <= 1024 && (t->D & 3) == 0 && t->n_pos >= 1, RDV_E_INVALID,
                 "vt5_input_embeds_f32: D=%d must be a multiple of 4 in [4, 1024]", t->D);
     if ((int64_t)B * L == 0) return RDV_OK;
@@ -357,7 +365,7 @@ extern "C" int rdv_vt5_input_embeds_f32(const rdv_vt5_embed_tables* t, const int
                 (!d_ids || aligned16(t->shared)) && (!d_labels || aligned16(t->layout)), RDV_E_ALIGN,
                 "vt5_input_embeds_f32: boxes, out and the tables must be 16-byte aligned");
     EmbedParams p;
-    p.t = *t; p.ids = d_ids; p.boxes = d_boxes; p.labels = d_labels; p.B = B; p.L = L; p.ld = ld; p.out = d_out; p.bad = d_bad; p.work = d_work;
+    p.t = *t; p.ids = d_ids; p.boxes = d_boxes; p.labels = d_labels; p.B = B; p.L = L; p.ld = ld; p.out = d_out; p.out_ld = out_ld; p.bad = d_bad; p.work = d_work;
     const int d4 = t->D / 4;
     const int threads = (d4 + 31) / 32 * 32 + 32;           // one float4 column per consumer thread + the producer warp
     const size_t layout_bytes = d_labels ? (size_t)t->n_labels * t->D * 4 : 0;

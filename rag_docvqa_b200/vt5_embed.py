@@ -79,7 +79,7 @@ class SpatialEmbeddings:
         t.layout_scale = float(layout_scale)
         return t
 
-    def _launch(self, struct, ids, boxes, labels) -> torch.Tensor:
+    def _launch(self, struct, ids, boxes, labels, extra_rows: int = 0) -> torch.Tensor:
         _require_cuda(boxes, "boxes")
         if boxes.dim() != 3 or boxes.shape[2] != 4 or boxes.dtype != torch.int64:
             raise ValueError("boxes must be (B, L, 4) int64 (tensor_boxes of src/VT5.py:174), got %s %s" % (tuple(boxes.shape), boxes.dtype))
@@ -91,7 +91,8 @@ class SpatialEmbeddings:
             if not pitched or boxes.data_ptr() % 16:
                 boxes = boxes.contiguous()
             ld = boxes.stride(0) // 4 if B > 1 else L
-        out = torch.empty((B, L, self.D), dtype=torch.float32, device=boxes.device)
+        # extra_rows: room after every row's L tokens (the generator's visual tokens): the kernel writes with that row pitch
+        out = torch.empty((B, L + int(extra_rows), self.D), dtype=torch.float32, device=boxes.device)
 
         def rows(t, what):
             if t is None:
@@ -116,7 +117,8 @@ class SpatialEmbeddings:
                 work = self._work[stream] = torch.zeros((2,), dtype=torch.int32, device=self.device)
             _lib.check(_lib_fn.rdv_vt5_input_embeds_f32(
                 ctypes.byref(struct), 0 if ids_r is None else ids_r.data_ptr(), boxes.data_ptr(),
-                0 if lab_r is None else lab_r.data_ptr(), B, L, ld, out.data_ptr(), self.bad.data_ptr(), work.data_ptr(), stream))
+                0 if lab_r is None else lab_r.data_ptr(), B, L, ld, out.data_ptr(), L + int(extra_rows), self.bad.data_ptr(),
+                work.data_ptr(), stream))
         return out
 
     def forward(self, bbox: torch.Tensor) -> torch.Tensor:
@@ -138,7 +140,8 @@ class SpatialEmbeddings:
 class VT5InputEmbeddings:
     """semantic + spatial (+ layout * scale): the embedding sum of VT5.prepare_inputs_for_vqa (src/VT5.py:194-204), one
     launch over the gather's tensors.  The visual tokens the reference concatenates after it (:205) come from the
-    generator's own ViT and are not part of this path."""
+    generator's own ViT and are not computed here; `prepare_inputs` takes them and returns what the reference's
+    prepare_inputs_for_vqa returns, writing the text part straight into the concatenated buffer."""
 
     def __init__(self, spatial: SpatialEmbeddings, shared_weight: torch.Tensor, layout_weight: torch.Tensor = None,
                  layout_scale: float = 1.0):
@@ -166,6 +169,29 @@ class VT5InputEmbeddings:
             raise ValueError("layout labels given, but the model has no layout embedding (use_layout_labels != 'Embed')")
         _require_cuda(input_ids, "input_ids")
         return self.spatial._launch(self._plain if layout_labels is None else self._with_layout, input_ids, boxes, layout_labels)
+
+    def prepare_inputs(self, packed, visual_embedding: torch.Tensor = None, visual_mask: torch.Tensor = None):
+        """(input_embeds, attention_mask) of VT5.prepare_inputs_for_vqa (src/VT5.py:194-207) from the gather's PackedInputs
+        (docstore.PackedInputs: input_ids / boxes / attention_mask / layout_labels on the device) and the generator's
+        visual tokens (B, n_visual, hidden) + their mask (B, n_visual): the embedding kernel writes rows [0, longest) of the
+        (B, longest + n_visual, hidden) result directly, so the reference's torch.cat of the text part costs nothing."""
+        labels = packed.layout_labels if self._with_layout is not None else None
+        n_vis = 0 if visual_embedding is None else int(visual_embedding.shape[1])
+        if visual_embedding is not None:
+            _require_cuda(visual_embedding, "visual_embedding")
+            if visual_embedding.dim() != 3 or visual_embedding.shape[0] != packed.input_ids.shape[0] or visual_embedding.shape[2] != self.spatial.D:
+                raise ValueError("visual_embedding must be (B, n_visual, %d)" % self.spatial.D)
+        _require_cuda(packed.input_ids, "input_ids")
+        struct = self._plain if labels is None else self._with_layout
+        embeds = self.spatial._launch(struct, packed.input_ids, packed.boxes, labels, extra_rows=n_vis)
+        mask = packed.attention_mask
+        if n_vis:
+            L = int(packed.input_ids.shape[1])
+            embeds[:, L:].copy_(visual_embedding)
+            if visual_mask is None:
+                visual_mask = torch.ones(visual_embedding.shape[:2], dtype=mask.dtype, device=mask.device)
+            mask = torch.cat([mask, visual_mask.to(mask.dtype)], dim=1)
+        return embeds, mask
 
     def check(self) -> None:
         self.spatial.check()

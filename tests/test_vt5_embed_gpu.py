@@ -171,3 +171,16 @@ def test_after_the_gather_kernel():
     assert out.shape == (len(words), packed.longest, 96)
     ref = _oracle(w, 1e-12, packed.boxes.cpu(), packed.input_ids.cpu(), packed.layout_labels.cpu(), 0.5)
     np.testing.assert_allclose(out.cpu().double().numpy(), ref.numpy(), rtol=EMB_RTOL, atol=EMB_ATOL)
+    # prepare_inputs: the reference's return values (src/VT5.py:205-207), the text part written with the row pitch of the
+    # concatenated buffer -- bit-identical to the contiguous call, the visual tokens behind it, the masks concatenated
+    g = torch.Generator().manual_seed(6)
+    vis = torch.randn(len(words), 7, 96, generator=g).to(DEV)
+    vmask = torch.ones(len(words), 7, dtype=torch.int64, device=DEV)
+    vmask[0, 5:] = 0
+    embeds, mask = emb.prepare_inputs(packed, vis, vmask)
+    emb.check()
+    assert embeds.shape == (len(words), packed.longest + 7, 96)
+    assert torch.equal(embeds[:, :packed.longest], out) and torch.equal(embeds[:, packed.longest:], vis)
+    assert torch.equal(mask, torch.cat([packed.attention_mask, vmask], dim=1))
+    plain, mask0 = emb.prepare_inputs(packed)
+    assert torch.equal(plain, out) and torch.equal(mask0, packed.attention_mask)
