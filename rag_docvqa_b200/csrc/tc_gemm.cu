@@ -417,19 +417,26 @@ static int launch_n(const CUtensorMap& ma, const CUtensorMap& mb, const Params& 
     return RDV_OK;
 }
 
-// Which shape runs is a measured choice (B200, 1024 questions x 768-d bf16):
-//   short launches (1.25 M rows, 1.5 ms, clocks near max): pairs 1.29 vs 1.23 PFLOP/s; MaxSim 1.46 vs 1.43;
-//   sustained (10 M rows, 13 ms, `sw_power_cap` active):   pairs 72.2 k vs 80.6 k questions/s -- the pair kernel
-//   draws more power per clock (SM clocks settle at 1.19 vs 1.37 GHz), and under the 1 kW cap that decides.
-// So the single-CTA kernel is the default and RDV_TC_CTAS=2 in the environment selects CTA pairs (only when the
-// A tiles pair up: with an odd tile count the pair's second CTA would idle).
-static int tc_ctas(int n_a) {
+// Which shape runs is a measured choice (B200, 1024 questions x 768-d bf16; scripts/probe_c5_pairs.sh, round 2):
+//   rows per launch      1.25 M     2.5 M      5 M       10 M
+//   one CTA   (q/s)      631 k      323 k      154 k     78 k
+//   CTA pairs (q/s)      656 k      335 k      124 k     66 k
+// Pairs read a third less from L2 per tile (each CTA loads half of the B tile) and win by 4 % while the launch is short;
+// in launches that run long enough for the 1 kW power cap to bite they draw more power per clock and lose 15-20 %.
+// So: pairs for launches of up to ~3 M rows x 1024 questions x 768 (4.7 TFLOP; the per-rank share of the 10 M corpus at
+// N >= 4), the single-CTA kernel above that; RDV_TC_CTAS=1 / 2 in the environment forces either (pairs only when the A
+// tiles pair up: with an odd tile count the pair's second CTA would idle).
+static int tc_ctas(const Params& p) {
     const char* v = getenv("RDV_TC_CTAS");
-    return (v && v[0] == '2' && !(n_a & 1)) ? 2 : 1;
+    if (p.n_a & 1) return 1;
+    if (v && v[0] == '2') return 2;
+    if (v && v[0] == '1') return 1;
+    const double flops = 2.0 * (double)p.a_rows * (double)p.b_rows * 64.0 * (double)p.k_blocks;
+    return (p.mode == kCorpus && flops <= 4.7e12) ? 2 : 1;
 }
 
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
-    return tc_ctas(p.n_a) == 2 ? launch_n<2>(ma, mb, p, stream) : launch_n<1>(ma, mb, p, stream);
+    return tc_ctas(p) == 2 ? launch_n<2>(ma, mb, p, stream) : launch_n<1>(ma, mb, p, stream);
 }
 
 }  // namespace tc
@@ -500,7 +507,7 @@ extern "C" int rdv_corpus_score_topk_bf16(const void* d_e_bf16, const float* d_e
     CUtensorMap ma, mb;
     int rc = tc::make_map(&ma, d_q_bf16, d, n_questions, 1, tc::BM);
     if (rc) return rc;
-    rc = tc::make_map(&mb, d_e_bf16, d, n_rows, 1, tc::BN / tc::tc_ctas(p.n_a));
+    rc = tc::make_map(&mb, d_e_bf16, d, n_rows, 1, tc::BN / tc::tc_ctas(p));
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rc = tc::launch(ma, mb, p, s);
@@ -531,7 +538,7 @@ extern "C" int rdv_maxsim_bf16_tc(const void* d_qn_bf16, const void* d_pn_bf16, 
     CUtensorMap ma, mb;
     int rc = tc::make_map(&ma, d_qn_bf16, d, Lq, 1, tc::BM);
     if (rc) return rc;
-    rc = tc::make_map(&mb, d_pn_bf16, d, Lp, n, tc::BN / tc::tc_ctas(p.n_a));
+    rc = tc::make_map(&mb, d_pn_bf16, d, Lp, n, tc::BN / tc::tc_ctas(p));
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rc = tc::launch(ma, mb, p, s);
