@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(kPoolThreads, 4) mean_pool_kernel(const PoolPa
 // and after one cluster barrier the leader adds the S partial rows in rank order (deterministic), divides and normalises.
 // ---------------------------------------------------------------------------------------------------------------------
 // 1024 threads: with D = 768 that is five token groups per CTA, 960 threads x 8 independent 128-bit loads = 120 KB in
-// flight per SM (256 threads: one group, 24 KB in flight, 60 us for the 50 MB of 8 x 2048 x 768 questions).
+// flight per SM (256 threads: one group, 24 KB in flight, 60 us for the 50 MB of 8 x 2048 x 768 questions; 512 threads
+// with clusters of 16: 38 us; 1024: 32-36 us).
 constexpr int kSplitThreads = 1024;
 
 __device__ __forceinline__ uint32_t pool_cluster_rank() {
@@ -218,14 +219,16 @@ __global__ void __launch_bounds__(kSplitThreads) mean_pool_split_kernel(const Po
     for (int c = c0; c < d4; c += cols) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
-            int t = t_lo + g;
-            for (; t + (kPoolUnroll - 1) * G < t_hi; t += kPoolUnroll * G) {
+            // rounds of kPoolUnroll independent loads; the last round is bounds-checked per load instead of falling back to
+            // one dependent load at a time (a CTA's slice is ~26 tokens per group: the tail was a third of the work)
+            for (int t = t_lo + g; t < t_hi; t += kPoolUnroll * G) {
                 float m[kPoolUnroll];
                 float4 v[kPoolUnroll];
 #pragma unroll
                 for (int u = 0; u < kPoolUnroll; ++u) {
-                    m[u] = s_mask[t + u * G];
-                    if (m[u] != 0.f) v[u] = ldg_stream(base + (size_t)(t + u * G) * d4 + c);
+                    const int tu = t + u * G;
+                    m[u] = tu < t_hi ? s_mask[tu] : 0.f;
+                    if (m[u] != 0.f) v[u] = ldg_stream(base + (size_t)tu * d4 + c);
                 }
 #pragma unroll
                 for (int u = 0; u < kPoolUnroll; ++u) {
@@ -233,14 +236,6 @@ __global__ void __launch_bounds__(kSplitThreads) mean_pool_split_kernel(const Po
                         acc.x = fmaf(v[u].x, m[u], acc.x); acc.y = fmaf(v[u].y, m[u], acc.y);
                         acc.z = fmaf(v[u].z, m[u], acc.z); acc.w = fmaf(v[u].w, m[u], acc.w);
                     }
-                }
-            }
-            for (; t < t_hi; t += G) {
-                const float m = s_mask[t];
-                if (m != 0.f) {
-                    const float4 v = ldg_stream(base + (size_t)t * d4 + c);
-                    acc.x = fmaf(v.x, m, acc.x); acc.y = fmaf(v.y, m, acc.y);
-                    acc.z = fmaf(v.z, m, acc.z); acc.w = fmaf(v.w, m, acc.w);
                 }
             }
         }
@@ -322,6 +317,31 @@ static int pool_split(int n, int L, int d, size_t base_smem) {
     return S;
 }
 
+// Clusters of S CTAs of this kernel the device holds at once (cudaOccupancyMaxActiveClusters), remembered per device, S and d.
+static int split_clusters_resident(int S, int d, const cudaLaunchConfig_t& cfg) {
+    struct Entry { int dev, S, d, active; };
+    static Entry cache[16];
+    static std::atomic<int> used{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1 << 30;
+    const int n_used = used.load(std::memory_order_acquire);
+    for (int i = 0; i < n_used; ++i)
+        if (cache[i].dev == dev && cache[i].S == S && cache[i].d == d) return cache[i].active;
+    int active = 0;
+    if (cudaOccupancyMaxActiveClusters(&active, mean_pool_split_kernel, &cfg) != cudaSuccess || active <= 0) {
+        cudaGetLastError();
+        return 1 << 30;                                     // unknown: do not shrink the clusters on a guess
+    }
+    static std::atomic<int> claim{0};
+    const int slot = claim.fetch_add(1, std::memory_order_relaxed);
+    if (slot < 16) {
+        cache[slot] = {dev, S, d, active};
+        int expect = slot;                                  // publish in order; a racing reader simply asks the driver again
+        used.compare_exchange_strong(expect, slot + 1, std::memory_order_release);
+    }
+    return active;
+}
+
 }  // namespace rdv
 
 extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int32_t n, int32_t L, int32_t d,
@@ -348,21 +368,29 @@ extern "C" int rdv_mean_pool_f32(const float* d_embs, const int64_t* d_mask, int
                         "cudaFuncSetAttribute(mean_pool)");
     const int cols_s = d4 < kSplitThreads ? d4 : kSplitThreads;
     const int G_s = kSplitThreads / cols_s;
-    const int S = pool_split(n, L, d, (size_t)G_s * cols_s * sizeof(float4));
+    int S = pool_split(n, L, d, (size_t)G_s * cols_s * sizeof(float4));
     if (S > 1) {
         RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSplitSmem),
                             "cudaFuncSetAttribute(mean_pool_split)");
         RDV_ONCE_PER_DEVICE(cudaFuncSetAttribute(mean_pool_split_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
                             "cudaFuncSetAttribute(mean_pool_split, cluster)");
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)n * S);
-        cfg.blockDim = dim3(kSplitThreads);
-        cfg.dynamicSmemBytes = ((size_t)G_s * cols_s + (size_t)S * d4) * sizeof(float4);
-        cfg.stream = static_cast<cudaStream_t>(stream);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(kSplitThreads);
+        cfg.stream = static_cast<cudaStream_t>(stream);
         cfg.attrs = attr; cfg.numAttrs = 1;
+        const bool forced = getenv("RDV_POOL_SPLIT") != nullptr;
+        for (;; S /= 2) {
+            cfg.gridDim = dim3((unsigned)n * S);
+            cfg.dynamicSmemBytes = ((size_t)G_s * cols_s + (size_t)S * d4) * sizeof(float4);
+            attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            // all clusters resident at once: a B200 holds 7 clusters of 16 full-SM CTAs (ncu launch__cluster_max_active), so
+            // the 8th row of a C4p batch waited for a second wave (36 us); 8 clusters of 8 are one wave (32 us).  What is
+            // left is round latency: a CTA's slice is 3-4 rounds of 8 loads per thread (~2 us each) after a ~3 us mask pass
+            // and before a ~2 us hand-over -- a CTA streams at 24 GB/s, and only 64-128 of the 148 SMs have one
+            if (forced || S <= 2 || split_clusters_resident(S, d, cfg) >= n) break;
+        }
         cudaError_t e = cudaLaunchKernelEx(&cfg, mean_pool_split_kernel, p, S);
         if (e != cudaSuccess) return cuda_fail(e, "mean_pool_split_kernel");
         return RDV_OK;
