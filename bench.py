@@ -1096,7 +1096,7 @@ def corpus_leg(ctx, args, compact=False):
                         "rag_docvqa_b200.sharded.CorpusSearcher.search (pinned host questions in, (Q,k) scores + global ids out)")},
         "graph": searcher.graphed, "clocks": clocks.summary(),
         "limiter": ("N=1: tc_score_kernel (tensor pipe / 1 kW power cap)" if world == 1 else
-                    "tc_score_kernel %.3f of the %.3f ms step; all-gather + merges %.3f ms" % (ms_kernel, ms_per_step, ms_exchange)
+                    "tc_score_kernel %.3f ms alone (timed separately) against the %.3f ms step; all-gather + merges %.3f ms" % (ms_kernel, ms_per_step, ms_exchange)
                     if compact else
                     "tc_score_kernel %.3f ms of the %.3f ms step; the rest (%.3f ms) is the question cast, the two merges and "
                     "the all-gather (%.3f ms alone)" % (ms_kernel, ms_per_step, ms_per_step - ms_kernel, ms_exchange)),
