@@ -84,7 +84,8 @@ __device__ __forceinline__ void emb_mbar_wait(uint64_t* bar, uint32_t parity) {
 // token) 122 us; per-warp shared-memory rings filled by 1-D bulk copies (TMA) or by cp.async 67-77 us -- six warps per SM
 // spent ~460 instructions per token on addressing and issue, and the rings sat half empty; a thread per column with a
 // static split of the tokens and a __syncthreads per chunk 59 us (26 % of the stall samples at the barrier); this kernel
-// with the thread's ring in shared memory instead of registers (cp.async per thread, wait_group): 81 us.
+// with the thread's ring in shared memory instead of registers (cp.async per thread, wait_group): 81 us; coordinate rows
+// in registers + token rows in a cp.async ring + three blocks per SM (80 registers, spills): 103 us.
 // scripts/probe_embed_parts.py takes the 59 us apart: writing the output alone 17 us, the kernel with no row to load 28 us,
 // with every load a cache hit 44 us, coordinate rows from L2 +7 us, token rows from L2 / HBM +7 us.
 constexpr int kEmbSlots = 4;
