@@ -92,3 +92,29 @@ def test_ctypes_struct_layouts_match_the_header():
         assert _lib.lib.rdv_struct_size(name.encode()) == ctypes.sizeof(mirror), name
     assert _lib.lib.rdv_struct_size(b"rdv_chunk_rec") == 32 and _lib.lib.rdv_struct_size(b"rdv_tok_rec") == 32
     assert _lib.lib.rdv_struct_size(b"no_such_struct") == -1
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/rdv.h is what a cgo / JNI / N-API binding would include: it must compile as C99 (and as C++) on its own, and a
+    C program that calls through it must link against librdv.so and agree with the binding about the ABI version."""
+    import shutil
+    from rag_docvqa_b200 import _lib, build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    lib = build.build()
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "rdv.h"\n'
+                   'int main(void) { printf("%d %lld\\n", rdv_abi_version(), (long long)rdv_struct_size("rdv_gather_args")); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(lib)
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:librdv.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()
+    assert int(out[0]) == _lib.ABI_VERSION
+    assert int(out[1]) == ctypes.sizeof(_lib.GatherArgsStruct)
