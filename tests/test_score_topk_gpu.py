@@ -210,3 +210,33 @@ def test_c3_slice_32_documents_at_full_length():
     emb, q = synth.make_embeddings(sizes, 768, 41, dup_frac=0.01)
     res = run_case(emb, q, 10)
     check_against_oracle(res, emb, q, 10)
+
+
+@pytest.mark.parametrize("algo", [0] + ALGOS)
+def test_fuzz_shapes_against_the_oracle(algo):
+    """Forty batches nobody chose (fixed seeds): 1-12 documents of 0-1500 rows, d in {4 .. 1024} (multiples of 4), k in 1 .. 32,
+    duplicated rows (exact ties), zero rows, rows scaled by 1e-20 / 1e20, a zero question -- every path must agree with the
+    oracle on the scores and, on its own scores, on the order."""
+    rng = np.random.RandomState(4242)
+    for case in range(40):
+        B = int(rng.randint(1, 13))
+        d = 4 * int(rng.choice([1, 2, 8, 24, 25, 48, 96, 160, 192, 256]))
+        if algo == TMA:                                       # the TMA-ring kernel exists for these widths only (rdv_score_plan says so)
+            d = int(rng.choice([128, 256, 384, 512, 768, 1024]))
+        k = int(rng.randint(1, 33))
+        g = torch.Generator().manual_seed(1000 + case)
+        emb = []
+        for b in range(B):
+            n = int(rng.choice([0, 1, 2, 7, 31, 33, 64, 300, 600, 1500], p=[.08, .08, .08, .1, .1, .1, .1, .16, .1, .1]))
+            e = torch.randn(n, d, generator=g)
+            if n > 3:
+                e[n // 2] = e[0]                                  # exact duplicate: lowest index first
+                e[n - 1] = 0.0                                    # zero row: score exactly 0
+                e[1] *= 1e-20
+                e[2] *= 1e20
+            emb.append(e)
+        q = torch.randn(B, d, generator=g)
+        if B > 2:
+            q[2] = 0.0
+        res = run_case(emb, q, k, algo=algo)
+        check_against_oracle(res, emb, q, k)
