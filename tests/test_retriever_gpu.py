@@ -359,3 +359,38 @@ def test_resident_embedding_cache():
         got = tiny.retrieve(emb, q, *lists)
         assert got[0] == want2[0]
     assert tiny._cache.bytes <= 0.05 * (1 << 20)
+
+
+def test_packed_inputs_fuzz():
+    """Sixteen seeded combinations nobody chose of k, neighbour window, chunk reordering, separator, truncation length and
+    store construction: the packed ids / boxes / mask / labels must equal the oracle's flatten + VT5 packing bit for bit."""
+    from rag_docvqa_b200.docstore import DocStore
+    from rag_docvqa_b200.retriever import Retriever
+    rng = np.random.RandomState(99)
+    for case in range(16):
+        k = int(rng.randint(1, 9))
+        s = int(rng.choice([0, 0, 1, 4, 50]))
+        reorder, sep, derived = bool(rng.randint(2)), bool(rng.randint(2)), bool(rng.randint(2))
+        max_len = int(rng.choice([24, 65, 200, 512]))
+        batch = synth.make_text_batch("C2", with_lists=True, docs=int(rng.randint(2, 7)), seed=300 + case, dup_frac=0.05)
+        words, boxes, labels = batch["words_text_chunks"], batch["words_box_chunks"], batch["layout_labels_chunks"]
+        pages, images = batch["page_indices"], batch["images"]
+        table = synth.make_tokens_for_words(words, seed=case)
+        tok = lambda w, _t=table: _t.get(w, [2])
+        store = DocStore.from_lists(words, boxes, labels, pages, tok, torch.device(DEV), images=images, derived=derived)
+        prompts = prompts_for(["what is item %d about ?" % b for b in range(len(words))])
+        sep_ids = [2, 9] if sep else []
+        retr = Retriever({**BASE, "chunk_num": k, "include_surroundings": s, "reorder_chunks": reorder})
+        packed, res = retr.retrieve_packed([e.to(DEV) for e in batch["text_embeddings"]], batch["question_embeddings"].to(DEV),
+                                           store, prompts, sep_ids=sep_ids, max_source_length=max_len, with_layout_labels=True)
+        hits = Retriever._hits_to_host(res.topk_idx, res.topk_cnt)
+        ref = R.gather_hits(hits, words, boxes, labels, images, pages, include_surroundings=s, reorder_chunks=reorder, crop=False)
+        sep_word = "<sep>" if sep else None
+        tok_ref = lambda w, _s=sep_ids, _t=tok: _s if w == "<sep>" else _t(w)
+        ids, bxs, mask, labs = R.vt5_pack(prompts, [R.flatten(x, sep_word) for x in ref[3]], [R.flatten(x, sep_word) for x in ref[4]],
+                                          tok_ref, layout_labels=[R.flatten(x, sep_word) for x in ref[5]], max_source_length=max_len)
+        what = "case %d: k=%d s=%d reorder=%s sep=%s max_len=%d derived=%s" % (case, k, s, reorder, sep, max_len, derived)
+        assert torch.equal(packed.input_ids.cpu(), ids), what
+        assert torch.equal(packed.boxes.cpu(), bxs), what
+        assert torch.equal(packed.attention_mask.cpu(), mask), what
+        assert torch.equal(packed.layout_labels.cpu(), labs), what
