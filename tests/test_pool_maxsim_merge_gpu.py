@@ -270,3 +270,45 @@ def test_mean_pooling_row_split_over_a_cluster(monkeypatch, split, n, L, d):
     assert torch.equal(bf.cpu(), got.cpu().to(torch.bfloat16))
     gotn = F.mean_pooling(e, m, normalise=True)
     torch.testing.assert_close(gotn.cpu(), torch.nn.functional.normalize(ref, dim=1), rtol=2e-5, atol=2e-6)
+
+
+def test_pooled_patch_fuzz():
+    """Twelve seeded batches nobody chose: 1-6 documents of 0-9 strips, L in {1, 3, 17, 64, 300}, k and k_strips from 1 to
+    12 (above and below L and the strip count), a padded question mask, duplicated patches (exact ties) -- against the
+    oracle's composition of the reference's functions."""
+    from rag_docvqa_b200 import functional as F
+    rng = np.random.RandomState(31)
+    for case in range(12):
+        B = int(rng.randint(1, 7))
+        L = int(rng.choice([1, 3, 17, 64, 300]))
+        d = 4 * int(rng.choice([2, 24, 96, 192]))
+        k, ks = int(rng.randint(1, 13)), int(rng.randint(1, 13))
+        Lq = int(rng.randint(1, 40))
+        g = torch.Generator().manual_seed(500 + case)
+        u = torch.randn(d, generator=g)
+        patches = [torch.randn(int(rng.randint(0, 10)), L, d, generator=g) + 0.5 * u for _ in range(B)]
+        for p in patches:
+            if p.shape[0] >= 2 and L >= 2:
+                p[1, L - 1] = p[0, 0]                             # an exact tie across strips: lowest index first
+        q = torch.randn(B, Lq, d, generator=g) + 0.5 * u
+        mask = (torch.rand(B, Lq, generator=g) < 0.7).to(torch.int64)
+        mask[:, 0] = 1
+        sims, strips, pooled = R.pooled_patch_scores(patches, q, mask)
+        res = F.pooled_patch_topk([p.to(DEV) for p in patches], q.to(DEV), k, question_mask=mask.to(DEV), k_strips=ks)
+        torch.cuda.synchronize()
+        p_idx, p_cnt = res.patch_idx.cpu().numpy(), res.patch_cnt.cpu().numpy()
+        s_idx, s_cnt = res.strip_idx.cpu().numpy(), res.strip_cnt.cpu().numpy()
+        for b in range(B):
+            what = "case %d doc %d (L=%d k=%d ks=%d)" % (case, b, L, k, ks)
+            ref, own = sims[b].numpy(), res.similarities[b].cpu().numpy()
+            compare.assert_scores_close(own, ref, what=what)
+            kb = min(k, len(ref))
+            assert p_cnt[b] == kb and (p_idx[b, kb:] == -1).all(), what
+            compare.assert_topk_matches(p_idx[b, :kb], own, ref, k, what=what)
+            n = patches[b].shape[0]
+            sown = res.strip_scores[b].cpu().numpy()
+            if n:
+                np.testing.assert_array_equal(sown, own.reshape(n, -1).max(axis=1))
+            kb = min(ks, n)
+            assert s_cnt[b] == kb and (s_idx[b, kb:] == -1).all(), what
+            compare.assert_topk_matches(s_idx[b, :kb], sown, strips[b].numpy(), ks, what=what)
